@@ -1,0 +1,179 @@
+/*
+ * vqb200.h — C-ABI of the B200-native codebook-quantization hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch
+ * types.  The reference (magic-research/vector_quantization) is 100 % Python and
+ * has no FFI of its own; every entry point below replaces the ATen/cuBLAS call
+ * sequence of one reference function, cited as file:line relative to the
+ * reference root.  The Python host layer (`vector_quantization_b200/`) binds these
+ * with ctypes; `INTEGRATION.md` shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream);
+ *  - the caller allocates everything (outputs and workspaces); nothing is
+ *    allocated, freed or synchronised inside the library;
+ *  - return value: 0 on success, negative `vqb_status` on error; the message is
+ *    available from `vqb_last_error()` (thread-local);
+ *  - dtype codes: `VQB_F32` / `VQB_BF16`; all reductions and statistics are fp32;
+ *  - there is NO CPU implementation behind any entry point.
+ */
+#ifndef VQB200_H_
+#define VQB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB200_ABI_VERSION 1
+
+typedef enum { VQB_OK = 0, VQB_ERR_ARG = -1, VQB_ERR_CUDA = -2, VQB_ERR_UNSUPPORTED = -3 } vqb_status;
+typedef enum { VQB_F32 = 0, VQB_BF16 = 1 } vqb_dtype;
+typedef enum { VQB_BACKEND_TCGEN05 = 0, VQB_BACKEND_SIMT = 1 } vqb_backend;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int vqb_abi_version(void);
+const char* vqb_last_error(void);
+/* Fills SM count / compute capability of the current device. */
+int vqb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- operand packing -------------------------------------------------------------------- *
+ * The distance contraction runs on bf16 tensor cores with fp32 accumulation.  An fp32 matrix
+ * is represented EXACTLY as a sum of up to three bf16 "planes" (hi + mid + lo, 3 x 8 mantissa
+ * bits); a bf16 matrix is one plane.  `vqb_pack_rows` builds the zero-padded K-major operand
+ * buffer  bf16[planes][rows_pad][Dp]  that the TMA descriptors of `vqb_assign` read, and the
+ * per-row fp32 side terms.  It also performs the reference's row normalisation:
+ *   F.normalize(v) = v / max(||v||, 1e-12)      vq/algorithms/vq/callbacks/normalize.py:24,27
+ *                                               vq/algorithms/vq/distances.py:41-42
+ * Dp       = vqb_operand_dp(D)        (16, 32 or a multiple of 64)
+ * rows_pad = vqb_operand_rows_pad(rows) (multiple of 256)
+ */
+int64_t vqb_operand_dp(int D);
+int64_t vqb_operand_rows_pad(int64_t rows);
+size_t vqb_operand_bytes(int64_t rows, int D, int planes);
+int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D,
+                  int normalize,            /* 1: pack F.normalize(row) instead of row */
+                  int planes,               /* 1..3 bf16 planes */
+                  void* dst_planes,         /* bf16 [planes][rows_pad][Dp], fully written (padding zeroed) */
+                  float* half_sqnorm,       /* optional [rows_pad]: 0.5*||packed row||^2 (fp32); +inf in padding */
+                  float* writeback_f32,     /* optional [rows, D]: the (normalised) fp32 row; may alias src when src is fp32 */
+                  unsigned long long* keys_to_reset, int64_t n_keys, /* optional: fill with 0xFF.. (fused memset for vqb_assign) */
+                  void* stream);
+
+/* ---- nearest-code assignment ------------------------------------------------------------ *
+ * Replaces VectorQuantizer._encode = distance + argmin      vq/algorithms/vq/quantizers.py:92-100
+ *   L2Distance  torch.cdist                                 vq/algorithms/vq/distances.py:28-32
+ *   CosineDistance 1 - normalize(x) normalize(e)^T          vq/algorithms/vq/distances.py:35-46
+ * and, with the operands swapped, NearestAnchor's column argmin `d.argmin(0)`
+ *                                                           vq/algorithms/cvqvae/anchors.py:83
+ * WITHOUT materialising the [a_rows x b_rows] matrix.  For every row i of A it finds
+ *      argmax_j  score(i,j) = <A_i, B_j> - half_sqnorm_b[j]        (half_sqnorm_b == NULL -> 0)
+ * which is argmin_j ||A_i - B_j|| (L2) or argmin_j (1 - cos) when B rows are normalised.
+ * Ties resolve to the lowest j (torch.argmin semantics).  The result is min-combined into
+ *      keys[i] = (~orderable(score) << 32) | (uint32)(j + b_index_offset)
+ * with 64-bit atomicMin, so several launches (codebook shards) and several GPUs (packed
+ * min-loc all-reduce) compose.  keys must be initialised to all-ones.
+ * backend VQB_BACKEND_TCGEN05: TMA -> smem -> tcgen05.mma (TMEM accumulators) -> fused argmax
+ * epilogue; VQB_BACKEND_SIMT: fp32 CUDA-core kernel with the same contract (cross-check).
+ */
+int vqb_assign(const void* a_planes, int a_nplanes, int64_t a_rows,
+               const void* b_planes, int b_nplanes, int64_t b_rows,
+               int D, const float* b_half_sqnorm, int64_t b_index_offset,
+               unsigned long long* keys, int backend, void* stream);
+
+/* keys -> int64 indices (and optional fp32 scores); `index_offset` is subtracted. */
+int vqb_unpack_keys(const unsigned long long* keys, int64_t n, int64_t index_offset,
+                    int64_t* index_out, float* score_out, void* stream);
+/* Flip bit 63 so signed-int64 MIN (NCCL/gloo ReduceOp.MIN on torch.int64) orders like unsigned. */
+int vqb_keys_flip_sign(unsigned long long* keys, int64_t n, void* stream);
+
+/* ---- codebook gather + straight-through + loss reduction -------------------------------- *
+ * Replaces  nn.Embedding gather          vq/algorithms/vq/quantizers.py:102-108
+ *           ste: x + (z - x).detach()    vq/tasks/image_tokenization/models/quantizers/utils/ste.py:9-10
+ *           CodebookLoss/CommitmentLoss  vq/algorithms/vq/losses.py:41-62 (todd MSELoss, mean; norm=True
+ *                                        normalises both arguments first)
+ * One pass.  mse4_out = { mean((z-x)^2) [codebook role], same [commitment role],
+ *                         mean((n(z)-n(x))^2) [codebook role], same [commitment role] }
+ * (the two roles have equal value and different gradient routing).  The reduction is a
+ * deterministic two-stage sum: `partials` needs vqb_loss_partials_count() floats x 2 and
+ * `ticket` one zero-initialised uint32 (self-resetting).
+ */
+int64_t vqb_loss_partials_count(void);
+int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D,
+                        const float* W, int64_t K,
+                        const int64_t* quant,          /* [N] */
+                        void* z_ste_out, int out_dtype, /* [N,D] value x + (W[q] - x) */
+                        int want_norm_mse,
+                        float* mse4_out, float* partials, unsigned int* ticket, void* stream);
+
+/* Backward of the above (closed form):
+ *   gx = g_zste + g4[1]*2(x-z)/(ND) + J_n(x)^T [ g4[3]*2(n(x)-n(z))/(ND) ]
+ *   gW[q] += g4[0]*2(z-x)/(ND) + J_n(z)^T [ g4[2]*2(n(z)-n(x))/(ND) ]     (fp32 atomics; gW pre-zeroed or NULL)
+ * g4 is a DEVICE pointer to the 4 upstream loss gradients. */
+int vqb_quantize_backward(const void* g_zste, int g_dtype, const void* x, int x_dtype,
+                          const float* W, int64_t K, const int64_t* quant, int64_t N, int D,
+                          const float* g4, int want_norm_mse,
+                          void* gx_out, int gx_dtype, float* gW_accum, void* stream);
+
+/* ---- row l2-normalisation (NormalizeCallback.before_encode on x) ------------------------ *
+ * vq/algorithms/vq/callbacks/normalize.py:24  — forward y = x / max(||x||, 1e-12); backward
+ * gx = (gy - (gy.y) y) / max(||x||, 1e-12). */
+int vqb_l2norm_forward(const void* x, int x_dtype, int64_t rows, int D, void* y, int y_dtype, void* stream);
+int vqb_l2norm_backward(const void* gy, int g_dtype, const void* x, int x_dtype, int64_t rows, int D,
+                        void* gx, int gx_dtype, void* stream);
+
+/* ---- usage / EMA statistics -------------------------------------------------------------- *
+ * Replaces QuantStatistics.bin_count                vq/algorithms/vq/utils.py:40-43
+ *          VQKDCallback._kmeans scatter_add_        vq/algorithms/vqkd/quantizers/callbacks.py:60-62
+ * stats = fp32 [K*D sums | K counts] in ONE buffer (one all-reduce), pre-zeroed by the caller.
+ * normalize_x: accumulate F.normalize(x) rows (callbacks.py:124). */
+int vqb_scatter_stats(const void* x, int x_dtype, int64_t N, int D, int normalize_x,
+                      const int64_t* quant, float* stats, int64_t K, void* stream);
+/* int64 histogram accumulate — CodebookMixin.forward, vq/tasks/image_tokenization/runners/metrics.py:37-45 */
+int vqb_bincount_accumulate(const int64_t* quant, int64_t n, int64_t* counts, int64_t K, void* stream);
+
+/* VQKDCallback._kmeans tail + after_encode:  callbacks.py:66-71,126-128,73-75
+ *   C = cnt>0 ? S/max(cnt,1) : E ;  W <- normalize( E*decay + normalize(C)*(1-decay) )   (in place) */
+int vqb_kmeans_ema_update(const float* stats, float* W, int64_t K, int D, float decay, float one_minus_decay,
+                          void* stream);
+
+/* rows_out[k] = x[idx(keys[k])]  (fp32)  — NearestAnchor `x[indices]`, cvqvae/anchors.py:84.
+ * Keys whose index falls outside [index_offset, index_offset+N) produce zero rows (their owner
+ * rank supplies them; the caller sums over ranks). */
+int vqb_gather_rows_by_key(const void* x, int x_dtype, int64_t N, int D,
+                           const unsigned long long* keys, int64_t K, int64_t index_offset,
+                           float* rows_out, void* stream);
+
+/* CVQVAECallback.after_encode tail:  vq/algorithms/cvqvae/quantizer_callback.py:93-103
+ *   p <- p*decay + (cnt/total)*(1-decay)
+ *   dec = 1 - exp(-p*K*10/(1-decay) - eps) ;  W <- W*dec + anchors*anchor_scale*(1-dec)   (in place)
+ * counts = fp32 [K] (all-reduced), total = all-reduced token count. */
+int vqb_cvq_update(float* W, const float* anchors, float anchor_scale, float* prob, const float* counts,
+                   float total, int64_t K, int D, float decay, float one_minus_decay, float eps, void* stream);
+
+/* ---- finite scalar quantisation ---------------------------------------------------------- *
+ * FiniteScalarQuantizer._encode / _decode           vq/algorithms/fsq/quantizers.py:108-137
+ * Per-channel constants are computed by the host exactly as torch computes them and passed by
+ * value: max_[d], odd[d], shift[d] = atanh(odd/max_), half[d] = L//2, cumprod[d], levels[d]. D <= 16. */
+typedef struct {
+  int D;
+  float max_[16];
+  float odd[16];
+  float shift[16];
+  float half[16];
+  int cumprod[16];
+  int levels[16];
+} vqb_fsq_params;
+int vqb_fsq_forward(const void* x, int x_dtype, int64_t N, const vqb_fsq_params* p_host,
+                    void* zq_out, int out_dtype, int32_t* index_out, void* stream);
+int vqb_fsq_backward(const void* gz, int g_dtype, const void* x, int x_dtype, int64_t N,
+                     const vqb_fsq_params* p_host, void* gx, int gx_dtype, void* stream);
+int vqb_fsq_decode(const int32_t* index, int64_t N, const vqb_fsq_params* p_host, float* z_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQB200_H_ */

@@ -1,0 +1,268 @@
+"""GPU parity tests of the C-ABI kernels against the CPU oracle (`oracle/oracle.py`).
+Everything here calls libvqb200.so through ctypes (`vector_quantization_b200.ops`)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+from vector_quantization_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+IDX_EPS = 1e-5  # accepted near-tie: oracle distance gap of a differing index, relative to max(1, d)
+
+
+def _check_indices(d_oracle, q_oracle, q_test, eps=IDX_EPS, what=''):
+    rows, gap = O.index_mismatch_report(d_oracle, q_oracle, q_test)
+    if rows.numel():
+        scale = d_oracle[rows, q_oracle[rows]].abs().clamp_min(1.0)
+        bad = gap > eps * scale
+        assert not bad.any(), (f'{what}: {int(bad.sum())} index mismatches beyond the near-tie epsilon '
+                               f'(max gap {float(gap.max()):.3e}, of {rows.numel()} differing rows)')
+    return rows.numel()
+
+
+def _assign(x, E, metric, dev, backend, planes_x=None, planes_e=None, normalize_e=None):
+    """row arg-min of the reference distance through vqb_pack_rows + vqb_assign."""
+    cos = metric == 'Cosine'
+    xe = x.to(dev)
+    Ee = E.to(dev)
+    a = ops.pack_rows(xe, normalize=False, planes=planes_x)
+    b = ops.pack_rows(Ee, normalize=cos if normalize_e is None else normalize_e, planes=planes_e,
+                      want_half_sqnorm=not cos)
+    keys = ops.new_keys(x.shape[0], dev)
+    ops.assign(a, b, keys, l2=not cos, backend=backend)
+    return ops.unpack_keys(keys, want_score=True)
+
+
+# --------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize('rows,D,normalize,planes,dtype', [
+    (1000, 32, False, 3, torch.float32), (513, 8, True, 3, torch.float32), (300, 256, True, 2, torch.float32),
+    (777, 32, False, 1, torch.bfloat16), (64, 5, False, 3, torch.float32), (130, 768, True, 3, torch.bfloat16)])
+def test_pack_rows(dev, rows, D, normalize, planes, dtype):
+    g = torch.Generator().manual_seed(1)
+    src = torch.randn(rows, D, generator=g).to(dtype)
+    wb = torch.empty(rows, D, dtype=torch.float32, device=dev)
+    op = ops.pack_rows(src.to(dev), normalize=normalize, planes=planes, want_half_sqnorm=True, writeback=wb)
+    ref = F.normalize(src.float()) if normalize else src.float()
+    rows_pad, Dp = ops.operand_shape(rows, D)
+    assert op.planes.shape == (planes, rows_pad, Dp)
+    recon = op.planes.float().sum(0).cpu()
+    tol = {1: 2 ** -8, 2: 2 ** -16, 3: 1e-7}[planes] if not (dtype == torch.bfloat16 and not normalize) else 0.0
+    assert torch.allclose(recon[:rows, :D], ref, rtol=tol, atol=1e-7 if tol else 0.0)
+    assert (recon[rows:] == 0).all() and (recon[:, D:] == 0).all()
+    torch.testing.assert_close(wb.cpu(), ref, rtol=2e-6, atol=1e-7)
+    h = op.half_sqnorm.cpu()
+    torch.testing.assert_close(h[:rows], 0.5 * (ref * ref).sum(1), rtol=1e-5, atol=1e-7)
+    assert torch.isinf(h[rows:]).all()
+    if planes == 3:  # the three planes reproduce the fp32 value bit for bit
+        assert torch.equal(recon[:rows, :D], wb.cpu())
+
+
+@pytest.mark.parametrize('backend', [ops.BACKEND_SIMT, ops.BACKEND_TCGEN05], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('metric', ['L2', 'Cosine'])
+@pytest.mark.parametrize('N,K,D', [(1000, 700, 32), (2048, 1024, 8), (384, 512, 256), (300, 333, 64), (257, 4100, 20),
+                                   (128, 256, 768)])
+def test_assign_fp32_parity(dev, backend, metric, N, K, D):
+    x, E = O.synthetic_latents(N, K, D, seed=3407 + N + D)
+    q_ref, d = O.encode(metric, x, E)
+    q, score = _assign(x, E, metric, dev, backend)
+    n_diff = _check_indices(d, q_ref, q.cpu(), what=f'{metric} {N}x{K}x{D}')
+    assert n_diff <= max(2, N // 200)
+    # the kernel's score is <x, e> - 0.5|e|^2 (L2) or <x, e/|e|> (cosine)
+    Ef = F.normalize(E) if metric == 'Cosine' else E
+    s_ref = (x * Ef[q.cpu()]).sum(1) - (0.5 * (Ef[q.cpu()] ** 2).sum(1) if metric == 'L2' else 0)
+    torch.testing.assert_close(score.cpu(), s_ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('backend', [ops.BACKEND_SIMT, ops.BACKEND_TCGEN05], ids=['simt', 'tcgen05'])
+def test_assign_bf16_tokens_exact_operands(dev, backend):
+    """bf16 tokens are ONE exact plane; the fp32 codebook is three: products are exact, so the only
+    difference from the fp32 oracle on the up-cast inputs is fp32 accumulation order."""
+    N, K, D = 4096, 2048, 32
+    x, E = O.synthetic_latents(N, K, D, normalized_codebook=True)
+    xb = x.to(torch.bfloat16)
+    q_ref, d = O.encode('Cosine', xb.float(), E)
+    q, _ = _assign(xb, E, 'Cosine', dev, backend)
+    _check_indices(d, q_ref, q.cpu(), what='bf16 tokens')
+
+
+def test_assign_tie_break_lowest_index(dev):
+    """Exact ties resolve to the lowest index, like torch.argmin (duplicate codebook rows)."""
+    N, D = 512, 32
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(300, D, generator=g).to(torch.bfloat16).float()
+    E = torch.cat([base, base, base])            # every code appears three times: 300-periodic ties
+    x = base[torch.randint(0, 300, (N,), generator=g)] + 0.01 * torch.randn(N, D, generator=g)
+    x = x.to(torch.bfloat16)
+    for backend in (ops.BACKEND_SIMT, ops.BACKEND_TCGEN05):
+        q, _ = _assign(x, E, 'L2', dev, backend)
+        assert int(q.max()) < 300, 'a duplicate with a higher index won a tie'
+        q_ref, d = O.encode('L2', x.float(), E)
+        _check_indices(d, q_ref, q.cpu(), what='ties')
+
+
+def test_assign_column_argmin_swapped_operands(dev):
+    """NearestAnchor's d.argmin(0) == the same kernel with codes as rows and tokens as columns."""
+    N, K, D = 3000, 640, 32
+    x, E = O.synthetic_latents(N, K, D, seed=11)
+    for metric in ('L2', 'Cosine'):
+        _, d = O.encode(metric, x, E)
+        idx_ref = d.argmin(0)
+        cos = metric == 'Cosine'
+        codes = ops.pack_rows(E.to(dev), normalize=cos)
+        toks = ops.pack_rows(x.to(dev), normalize=cos, want_half_sqnorm=not cos)
+        keys = ops.new_keys(K, dev)
+        ops.assign(codes, toks, keys, l2=not cos)
+        idx = ops.unpack_keys(keys).cpu()
+        _check_indices(d.t().contiguous(), idx_ref, idx, what=f'column argmin {metric}')
+
+
+def test_assign_sharded_codebook_min_combine(dev):
+    """Two launches over two codebook shards min-combine into the same keys as one launch."""
+    N, K, D = 2000, 1024, 32
+    x, E = O.synthetic_latents(N, K, D, seed=21)
+    q_ref, d = O.encode('L2', x, E)
+    a = ops.pack_rows(x.to(dev))
+    keys = ops.new_keys(N, dev)
+    for r in range(2):
+        b = ops.pack_rows(E[r * 512:(r + 1) * 512].to(dev), want_half_sqnorm=True)
+        ops.assign(a, b, keys, l2=True, index_offset=r * 512)
+    _check_indices(d, q_ref, ops.unpack_keys(keys).cpu(), what='sharded')
+
+
+# --------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('N,K,D,norm', [(1000, 64, 32, False), (777, 100, 256, True), (4096, 512, 8, True),
+                                        (333, 50, 20, False)])
+def test_gather_ste_loss_and_backward(dev, dtype, N, K, D, norm):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(N, D, generator=g).to(dtype)
+    W = torch.randn(K, D, generator=g)
+    q = torch.randint(0, K, (N,), generator=g)
+    gz = torch.randn(N, D, generator=g)
+    g4 = torch.tensor([0.7, -1.3, 0.4, 2.0])
+    if not norm:
+        g4[2:] = 0
+    # oracle (fp32 on up-cast inputs), autograd for the gradients
+    xo = x.float().clone().requires_grad_(True)
+    Wo = W.clone().requires_grad_(True)
+    z = O.decode(Wo, q)
+    cb, cm = O.codebook_loss(z, xo), O.commitment_loss(z, xo)
+    cbn, cmn = O.codebook_loss(z, xo, True), O.commitment_loss(z, xo, True)
+    z_ste = O.ste(z, xo)
+    total = (z_ste * gz).sum() + g4[0] * cb + g4[1] * cm + g4[2] * cbn + g4[3] * cmn
+    total.backward()
+
+    xd, Wd, qd = x.to(dev), W.to(dev), q.to(dev)
+    z_k, mse4 = ops.gather_ste_loss(xd, Wd, qd, want_norm=norm)
+    assert torch.equal(z_k.cpu(), z_ste.detach()), 'z_ste must be bit-exact: x + (W[q] - x)'
+    ref4 = torch.stack([cb, cm, cbn, cmn]).detach()
+    if not norm:
+        ref4[2:] = mse4.cpu()[2:]
+    torch.testing.assert_close(mse4.cpu(), ref4, rtol=1e-5, atol=1e-8)
+    # deterministic reduction: a second launch returns the same bits
+    _, mse4b = ops.gather_ste_loss(xd, Wd, qd, want_norm=norm)
+    assert torch.equal(mse4, mse4b)
+
+    gx, gW = ops.quantize_backward(gz.to(dev), xd, Wd, qd, g4.to(dev), want_norm=norm, need_gW=True)
+    tol = dict(rtol=1e-4, atol=1e-6) if dtype == torch.float32 else dict(rtol=2 ** -7, atol=1e-3)
+    torch.testing.assert_close(gx.float().cpu(), xo.grad, **tol)
+    torch.testing.assert_close(gW.cpu(), Wo.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('N,D', [(1000, 32), (77, 8), (300, 256), (65, 768), (10, 5)])
+def test_l2norm(dev, dtype, N, D):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, D, generator=g).to(dtype)
+    x[0] = 0  # eps-clamped row
+    xo = x.float().clone().requires_grad_(True)
+    y = F.normalize(xo)
+    gy = torch.randn(N, D, generator=g)
+    y.backward(gy)
+    yk = ops.l2norm_forward(x.to(dev))
+    torch.testing.assert_close(yk.cpu(), y.detach(), rtol=2e-6, atol=1e-7)
+    gx = ops.l2norm_backward(gy.to(dev), x.to(dev))
+    tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=2 ** -7, atol=1e-2)
+    torch.testing.assert_close(gx.float().cpu()[1:], xo.grad[1:], **tol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('N,K,D,normalize,hot', [(5000, 300, 32, True, False), (4096, 64, 8, False, True),
+                                                 (1000, 128, 256, True, False), (999, 50, 20, False, True),
+                                                 (3000, 16, 768, True, True)])
+def test_scatter_stats_and_kmeans_update(dev, dtype, N, K, D, normalize, hot):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, D, generator=g).to(dtype)
+    q = torch.randint(0, K // 2 if hot else K, (N,), generator=g)  # hot: half the codebook unused
+    if hot:
+        q[: N // 2] = 3  # long runs of the same code exercise the warp-aggregated path
+    W = F.normalize(torch.randn(K, D, generator=g))
+    xs = F.normalize(x.float()) if normalize else x.float()
+    sums = torch.zeros(K, D).index_add_(0, q, xs)
+    cnt = q.bincount(minlength=K)
+    stats = ops.scatter_stats(x.to(dev), q.to(dev), K, normalize_x=normalize)
+    assert torch.equal(stats[K * D:].cpu(), cnt.float()), 'counts are exact'
+    torch.testing.assert_close(stats[:K * D].view(K, D).cpu(), sums, rtol=1e-4, atol=2e-5)
+    counts = torch.zeros(K, dtype=torch.int64, device=dev)
+    ops.bincount_accumulate(q.to(dev), counts)
+    ops.bincount_accumulate(q.to(dev), counts)
+    assert torch.equal(counts.cpu(), 2 * cnt)
+    if normalize:  # the VQ-KD update on top of these statistics
+        W_ref = O.vqkd_update([x.float()], [q], W, 0.99)
+        Wd = W.to(dev).clone()
+        ops.kmeans_ema_update(stats, Wd, 0.99)
+        torch.testing.assert_close(Wd.cpu(), W_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_cvq_update(dev):
+    N, K, D = 3000, 256, 32
+    x, E = O.synthetic_latents(N, K, D, seed=5)
+    q, d = O.encode('Cosine', x, E)
+    prob = torch.rand(K, generator=torch.Generator().manual_seed(2)) / K
+    W_ref, p_ref, anchors_ref, idx_ref = O.cvq_update([x], [d], [q], E, prob, 0.99, 1e-3, False)
+    xd = x.to(dev)
+    codes = ops.pack_rows(E.to(dev), normalize=True)
+    toks = ops.pack_rows(xd, normalize=True)
+    keys = ops.new_keys(K, dev)
+    ops.assign(codes, toks, keys, l2=False)
+    _check_indices(d.t().contiguous(), idx_ref, ops.unpack_keys(keys).cpu(), what='anchor index')
+    anchors = ops.gather_rows_by_key(xd, keys)
+    same = ops.unpack_keys(keys).cpu() == idx_ref
+    assert torch.equal(anchors.cpu()[same], anchors_ref[same])
+    Wd, pd = E.to(dev).clone(), prob.to(dev).clone()
+    counts = q.bincount(minlength=K).float().to(dev)
+    ops.cvq_update(Wd, anchors_ref.to(dev), pd, counts, float(N), decay=0.99, eps=1e-3)
+    torch.testing.assert_close(pd.cpu(), p_ref, rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(Wd.cpu(), W_ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('levels', [[8, 8, 5, 5, 5], [8, 8, 8, 5, 5, 5], [7, 5, 5, 5, 5], [4, 3]])
+@pytest.mark.parametrize('N', [1, 255, 24576])
+def test_fsq(dev, levels, N):
+    fsq = O.FSQ(levels)
+    g = torch.Generator().manual_seed(N)
+    x = 1.5 * torch.randn(N, len(levels), generator=g)
+    xo = x.clone().requires_grad_(True)
+    quant, zq, pre = fsq.encode(xo)
+    gz = torch.randn(N, len(levels), generator=g)
+    zq.backward(gz)
+    p = ops.fsq_params(levels, 1e-3)
+    zk, ik = ops.fsq_forward(x.to(dev), p)
+    # round-half-even boundary: tanhf differs from the CPU tanh by an ulp or two
+    safe = ((pre.detach() - pre.detach().floor() - 0.5).abs() > 1e-5).all(1)
+    assert safe.float().mean() > 0.99
+    assert torch.equal(ik.cpu()[safe], quant[safe])
+    assert torch.equal(zk.cpu()[safe], zq.detach()[safe])
+    assert ik.dtype == torch.int32 and int(ik.max()) < fsq.codebook_size and int(ik.min()) >= 0
+    gx = ops.fsq_backward(gz.to(dev), x.to(dev), p)
+    torch.testing.assert_close(gx.cpu(), xo.grad, rtol=1e-4, atol=1e-7)
+    # decode-only path inverts the index packing exactly
+    zd = ops.fsq_decode(ik, p)
+    assert torch.equal(zd.cpu(), fsq.decode(ik.cpu().long()).float())
+    assert torch.equal(zd, zk)

@@ -1,0 +1,103 @@
+// Shared helpers for the vqb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vqb200.h"
+
+namespace vqb {
+
+void set_error(const char* fmt, ...);
+
+#define VQB_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::vqb::set_error(__VA_ARGS__);      \
+      return VQB_ERR_ARG;                 \
+    }                                     \
+  } while (0)
+
+#define VQB_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::vqb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return VQB_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define VQB_LAUNCH_OK() VQB_CUDA_OK(cudaGetLastError())
+
+constexpr float kNormEps = 1e-12f;  // F.normalize default eps
+
+__host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- dtype-generic row element access -------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- packed (score, index) keys ----------------------------------------------------------
+// orderable(): monotone map fp32 -> uint32 (larger float => larger uint).
+__host__ __device__ __forceinline__ uint32_t orderable(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float from_orderable(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+// Smaller key == better (higher score, then lower index).
+__host__ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t index) {
+  return (static_cast<unsigned long long>(~orderable(score)) << 32) | index;
+}
+__host__ __device__ __forceinline__ uint32_t key_index(unsigned long long k) { return static_cast<uint32_t>(k); }
+__host__ __device__ __forceinline__ float key_score(unsigned long long k) {
+  return from_orderable(~static_cast<uint32_t>(k >> 32));
+}
+
+// ---- warp helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int W>
+__device__ __forceinline__ float group_sum(float v) {  // sum over aligned groups of W lanes
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace vqb

@@ -1,0 +1,242 @@
+// Operand packing (fp32/bf16 rows -> exact bf16 planes for the tcgen05 contraction) and the
+// row l2-normalisation forward/backward.  All HBM-bound, one pass, sub-warp group per row.
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vqb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// lanes per row: each lane handles ~4 elements, rows of a warp stay sector-aligned.
+static inline int lanes_per_row(int D) {
+  int g = 1;
+  while (g < 32 && g * 4 < D) g <<= 1;
+  return g;
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(256) pack_rows_kernel(
+    const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
+    __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
+    unsigned long long* __restrict__ keys, int64_t n_keys) {
+  // fused memset of the assignment keys
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_keys;
+       i += (int64_t)gridDim.x * blockDim.x)
+    keys[i] = ~0ull;
+
+  const int lane = threadIdx.x % G;
+  const int64_t rows_per_block = blockDim.x / G;
+  for (int64_t r = blockIdx.x * rows_per_block + threadIdx.x / G; r < rows_pad;
+       r += (int64_t)gridDim.x * rows_per_block) {
+    const bool real = r < rows;
+    float ss = 0.f;
+    if (real)
+      for (int d = lane; d < D; d += G) {
+        float v = to_f32<T>(src[r * D + d]);
+        ss = fmaf(v, v, ss);
+      }
+    ss = group_sum<G>(ss);
+    const float denom = normalize ? fmaxf(sqrtf(ss), kNormEps) : 1.f;
+    float ss2 = 0.f;
+    for (int d = lane; d < Dp; d += G) {
+      float v = 0.f;
+      if (real && d < D) {
+        v = to_f32<T>(src[r * D + d]);
+        if (normalize) v = __fdiv_rn(v, denom);
+        if (writeback) writeback[r * D + d] = v;
+      }
+      ss2 = fmaf(v, v, ss2);
+      // exact 3-way split: v == hi + mid + lo
+      float rem = v;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        if (p < planes) {
+          __nv_bfloat16 h = __float2bfloat16_rn(rem);
+          dst[((int64_t)p * rows_pad + r) * Dp + d] = h;
+          rem = rem - __bfloat162float(h);
+        }
+      }
+    }
+    if (half_sqnorm) {
+      ss2 = group_sum<G>(ss2);
+      if (lane == 0) half_sqnorm[r] = real ? 0.5f * ss2 : INFINITY;
+    }
+  }
+}
+
+template <typename TI, typename TO, int G>
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const TI* __restrict__ x, int64_t rows, int D,
+                                                         TO* __restrict__ y) {
+  const int lane = threadIdx.x % G;
+  const int64_t rows_per_block = blockDim.x / G;
+  for (int64_t base = blockIdx.x * rows_per_block; base < rows; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t r = base + threadIdx.x / G;  // warp-uniform trip count: shuffles below need every lane
+    const bool valid = r < rows;
+    float ss = 0.f;
+    if (valid)
+      for (int d = lane; d < D; d += G) {
+        float v = to_f32<TI>(x[r * D + d]);
+        ss = fmaf(v, v, ss);
+      }
+    ss = group_sum<G>(ss);
+    const float denom = fmaxf(sqrtf(ss), kNormEps);
+    if (valid)
+      for (int d = lane; d < D; d += G) y[r * D + d] = from_f32<TO>(__fdiv_rn(to_f32<TI>(x[r * D + d]), denom));
+  }
+}
+
+// gx = (gy - (gy . y) y) / denom with y = x / denom   (exact Jacobian of F.normalize away from the eps clamp;
+// when ||x|| < eps the forward is x/eps and the Jacobian is I/eps)
+template <typename TG, typename TI, typename TO, int G>
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const TG* __restrict__ gy, const TI* __restrict__ x,
+                                                         int64_t rows, int D, TO* __restrict__ gx) {
+  const int lane = threadIdx.x % G;
+  const int64_t rows_per_block = blockDim.x / G;
+  for (int64_t base = blockIdx.x * rows_per_block; base < rows; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t r = base + threadIdx.x / G;
+    const bool valid = r < rows;
+    float ss = 0.f, gd = 0.f;
+    for (int d = lane; valid && d < D; d += G) {
+      float v = to_f32<TI>(x[r * D + d]);
+      float g = to_f32<TG>(gy[r * D + d]);
+      ss = fmaf(v, v, ss);
+      gd = fmaf(g, v, gd);
+    }
+    ss = group_sum<G>(ss);
+    gd = group_sum<G>(gd);
+    const float nrm = sqrtf(ss);
+    const bool clamped = nrm < kNormEps;
+    const float denom = fmaxf(nrm, kNormEps);
+    const float inv = 1.f / denom;
+    const float proj = clamped ? 0.f : gd * inv * inv;  // (g . y)/denom, y = x*inv
+    for (int d = lane; valid && d < D; d += G) {
+      float v = to_f32<TI>(x[r * D + d]);
+      float g = to_f32<TG>(gy[r * D + d]);
+      gx[r * D + d] = from_f32<TO>((g - proj * v * inv) * inv);
+    }
+  }
+}
+
+template <int G, typename F>
+static inline void launch_rows(int64_t rows, F&& f) {
+  const int rows_per_block = 256 / G;
+  int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  f((int)blocks);
+}
+
+#define VQB_DISPATCH_G(G_, ...)                  \
+  switch (G_) {                                  \
+    case 1: { constexpr int G = 1; __VA_ARGS__; } break;   \
+    case 2: { constexpr int G = 2; __VA_ARGS__; } break;   \
+    case 4: { constexpr int G = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int G = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int G = 16; __VA_ARGS__; } break; \
+    default: { constexpr int G = 32; __VA_ARGS__; } break; \
+  }
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" {
+
+int vqb_abi_version(void) { return VQB200_ABI_VERSION; }
+const char* vqb_last_error(void) { return g_err; }
+
+int vqb_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  VQB_CUDA_OK(cudaGetDevice(&dev));
+  if (sm) VQB_CUDA_OK(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, dev));
+  if (major) VQB_CUDA_OK(cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (minor) VQB_CUDA_OK(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return VQB_OK;
+}
+
+int64_t vqb_operand_dp(int D) {
+  if (D <= 16) return 16;
+  if (D <= 32) return 32;
+  return round_up(D, 64);
+}
+int64_t vqb_operand_rows_pad(int64_t rows) { return round_up(rows < 1 ? 1 : rows, 256); }
+size_t vqb_operand_bytes(int64_t rows, int D, int planes) {
+  return (size_t)planes * (size_t)vqb_operand_rows_pad(rows) * (size_t)vqb_operand_dp(D) * 2;
+}
+
+int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes,
+                  void* dst_planes, float* half_sqnorm, float* writeback, unsigned long long* keys,
+                  int64_t n_keys, void* stream) {
+  VQB_REQUIRE(src && dst_planes, "vqb_pack_rows: null pointer");
+  VQB_REQUIRE(rows >= 0 && D >= 1 && D <= 8192, "vqb_pack_rows: bad shape rows=%lld D=%d", (long long)rows, D);
+  VQB_REQUIRE(planes >= 1 && planes <= 3, "vqb_pack_rows: planes must be 1..3 (got %d)", planes);
+  VQB_REQUIRE(src_dtype == VQB_F32 || src_dtype == VQB_BF16, "vqb_pack_rows: bad dtype %d", src_dtype);
+  const int64_t rows_pad = vqb_operand_rows_pad(rows);
+  const int Dp = (int)vqb_operand_dp(D);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = lanes_per_row(Dp);
+  VQB_DISPATCH_G(g, launch_rows<G>(rows_pad, [&](int blocks) {
+    if (src_dtype == VQB_F32)
+      pack_rows_kernel<float, G><<<blocks, 256, 0, st>>>((const float*)src, rows, rows_pad, D, Dp, normalize,
+                                                          planes, (__nv_bfloat16*)dst_planes, half_sqnorm,
+                                                          writeback, keys, keys ? n_keys : 0);
+    else
+      pack_rows_kernel<__nv_bfloat16, G><<<blocks, 256, 0, st>>>(
+          (const __nv_bfloat16*)src, rows, rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes,
+          half_sqnorm, writeback, keys, keys ? n_keys : 0);
+  }));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_l2norm_forward(const void* x, int x_dtype, int64_t rows, int D, void* y, int y_dtype, void* stream) {
+  VQB_REQUIRE(x && y, "vqb_l2norm_forward: null pointer");
+  VQB_REQUIRE(rows >= 0 && D >= 1, "vqb_l2norm_forward: bad shape");
+  if (rows == 0) return VQB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = lanes_per_row(D);
+  VQB_DISPATCH_G(g, launch_rows<G>(rows, [&](int blocks) {
+    if (x_dtype == VQB_F32 && y_dtype == VQB_F32)
+      l2norm_fwd_kernel<float, float, G><<<blocks, 256, 0, st>>>((const float*)x, rows, D, (float*)y);
+    else if (x_dtype == VQB_BF16 && y_dtype == VQB_F32)
+      l2norm_fwd_kernel<__nv_bfloat16, float, G><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, D, (float*)y);
+    else if (x_dtype == VQB_BF16 && y_dtype == VQB_BF16)
+      l2norm_fwd_kernel<__nv_bfloat16, __nv_bfloat16, G><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, D, (__nv_bfloat16*)y);
+    else
+      l2norm_fwd_kernel<float, __nv_bfloat16, G><<<blocks, 256, 0, st>>>((const float*)x, rows, D, (__nv_bfloat16*)y);
+  }));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_l2norm_backward(const void* gy, int g_dtype, const void* x, int x_dtype, int64_t rows, int D, void* gx,
+                        int gx_dtype, void* stream) {
+  VQB_REQUIRE(gy && x && gx, "vqb_l2norm_backward: null pointer");
+  VQB_REQUIRE(g_dtype == VQB_F32, "vqb_l2norm_backward: upstream gradient must be fp32");
+  if (rows == 0) return VQB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = lanes_per_row(D);
+  VQB_DISPATCH_G(g, launch_rows<G>(rows, [&](int blocks) {
+    if (x_dtype == VQB_F32 && gx_dtype == VQB_F32)
+      l2norm_bwd_kernel<float, float, float, G><<<blocks, 256, 0, st>>>((const float*)gy, (const float*)x, rows, D, (float*)gx);
+    else if (x_dtype == VQB_BF16 && gx_dtype == VQB_BF16)
+      l2norm_bwd_kernel<float, __nv_bfloat16, __nv_bfloat16, G><<<blocks, 256, 0, st>>>((const float*)gy, (const __nv_bfloat16*)x, rows, D, (__nv_bfloat16*)gx);
+    else if (x_dtype == VQB_BF16 && gx_dtype == VQB_F32)
+      l2norm_bwd_kernel<float, __nv_bfloat16, float, G><<<blocks, 256, 0, st>>>((const float*)gy, (const __nv_bfloat16*)x, rows, D, (float*)gx);
+    else
+      l2norm_bwd_kernel<float, float, __nv_bfloat16, G><<<blocks, 256, 0, st>>>((const float*)gy, (const float*)x, rows, D, (__nv_bfloat16*)gx);
+  }));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+}  // extern "C"

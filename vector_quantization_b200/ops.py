@@ -1,0 +1,294 @@
+"""Tensor-level wrappers over the C-ABI (`include/vqb200.h`).
+
+PyTorch is used only as the owner of device memory and of the current CUDA stream: every function
+here passes raw device pointers + sizes + the stream handle to `libvqb200.so`.  All inputs must be
+CUDA tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, VQB_BF16, VQB_F32, FSQParams, check
+
+__all__ = [
+    'Operand', 'pack_rows', 'assign', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
+    'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
+    'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'fsq_params', 'fsq_forward', 'fsq_backward',
+    'fsq_decode', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
+]
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return VQB_F32
+    if t.dtype == torch.bfloat16:
+        return VQB_BF16
+    raise TypeError(f'vector_quantization_b200 supports float32 and bfloat16 tensors, got {t.dtype}')
+
+
+def _cuda(*ts: torch.Tensor | None) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.VQBError('vector_quantization_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
+        if not t.is_contiguous():
+            raise ValueError('expected a contiguous tensor')
+
+
+def _p(t: torch.Tensor | None):
+    return c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class Operand:
+    """A packed K-major bf16 operand: planes [P, rows_pad, Dp] + optional fp32 0.5*||row||^2."""
+    planes: torch.Tensor
+    rows: int
+    dim: int
+    nplanes: int
+    half_sqnorm: torch.Tensor | None = None
+
+
+def operand_shape(rows: int, D: int) -> tuple[int, int]:
+    lib = _lib.load()
+    return int(lib.vqb_operand_rows_pad(rows)), int(lib.vqb_operand_dp(D))
+
+
+def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None = None,
+              want_half_sqnorm: bool = False, writeback: torch.Tensor | None = None,
+              reset_keys: torch.Tensor | None = None) -> Operand:
+    """fp32/bf16 rows -> exact bf16 planes (see vqb_pack_rows).  `planes=None` picks the exact
+    representation: 1 plane for un-normalised bf16 input, 3 planes otherwise."""
+    lib = _lib.load()
+    _cuda(src, writeback, reset_keys)
+    assert src.dim() == 2
+    rows, D = src.shape
+    if planes is None:
+        planes = 1 if (src.dtype == torch.bfloat16 and not normalize) else 3
+    rows_pad, Dp = operand_shape(rows, D)
+    dst = torch.empty((planes, rows_pad, Dp), dtype=torch.bfloat16, device=src.device)
+    h = torch.empty((rows_pad,), dtype=torch.float32, device=src.device) if want_half_sqnorm else None
+    if writeback is not None:
+        assert writeback.dtype == torch.float32 and writeback.shape == src.shape
+    check(lib.vqb_pack_rows(_p(src), _dt(src), rows, D, int(normalize), planes, _p(dst), _p(h), _p(writeback),
+                            _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _stream()),
+          'vqb_pack_rows')
+    return Operand(dst, rows, D, planes, h)
+
+
+def new_keys(n: int, device) -> torch.Tensor:
+    """All-ones packed keys (int64 storage of the uint64 keys)."""
+    return torch.full((n,), -1, dtype=torch.int64, device=device)
+
+
+def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset: int = 0,
+           backend: int = BACKEND_TCGEN05) -> torch.Tensor:
+    """keys[i] = min(keys[i], key(argmax_j <a_i,b_j> - (l2 ? 0.5||b_j||^2 : 0)))."""
+    lib = _lib.load()
+    _cuda(a.planes, b.planes, keys)
+    assert a.dim == b.dim and keys.dtype == torch.int64 and keys.numel() >= a.rows
+    h = None
+    if l2:
+        assert b.half_sqnorm is not None, 'L2 assignment needs the packed operand to carry half_sqnorm'
+        h = b.half_sqnorm
+    check(lib.vqb_assign(_p(a.planes), a.nplanes, a.rows, _p(b.planes), b.nplanes, b.rows, a.dim, _p(h),
+                         index_offset, _p(keys), backend, _stream()), 'vqb_assign')
+    return keys
+
+
+def unpack_keys(keys: torch.Tensor, index_offset: int = 0, want_score: bool = False):
+    lib = _lib.load()
+    _cuda(keys)
+    n = keys.numel()
+    idx = torch.empty((n,), dtype=torch.int64, device=keys.device)
+    score = torch.empty((n,), dtype=torch.float32, device=keys.device) if want_score else None
+    check(lib.vqb_unpack_keys(_p(keys), n, index_offset, _p(idx), _p(score), _stream()), 'vqb_unpack_keys')
+    return (idx, score) if want_score else idx
+
+
+def keys_flip_sign(keys: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(keys)
+    check(lib.vqb_keys_flip_sign(_p(keys), keys.numel(), _stream()), 'vqb_keys_flip_sign')
+    return keys
+
+
+_WS: dict = {}
+
+
+def _loss_ws(device):
+    key = (device.type, device.index)
+    if key not in _WS:
+        lib = _lib.load()
+        _WS[key] = (torch.empty((int(lib.vqb_loss_partials_count()),), dtype=torch.float32, device=device),
+                    torch.zeros((1,), dtype=torch.int32, device=device))
+    return _WS[key]
+
+
+def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor, *, want_norm: bool,
+                    out_dtype: torch.dtype = torch.float32):
+    """(z_ste [N,D], mse4 [4]) — see vqb_gather_ste_loss."""
+    lib = _lib.load()
+    _cuda(x, W, quant)
+    assert W.dtype == torch.float32 and quant.dtype == torch.int64
+    N, D = x.shape
+    z = torch.empty((N, D), dtype=out_dtype, device=x.device)
+    mse4 = torch.empty((4,), dtype=torch.float32, device=x.device)
+    partials, ticket = _loss_ws(x.device)
+    check(lib.vqb_gather_ste_loss(_p(x), _dt(x), N, D, _p(W), W.shape[0], _p(quant), _p(z), _dt(z),
+                                  int(want_norm), _p(mse4), _p(partials), _p(ticket), _stream()),
+          'vqb_gather_ste_loss')
+    return z, mse4
+
+
+def quantize_backward(g_z: torch.Tensor, x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor,
+                      g4: torch.Tensor, *, want_norm: bool, need_gW: bool):
+    lib = _lib.load()
+    _cuda(g_z, x, W, quant, g4)
+    N, D = x.shape
+    gx = torch.empty_like(x)
+    gW = torch.zeros_like(W) if need_gW else None
+    check(lib.vqb_quantize_backward(_p(g_z), _dt(g_z), _p(x), _dt(x), _p(W), W.shape[0], _p(quant), N, D, _p(g4),
+                                    int(want_norm), _p(gx), _dt(gx), _p(gW), _stream()), 'vqb_quantize_backward')
+    return gx, gW
+
+
+def l2norm_forward(x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(x)
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(lib.vqb_l2norm_forward(_p(x), _dt(x), x.shape[0], x.shape[1], _p(y), _dt(y), _stream()),
+          'vqb_l2norm_forward')
+    return y
+
+
+def l2norm_backward(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(gy, x)
+    gx = torch.empty_like(x)
+    check(lib.vqb_l2norm_backward(_p(gy), _dt(gy), _p(x), _dt(x), x.shape[0], x.shape[1], _p(gx), _dt(gx),
+                                  _stream()), 'vqb_l2norm_backward')
+    return gx
+
+
+def scatter_stats(x: torch.Tensor, quant: torch.Tensor, K: int, *, normalize_x: bool = False,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 [K*D + K] = per-code feature sums followed by per-code counts (one all-reduce buffer)."""
+    lib = _lib.load()
+    _cuda(x, quant, out)
+    N, D = x.shape
+    stats = out if out is not None else torch.zeros((K * D + K,), dtype=torch.float32, device=x.device)
+    check(lib.vqb_scatter_stats(_p(x), _dt(x), N, D, int(normalize_x), _p(quant), _p(stats), K, _stream()),
+          'vqb_scatter_stats')
+    return stats
+
+
+def bincount_accumulate(quant: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(quant, counts)
+    assert quant.dtype == torch.int64 and counts.dtype == torch.int64
+    check(lib.vqb_bincount_accumulate(_p(quant), quant.numel(), _p(counts), counts.numel(), _stream()),
+          'vqb_bincount_accumulate')
+    return counts
+
+
+def _f32(v: float) -> float:
+    return float(torch.tensor(v, dtype=torch.float32).item())
+
+
+def kmeans_ema_update(stats: torch.Tensor, W: torch.Tensor, decay: float) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(stats, W)
+    K, D = W.shape
+    check(lib.vqb_kmeans_ema_update(_p(stats), _p(W), K, D, _f32(decay), _f32(1 - decay), _stream()),
+          'vqb_kmeans_ema_update')
+    return W
+
+
+def gather_rows_by_key(x: torch.Tensor, keys: torch.Tensor, index_offset: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(x, keys)
+    N, D = x.shape
+    K = keys.numel()
+    out = torch.empty((K, D), dtype=torch.float32, device=x.device)
+    check(lib.vqb_gather_rows_by_key(_p(x), _dt(x), N, D, _p(keys), K, index_offset, _p(out), _stream()),
+          'vqb_gather_rows_by_key')
+    return out
+
+
+def cvq_update(W: torch.Tensor, anchors: torch.Tensor, prob: torch.Tensor, counts: torch.Tensor, total: float, *,
+               decay: float, eps: float, anchor_scale: float = 1.0) -> None:
+    lib = _lib.load()
+    _cuda(W, anchors, prob, counts)
+    K, D = W.shape
+    check(lib.vqb_cvq_update(_p(W), _p(anchors), anchor_scale, _p(prob), _p(counts), float(total), K, D,
+                             _f32(decay), _f32(1 - decay), _f32(eps), _stream()), 'vqb_cvq_update')
+
+
+# ---- FSQ -------------------------------------------------------------------------------------
+
+
+def fsq_params(levels, eps: float) -> FSQParams:
+    """Per-channel constants computed with torch on the host EXACTLY as the reference computes them
+    (vq/algorithms/fsq/quantizers.py:30,114-115,122), then handed to the kernels by value."""
+    levels = [int(v) for v in levels]
+    if not 1 <= len(levels) <= 16:
+        raise ValueError('FSQ supports 1..16 channels')
+    max_per_digit = torch.tensor(levels, dtype=torch.int)
+    cumprod = torch.tensor((1,) + tuple(levels[:-1])).cumprod(0)
+    max_int = max_per_digit - 1
+    max_ = max_int * (1 - eps)
+    odd = max_int % 2
+    shift = torch.atanh(odd / max_)
+    half = max_per_digit // 2
+    p = FSQParams()
+    p.D = len(levels)
+    for d in range(len(levels)):
+        p.max_[d] = float(max_[d])
+        p.odd[d] = float(odd[d])
+        p.shift[d] = float(shift[d])
+        p.half[d] = float(half[d])
+        p.cumprod[d] = int(cumprod[d])
+        p.levels[d] = levels[d]
+    return p
+
+
+def fsq_forward(x: torch.Tensor, p: FSQParams, out_dtype: torch.dtype | None = None):
+    lib = _lib.load()
+    _cuda(x)
+    N, D = x.shape
+    assert D == p.D
+    zq = torch.empty((N, D), dtype=out_dtype or x.dtype, device=x.device)
+    idx = torch.empty((N,), dtype=torch.int32, device=x.device)
+    check(lib.vqb_fsq_forward(_p(x), _dt(x), N, ctypes.byref(p), _p(zq), _dt(zq), _p(idx), _stream()),
+          'vqb_fsq_forward')
+    return zq, idx
+
+
+def fsq_backward(gz: torch.Tensor, x: torch.Tensor, p: FSQParams) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(gz, x)
+    gx = torch.empty_like(x)
+    check(lib.vqb_fsq_backward(_p(gz), _dt(gz), _p(x), _dt(x), x.shape[0], ctypes.byref(p), _p(gx), _dt(gx),
+                               _stream()), 'vqb_fsq_backward')
+    return gx
+
+
+def fsq_decode(index: torch.Tensor, p: FSQParams) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(index)
+    index = index.to(torch.int32) if index.dtype != torch.int32 else index
+    flat = index.reshape(-1).contiguous()
+    z = torch.empty((flat.numel(), p.D), dtype=torch.float32, device=index.device)
+    check(lib.vqb_fsq_decode(_p(flat), flat.numel(), ctypes.byref(p), _p(z), _stream()), 'vqb_fsq_decode')
+    return z.reshape(*index.shape, p.D)
