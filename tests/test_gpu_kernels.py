@@ -226,6 +226,7 @@ def test_cvq_update(dev):
     q, d = O.encode('Cosine', x, E)
     prob = torch.rand(K, generator=torch.Generator().manual_seed(2)) / K
     W_ref, p_ref, anchors_ref, idx_ref = O.cvq_update([x], [d], [q], E, prob, 0.99, 1e-3, False)
+    idx_ref = idx_ref[0]
     xd = x.to(dev)
     codes = ops.pack_rows(E.to(dev), normalize=True)
     toks = ops.pack_rows(xd, normalize=True)
@@ -261,8 +262,9 @@ def test_fsq(dev, levels, N):
     assert torch.equal(zk.cpu()[safe], zq.detach()[safe])
     assert ik.dtype == torch.int32 and int(ik.max()) < fsq.codebook_size and int(ik.min()) >= 0
     gx = ops.fsq_backward(gz.to(dev), x.to(dev), p)
-    torch.testing.assert_close(gx.cpu(), xo.grad, rtol=1e-4, atol=1e-7)
-    # decode-only path inverts the index packing exactly
+    torch.testing.assert_close(gx.cpu(), xo.grad, rtol=1e-4, atol=1e-6)
+    # decode-only path (digit / half - 1) == the reference's decode-only branch, bit for bit; it agrees with the
+    # encode path's r / half only up to fp32 rounding (e.g. 4/3 - 1 != 1/3), exactly as in the reference
     zd = ops.fsq_decode(ik, p)
     assert torch.equal(zd.cpu(), fsq.decode(ik.cpu().long()).float())
-    assert torch.equal(zd, zk)
+    torch.testing.assert_close(zd, zk, rtol=0, atol=2e-7)

@@ -116,11 +116,11 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const TG* __restrict__ 
     const bool clamped = nrm < kNormEps;
     const float denom = fmaxf(nrm, kNormEps);
     const float inv = 1.f / denom;
-    const float proj = clamped ? 0.f : gd * inv * inv;  // (g . y)/denom, y = x*inv
+    const float proj = clamped ? 0.f : gd * inv * inv;  // (g . y) y == (g . x) x / denom^2
     for (int d = lane; valid && d < D; d += G) {
       float v = to_f32<TI>(x[r * D + d]);
       float g = to_f32<TG>(gy[r * D + d]);
-      gx[r * D + d] = from_f32<TO>((g - proj * v * inv) * inv);
+      gx[r * D + d] = from_f32<TO>((g - proj * v) * inv);
     }
   }
 }
