@@ -1,0 +1,349 @@
+"""bench.py — quantized tokens/sec of the codebook-quantization hot path on N B200 GPUs.
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on): VQ-KD cosine quantizer,
+l2-normalised 8192 x 32 codebook, batch 256 x 256 = 65 536 bf16 tokens per GPU, forward + straight-through
+backward, driven through the drop-in module (`VQKDQuantizer.forward`, reference-style config).
+A "step" is one forward+backward of the quantizer over one batch of synthetic latents.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU implementation of the
+path (the oracle port, pinned bit-for-bit to the reference source) on the host cores.
+Only this file's cpu_baseline / `--impl reference` legs execute anything under oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+SEED = 3407  # reference default (vq/train.py:21)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    'cfg2': dict(name='cfg2: VQ-KD cosine quantizer fwd + straight-through bwd', N=65536, K=8192, D=32,
+                 metric='Cosine', training=False,
+                 config=dict(type='VQKDQuantizer', distance=dict(type='CosineDistance'),
+                             callbacks=[dict(type='VQKDCallback', ema=dict())],
+                             losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True)))),
+                 oracle=dict(distance='Cosine', callback='VQKDCallback',
+                             losses={'commitment_loss': dict(type='CommitmentLoss', norm=True)})),
+    # BASELINE.json configs[2]: LlamaGen-style 16384 x 8 l2-normalised codebook + EMA update + usage stats
+    'cfg3': dict(name='cfg3: l2-normalised 16384x8 codebook, k-means/EMA update + usage stats, fwd + bwd', N=65536,
+                 K=16384, D=8, metric='Cosine', training=True,
+                 config=dict(type='VQKDQuantizer', distance=dict(type='CosineDistance'),
+                             callbacks=[dict(type='VQKDCallback', ema=dict())],
+                             losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True)))),
+                 oracle=dict(distance='Cosine', callback='VQKDCallback',
+                             losses={'commitment_loss': dict(type='CommitmentLoss', norm=True)})),
+}
+
+
+def emb(K, D):
+    return dict(type='torch_nn_modules_sparse_Embedding', num_embeddings=K, embedding_dim=D)
+
+
+def synth(N, K, D, seed):
+    """Seeded synthetic latents: trained-like unit-norm codebook, clustered tokens."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    E = torch.nn.functional.normalize(torch.randn(K, D, generator=g))
+    pi = torch.randint(0, K, (N,), generator=g)
+    x = E[pi] + 0.5 * E.std() * torch.randn(N, D, generator=g)
+    gz = torch.randn(N, D, generator=g)
+    return x.to(torch.bfloat16), E, gz
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the GPU legs run."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self._h).gpu
+                self.samples.append((mhz, util))
+                get = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                    nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self._h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        busy = sorted(m for m, u in self.samples if u > 0) or sorted(m for m, _ in self.samples)
+        return dict(sm_mhz=busy[len(busy) // 2] if busy else None, sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    """The reference's CPU implementation of the path (oracle port) on the host cores, bounded sample."""
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    N, K, D = wl['N'], wl['K'], wl['D']
+    x, E, gz = synth(N, K, D, SEED)
+    spec = O.QuantizerSpec(training=wl['training'], **wl['oracle'])
+
+    def step():
+        xo = x.float().requires_grad_(True)
+        out = O.quantizer_forward(spec, [xo], E)
+        torch.autograd.backward((out['z_ste'][0], out['loss'][0]), (gz, torch.ones([])))
+        return out
+
+    for _ in range(min(args.warmup, 2)):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = N / dt
+    sample = f'full {wl["name"]} batch (N={N}) x {steps} steps, fp32, torch {torch.__version__} CPU'
+    return dict(value=value, ms=dt * 1e3, cores=threads, kind='port', sample=sample, steps=steps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying CUDA graphs')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    metric, unit = 'quantized tokens/sec', 'tokens/s'
+    base_cfg = dict(workload=wl['name'], tokens_per_gpu=wl['N'], codebook=f'{wl["K"]}x{wl["D"]} fp32 master',
+                    token_dtype='bf16', parallelism=f'token-sharded x{world}' if world > 1 else 'single GPU')
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        r = run_reference(args, wl)
+        print(json.dumps(dict(
+            metric=metric, value=r['value'], unit=unit, n_gpus=args.gpus, steps=r['steps'], warmup=min(args.warmup, 2),
+            ms_per_step=r['ms'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+            impl='reference', config=base_cfg,
+            cpu_baseline=dict(value=r['value'], unit=unit, cores=r['cores'], kind=r['kind'], sample=r['sample']),
+            e2e=dict(value=r['value'], unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+        return
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch.distributed as dist
+
+    import vector_quantization_b200 as vqb
+    from vector_quantization_b200 import ops
+
+    assert torch.cuda.is_available(), 'bench.py --impl b200 needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    N, K, D = wl['N'], wl['K'], wl['D']
+    cfg = dict(wl['config'], embedding=emb(K, D))
+    q = vqb.build_quantizer(cfg, training=wl['training']).to(dev)
+    q._forward_pre_hooks.clear()  # steady-state step (the one-off k-means init is not part of the metric)
+    x0, E, gz0 = synth(N, K, D, SEED + rank)
+    with torch.no_grad():
+        q.embedding.weight.copy_(synth(N, K, D, SEED)[1])  # identical codebook on every rank
+    # rotating input sets: 24 x (4 MB tokens + 8 MB upstream grad) = 288 MB > 2 x 126 MB L2
+    n_sets = 24
+    sets = []
+    for i in range(n_sets):
+        xi = x0.roll(i * 977, 0).to(dev).requires_grad_(True)
+        sets.append((xi, gz0.roll(i * 977, 0).to(dev)))
+    one = torch.ones([], device=dev)
+    result = {}
+
+    def step(i):
+        xi, gzi = sets[i % n_sets]
+        xi.grad = None
+        z, loss, memo = q(xi, dict())
+        torch.autograd.backward((z, loss), (gzi, one))
+        result.update(loss=loss, quant=memo['quant'], gx=xi.grad)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.LAUNCHES = 0
+    step(0)
+    launches_per_step = ops.LAUNCHES
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+
+    graphs = None
+    if not args.no_graph:
+        # one CUDA graph per input set: replaying graph i runs the whole step on set i with cold inputs
+        graphs, outs = [], []
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for i in range(n_sets):
+                step(i)
+        torch.cuda.current_stream().wait_stream(s)
+        pool = None
+        for i in range(n_sets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                step(i)
+                outs.append(dict(result))
+            pool = g.pool()
+            graphs.append(g)
+
+        def run(i):
+            graphs[i % n_sets].replay()
+            return outs[i % n_sets]
+    else:
+        def run(i):
+            step(i)
+            return result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        run(i)
+    # ---- timed region: exactly K steps ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    value = N * world / (ms * 1e-3)
+
+    # ---- dominant kernel (tcgen05 assignment) timed live with CUDA events on the launching stream ----
+    ops.PROFILE = []
+    prof_steps = min(args.steps, 50)
+    for i in range(prof_steps):
+        step(i)  # eager launches with event pairs around vqb_assign
+    torch.cuda.synchronize()
+    assign_ms = [a.elapsed_time(b) for name, a, b in ops.PROFILE if name == 'vqb_assign']
+    ops.PROFILE = None
+    assign_ms.sort()
+    assign_avg = sum(assign_ms) / len(assign_ms)
+    peaks = {}
+    try:
+        peaks = json.load(open(ROOT / 'MEASURED_PEAKS.json'))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)  # kernel timed inside a long step -> sustained figure
+    flops = 2.0 * N * K * D                              # algorithmic: contraction only, un-padded, one plane
+    achieved = flops / (assign_avg * 1e-3) / 1e12
+    roofline = dict(bound='tensor', kernel='assign_tc_kernel (tcgen05 distance GEMM + fused arg-min)',
+                    achieved=achieved, peak=peak_tf, unit='TFLOP/s', frac=achieved / peak_tf,
+                    peak_source='MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (B200_PROFILING.md)',
+                    kernel_ms=assign_avg, kernel_share_of_step=assign_avg / ms,
+                    epilogue_gelem_per_s=N * K / (assign_avg * 1e-3) / 1e9, traffic=None)
+
+    # ---- end-to-end: pinned host inputs -> device -> step -> results back to pinned host ----
+    xh = x0.pin_memory()
+    gh = gz0.pin_memory()
+    loss_h = torch.empty([], dtype=torch.float32).pin_memory()
+    quant_h = torch.empty(N, dtype=torch.int64).pin_memory()
+    gx_h = torch.empty(N, D, dtype=torch.bfloat16).pin_memory()
+
+    def e2e_step(i):
+        xi, gzi = sets[i % n_sets]
+        with torch.no_grad():
+            xi.copy_(xh, non_blocking=True)
+            gzi.copy_(gh, non_blocking=True)
+        out = run(i)
+        loss_h.copy_(out['loss'], non_blocking=True)
+        quant_h.copy_(out['quant'], non_blocking=True)
+        gx_h.copy_(out['gx'], non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    k2 = min(args.steps, 100)
+    e0.record()
+    for i in range(k2):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / k2
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t)
+    h2d = xh.numel() * 2 + gh.numel() * 4
+    d2h = 4 + quant_h.numel() * 8 + gx_h.numel() * 2
+    clocks = sampler.stop()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_reference(argparse.Namespace(steps=3, warmup=1), wl)
+        cpu_baseline = dict(value=r['value'], unit=unit, cores=r['cores'], kind=r['kind'], sample=r['sample'])
+
+    if rank == 0:
+        print(json.dumps(dict(
+            metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
+            dtype='bf16 (bf16 tokens/operands, fp32 accumulate; fp32 codebook as exact bf16x3 planes)',
+            data='synthetic',
+            config=dict(base_cfg, l2_policy=f'rotating {n_sets} input sets, {n_sets * (N * D * 6) >> 20} MB > L2',
+                        launch='CUDA graph replay' if graphs else 'eager', kernels_per_step=launches_per_step),
+            clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline,
+            e2e=dict(value=N * world / (e2e_ms * 1e-3), unit=unit, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
+                     d2h_bytes_per_step=d2h),
+            gpu_launches=launches_per_step * args.steps)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

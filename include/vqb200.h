@@ -109,6 +109,11 @@ int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D,
                         int want_norm_mse,
                         float* mse4_out, float* partials, unsigned int* ticket, void* stream);
 
+/* Plain codebook gather out[i] = W[quant[i]] (fp32) — VectorQuantizer._decode on its own, as used by
+ * decode_from_quant (vq/tasks/image_reconstruction/models.py:97-108); any index shape, flattened. */
+int vqb_embedding_gather(const float* W, int64_t K, int D, const int64_t* quant, int64_t n, float* out,
+                         void* stream);
+
 /* Backward of the above (closed form):
  *   gx = g_zste + g4[1]*2(x-z)/(ND) + J_n(x)^T [ g4[3]*2(n(x)-n(z))/(ND) ]
  *   gW[q] += g4[0]*2(z-x)/(ND) + J_n(z)^T [ g4[2]*2(n(z)-n(x))/(ND) ]     (fp32 atomics; gW pre-zeroed or NULL)
@@ -133,7 +138,9 @@ int vqb_l2norm_backward(const void* gy, int g_dtype, const void* x, int x_dtype,
 int vqb_scatter_stats(const void* x, int x_dtype, int64_t N, int D, int normalize_x,
                       const int64_t* quant, float* stats, int64_t K, void* stream);
 /* int64 histogram accumulate — CodebookMixin.forward, vq/tasks/image_tokenization/runners/metrics.py:37-45 */
-int vqb_bincount_accumulate(const int64_t* quant, int64_t n, int64_t* counts, int64_t K, void* stream);
+int vqb_bincount_accumulate(const int64_t* quant, int64_t n, int64_t* counts, int64_t K,
+                            int add_total, /* 1: counts[K] += n (numel slot of the fused [K | 1] all-reduce buffer) */
+                            void* stream);
 
 /* VQKDCallback._kmeans tail + after_encode:  callbacks.py:66-71,126-128,73-75
  *   C = cnt>0 ? S/max(cnt,1) : E ;  W <- normalize( E*decay + normalize(C)*(1-decay) )   (in place) */
@@ -150,9 +157,11 @@ int vqb_gather_rows_by_key(const void* x, int x_dtype, int64_t N, int D,
 /* CVQVAECallback.after_encode tail:  vq/algorithms/cvqvae/quantizer_callback.py:93-103
  *   p <- p*decay + (cnt/total)*(1-decay)
  *   dec = 1 - exp(-p*K*10/(1-decay) - eps) ;  W <- W*dec + anchors*anchor_scale*(1-dec)   (in place)
- * counts = fp32 [K] (all-reduced), total = all-reduced token count. */
-int vqb_cvq_update(float* W, const float* anchors, float anchor_scale, float* prob, const float* counts,
-                   float total, int64_t K, int D, float decay, float one_minus_decay, float eps, void* stream);
+ * counts = int64 [K] (all-reduced bincount), total = DEVICE pointer to the all-reduced int64 token count
+ * (QuantStatistics.frequency, vq/algorithms/vq/utils.py:48-52: int64 / int64 -> fp32). */
+int vqb_cvq_update(float* W, const float* anchors, float anchor_scale, float* prob, const int64_t* counts,
+                   const int64_t* total, int64_t K, int D, float decay, float one_minus_decay, float eps,
+                   void* stream);
 
 /* ---- finite scalar quantisation ---------------------------------------------------------- *
  * FiniteScalarQuantizer._encode / _decode           vq/algorithms/fsq/quantizers.py:108-137

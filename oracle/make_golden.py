@@ -121,7 +121,7 @@ def run_case(name, ref_cfg, spec, N, K, D, normalized, steps, training):
         records.append(rec)
         W = W_after.clone()
         prob = rec['prob_after']
-    return dict(name=name, spec=spec.__dict__, N=N, K=K, D=D, steps=records,
+    return dict(name=name, config=cfg, training=training, spec=spec.__dict__, N=N, K=K, D=D, steps=records,
                 state_dict_keys=list(q.state_dict().keys()))
 
 

@@ -237,8 +237,9 @@ def test_cvq_update(dev):
     same = ops.unpack_keys(keys).cpu() == idx_ref
     assert torch.equal(anchors.cpu()[same], anchors_ref[same])
     Wd, pd = E.to(dev).clone(), prob.to(dev).clone()
-    counts = q.bincount(minlength=K).float().to(dev)
-    ops.cvq_update(Wd, anchors_ref.to(dev), pd, counts, float(N), decay=0.99, eps=1e-3)
+    counts = q.bincount(minlength=K).to(dev)
+    ops.cvq_update(Wd, anchors_ref.to(dev), pd, counts, torch.tensor([N], device=dev), decay=0.99, eps=1e-3)
+    assert torch.equal(ops.embedding_gather(E.to(dev), q.to(dev).view(30, 100)).cpu(), E[q].view(30, 100, D))
     torch.testing.assert_close(pd.cpu(), p_ref, rtol=1e-6, atol=1e-9)
     torch.testing.assert_close(Wd.cpu(), W_ref, rtol=1e-5, atol=1e-6)
 

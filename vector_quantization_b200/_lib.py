@@ -53,12 +53,13 @@ SIGNATURES = {
     'vqb_l2norm_forward': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p]),
     'vqb_l2norm_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p]),
     'vqb_scatter_stats': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
-    'vqb_bincount_accumulate': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    'vqb_bincount_accumulate': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     'vqb_kmeans_ema_update': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p]),
     'vqb_gather_rows_by_key': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int64, c_int64, c_void_p,
                                        c_void_p]),
-    'vqb_cvq_update': (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int64, c_int, c_float,
+    'vqb_cvq_update': (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float,
                                c_float, c_float, c_void_p]),
+    'vqb_embedding_gather': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     'vqb_fsq_forward': (c_int, [c_void_p, c_int, c_int64, POINTER(FSQParams), c_void_p, c_int, c_void_p, c_void_p]),
     'vqb_fsq_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, POINTER(FSQParams), c_void_p, c_int,
                                  c_void_p]),

@@ -1,0 +1,332 @@
+"""Quantizer callbacks under the reference's registry names and hook protocol.
+
+Reference protocol: 9 hook points dispatched in priority order by ComposedCallback
+(vq/tasks/image_tokenization/models/quantizers/callbacks/{base,composed,lazy_init_weights}.py).
+Reference callbacks re-implemented on the B200 kernels:
+    NormalizeCallback   vq/algorithms/vq/callbacks/normalize.py:19-29
+    UpdateMixin         vq/algorithms/vq/callbacks/update.py:15-56
+    VQKDCallback        vq/algorithms/vqkd/quantizers/callbacks.py:38-129   (k-means init + per-step EMA)
+    CVQVAECallback      vq/algorithms/cvqvae/quantizer_callback.py:25-105   (usage EMA + anchor re-init)
+Codebook updates keep the reference's ordering: they run in `after_encode`, i.e. BEFORE the gather, so
+`z` and the losses see the updated codebook.
+"""
+from __future__ import annotations
+
+import random
+from typing import Iterable, Mapping
+
+import torch
+
+from . import functional as Fq
+from . import ops, parallel
+from .registry import AnchorRegistry, Config, VQITQuantizerCallbackRegistry, get_config
+
+__all__ = ['BaseCallback', 'ComposedCallback', 'UpdateMixin', 'NormalizeCallback', 'LazyInitWeightsMixin',
+           'VQKDCallback', 'CVQVAECallback', 'EMA']
+
+HOOKS = ('bind', 'before_init_weights', 'after_init_weights', 'before_encode', 'after_encode', 'before_decode',
+         'after_decode', 'before_loss', 'after_loss')
+
+
+class EMA:
+    """todd.utils.EMA stand-in: only `decay` is consumed (the blends run inside the update kernels).
+    Default decay 0.99 as in upstream CVQ-VAE / BEiT-v2 (todd default UNVERIFIED)."""
+
+    def __init__(self, decay: float = 0.99) -> None:
+        self._decay = float(decay)
+
+    @property
+    def decay(self) -> float:
+        return self._decay
+
+
+class BaseCallback:
+    # B200 path: set by callbacks whose `after_encode` consumes the per-code nearest token
+    needs_column_nearest = False
+    column_nearest_global = False
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__()
+        self._instance = None
+
+    @classmethod
+    def build_pre_hook(cls, config: Mapping, registry, item) -> Mapping:
+        return config
+
+    def bind(self, instance) -> None:
+        self._instance = instance
+
+    @property
+    def quantizer(self):
+        return self._instance
+
+    @property
+    def vector_quantizer(self):
+        from .quantizers import VectorQuantizer
+        assert isinstance(self._instance, VectorQuantizer)
+        return self._instance
+
+    def before_init_weights(self, config: Mapping) -> None:
+        pass
+
+    def after_init_weights(self, config: Mapping, recursive: bool) -> bool:
+        return recursive
+
+    def before_encode(self, x: torch.Tensor, memo: dict) -> torch.Tensor:
+        return x
+
+    def after_encode(self, x: torch.Tensor, quant: torch.Tensor, memo: dict) -> torch.Tensor:
+        return quant
+
+    def before_decode(self, quant: torch.Tensor, memo: dict) -> torch.Tensor:
+        return quant
+
+    def after_decode(self, z: torch.Tensor, memo: dict) -> torch.Tensor:
+        return z
+
+    def before_loss(self, z: torch.Tensor, x: torch.Tensor, memo: dict):
+        return z, x
+
+    def after_loss(self, loss: torch.Tensor, memo: dict) -> torch.Tensor:
+        return loss
+
+
+@VQITQuantizerCallbackRegistry.register_()
+class ComposedCallback(BaseCallback):
+
+    def __init__(self, *args, priorities: Iterable[Mapping[str, int]], callbacks: Iterable[BaseCallback],
+                 **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self._priorities = [dict(p) for p in priorities]
+        self._callbacks = list(callbacks)
+
+    @classmethod
+    def build_pre_hook(cls, config, registry, item):
+        config = super().build_pre_hook(config, registry, item)
+        callbacks = [Config(c) if isinstance(c, Mapping) else c for c in config['callbacks']]
+        config['priorities'] = [c.pop('priority', dict()) if isinstance(c, Mapping) else dict() for c in callbacks]
+        config['callbacks'] = [VQITQuantizerCallbackRegistry.build_or_return(c) for c in callbacks]
+        return config
+
+    def __iter__(self):
+        return iter(self._callbacks)
+
+    def _queue(self, key: str):
+        order = sorted(range(len(self._callbacks)), key=lambda i: -self._priorities[i].get(key, 0))
+        return [self._callbacks[i] for i in order]
+
+    @property
+    def needs_column_nearest(self) -> bool:  # type: ignore[override]
+        return any(c.needs_column_nearest for c in self._callbacks)
+
+    @property
+    def column_nearest_global(self) -> bool:  # type: ignore[override]
+        return any(c.column_nearest_global for c in self._callbacks)
+
+    def overrides(self, hook: str) -> bool:
+        """True if any child customises `hook` (the fused decode/loss path checks this)."""
+        return any(getattr(type(c), hook) is not getattr(BaseCallback, hook) for c in self._callbacks)
+
+    def bind(self, instance) -> None:
+        super().bind(instance)
+        for c in self._queue('bind'):
+            c.bind(instance)
+
+    def before_init_weights(self, config) -> None:
+        for c in self._queue('before_init_weights'):
+            c.before_init_weights(config)
+
+    def after_init_weights(self, config, recursive: bool) -> bool:
+        for c in self._queue('after_init_weights'):
+            recursive = c.after_init_weights(config, recursive)
+        return recursive
+
+    def before_encode(self, x, memo):
+        for c in self._queue('before_encode'):
+            x = c.before_encode(x, memo)
+        return x
+
+    def after_encode(self, x, quant, memo):
+        for c in self._queue('after_encode'):
+            quant = c.after_encode(x, quant, memo)
+        return quant
+
+    def before_decode(self, quant, memo):
+        for c in self._queue('before_decode'):
+            quant = c.before_decode(quant, memo)
+        return quant
+
+    def after_decode(self, z, memo):
+        for c in self._queue('after_decode'):
+            z = c.after_decode(z, memo)
+        return z
+
+    def before_loss(self, z, x, memo):
+        for c in self._queue('before_loss'):
+            z, x = c.before_loss(z, x, memo)
+        return z, x
+
+    def after_loss(self, loss, memo):
+        for c in self._queue('after_loss'):
+            loss = c.after_loss(loss, memo)
+        return loss
+
+
+class UpdateMixin(BaseCallback):
+
+    def __init__(self, *args, ema: EMA | None = None, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        if ema is not None:
+            self._ema = ema
+
+    @classmethod
+    def build_pre_hook(cls, config, registry, item):
+        config = super().build_pre_hook(config, registry, item)
+        if config.get('ema') is not None and not isinstance(config['ema'], EMA):
+            config['ema'] = EMA(**config['ema'])
+        return config
+
+    @property
+    def with_ema(self) -> bool:
+        return hasattr(self, '_ema')
+
+    def _update_embedding(self, e: torch.Tensor) -> None:
+        self.vector_quantizer.embedding.weight.data = e
+
+
+@VQITQuantizerCallbackRegistry.register_()
+class NormalizeCallback(UpdateMixin, BaseCallback):
+    """x <- normalize(x);  weight.data <- normalize(weight)  every forward, train and eval.
+    One kernel normalises the codebook in place AND emits the bf16 operand planes (+0.5|e|^2) that the
+    assignment kernel reads, so the per-forward codebook rewrite costs no extra pass."""
+
+    def before_encode(self, x, memo):
+        x = super().before_encode(x, memo)
+        x = Fq.l2_normalize(x)
+        vq = self.vector_quantizer
+        memo['_codebook_operand'] = Fq.pack_codebook(vq.embedding.weight.data, vq.distance.metric,
+                                                     precision=vq.precision, writeback_normalized=True)
+        return x
+
+
+class LazyInitWeightsMixin(BaseCallback):
+    """Runs `lazy_init_weights(config, x, memo)` once, on the first forward (forward pre-hook)."""
+
+    def lazy_init_weights(self, config: Mapping, x: torch.Tensor, memo: dict) -> None:
+        raise NotImplementedError
+
+    def before_init_weights(self, config) -> None:
+        super().before_init_weights(config)
+        lazy_cfg = config.pop('lazy_init_weights', Config()) if hasattr(config, 'pop') else Config()
+
+        def forward_pre_hook(module, args):
+            x, memo = args
+            self.lazy_init_weights(lazy_cfg, x, memo)
+            handle.remove()
+
+        handle = self.quantizer.register_forward_pre_hook(forward_pre_hook)
+
+
+@VQITQuantizerCallbackRegistry.register_()
+class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
+    """Per training step: counts + sums of normalised tokens per code (warp-aggregated scatter-add) ->
+    ONE all-reduce of the fused [K*D | K] buffer -> centroid / normalise / EMA / normalise kernel."""
+
+    @torch.no_grad()
+    def lazy_init_weights(self, config, x, memo) -> None:
+        """k-means init (callbacks.py:77-112): gather tokens to rank 0, seed with `random.sample`, `iters`
+        rounds of (normalise codebook -> assign -> centroids), broadcast.  No N x K matrix, no CPU offload."""
+        vq = self.vector_quantizer
+        if not vq.training:
+            return
+        x = x.detach().contiguous()
+        world, rank = parallel.world_size(), parallel.rank()
+        if world > 1:
+            gathered = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
+            torch.distributed.gather(x, gathered, dst=0)
+            x = torch.cat(gathered) if rank == 0 else x.new_empty(0, x.shape[1])
+        W = vq.embedding.weight.data
+        K = W.shape[0]
+        iters = config.get('iters', 10)
+        if rank == 0:
+            if x.shape[0] < K:
+                W[:x.shape[0]] = x.float()
+            else:
+                xn = ops.l2norm_forward(x)
+                indices = random.sample(range(xn.shape[0]), K)
+                W.copy_(ops.embedding_gather(xn, torch.tensor(indices, device=x.device)))
+                for _ in range(iters):
+                    book = Fq.pack_codebook(W, vq.distance.metric, precision=vq.precision, writeback_normalized=True)
+                    quant = ops.unpack_keys(Fq.nearest_code(xn, book, vq.distance.metric, precision=vq.precision))
+                    stats = ops.scatter_stats(xn, quant, K)
+                    ops.kmeans_ema_update(stats, W, 0.0)  # decay 0: W <- normalize(centroids | old row if unused)
+        if world > 1:
+            torch.distributed.broadcast(W, 0)
+        Fq.pack_codebook(W, vq.distance.metric, precision=vq.precision, writeback_normalized=True)
+
+    @torch.no_grad()
+    def after_encode(self, x, quant, memo):
+        quant = super().after_encode(x, quant, memo)
+        vq = self.vector_quantizer
+        if not vq.training:
+            return quant
+        W = vq.embedding.weight.data
+        stats = ops.scatter_stats(x.detach(), quant, W.shape[0], normalize_x=True)
+        parallel.all_reduce_sum_(stats)
+        ops.kmeans_ema_update(stats, W, self._ema.decay)
+        return quant
+
+
+@VQITQuantizerCallbackRegistry.register_()
+class CVQVAECallback(UpdateMixin, BaseCallback):
+    """Usage-probability EMA + nearest-token anchors + per-code decay blend (training only)."""
+
+    needs_column_nearest = True
+
+    def __init__(self, *args, anchor, eps: float = 1e-3, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self._anchor = anchor
+        self._eps = eps
+
+    @classmethod
+    def build_pre_hook(cls, config, registry, item):
+        config = super().build_pre_hook(config, registry, item)
+        config['anchor'] = AnchorRegistry.build_or_return(config['anchor'])
+        return config
+
+    @property
+    def column_nearest_global(self) -> bool:  # type: ignore[override]
+        return bool(self._anchor.sync)
+
+    def before_init_weights(self, config) -> None:
+        super().before_init_weights(config)
+        if not self.quantizer.training:
+            return
+        dev = self.vector_quantizer.embedding.weight.device
+        self.quantizer.register_buffer('_probability', torch.zeros(self.quantizer.codebook_size, device=dev))
+
+    @property
+    def probability(self) -> torch.Tensor:
+        return self.quantizer.get_buffer('_probability')
+
+    @torch.no_grad()
+    def after_encode(self, x, quant, memo):
+        quant = super().after_encode(x, quant, memo)
+        vq = self.vector_quantizer
+        if not vq.training:
+            return quant
+        W = vq.embedding.weight.data
+        K = W.shape[0]
+        x = x.detach().contiguous()
+        N = x.shape[0]
+        # [K counts | numel] in one int64 buffer -> one all-reduce (utils.py:35 does two)
+        cnt = torch.zeros(K + 1, dtype=torch.int64, device=x.device)
+        ops.bincount_accumulate(quant, cnt, K, total_slot=True)
+        parallel.all_reduce_sum_(cnt)
+        col_keys = memo['encode']['column_keys']
+        world = parallel.world_size()
+        anchors = self._anchor.gather(x, col_keys, N)
+        scale = 1.0 if self._anchor.sync else 1.0 / world
+        ops.cvq_update(W, anchors, self.probability, cnt[:K], cnt[K:], decay=self._ema.decay, eps=self._eps,
+                       anchor_scale=scale)
+        return quant

@@ -176,6 +176,18 @@ __global__ void unpack_keys_kernel(const unsigned long long* __restrict__ keys, 
   }
 }
 
+__global__ void embedding_gather_kernel(const float* __restrict__ W, int64_t K, int D,
+                                        const int64_t* __restrict__ quant, int64_t n, float* __restrict__ out) {
+  const int64_t total = n * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D;
+    const int d = (int)(i - r * D);
+    int64_t q = quant[r];
+    q = q < 0 ? 0 : (q >= K ? K - 1 : q);
+    out[i] = __ldg(W + q * D + d);
+  }
+}
+
 __global__ void keys_flip_kernel(unsigned long long* __restrict__ keys, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     keys[i] ^= 0x8000000000000000ull;
@@ -259,6 +271,18 @@ int vqb_unpack_keys(const unsigned long long* keys, int64_t n, int64_t offset, i
   int blocks = (int)((n + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   unpack_keys_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(keys, n, offset, idx, score);
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_embedding_gather(const float* W, int64_t K, int D, const int64_t* quant, int64_t n, float* out,
+                         void* stream) {
+  VQB_REQUIRE(W && quant && out, "vqb_embedding_gather: null pointer");
+  VQB_REQUIRE(K >= 1 && D >= 1, "vqb_embedding_gather: bad shape");
+  if (n <= 0) return VQB_OK;
+  int64_t blocks64 = (n * D + 255) / 256;
+  const int blocks = (int)(blocks64 < (int64_t)sm_count() * 8 ? blocks64 : (int64_t)sm_count() * 8);
+  embedding_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, K, D, quant, n, out);
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

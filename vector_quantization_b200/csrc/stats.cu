@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(256) scatter_stats_kernel(const TX* __restrict
 }
 
 __global__ void bincount_kernel(const int64_t* __restrict__ quant, int64_t n, unsigned long long* __restrict__ counts,
-                                int64_t K) {
+                                int64_t K, int add_total) {
+  if (add_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counts + K, (unsigned long long)n);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < round_up(n, 32);
        i += (int64_t)gridDim.x * blockDim.x) {
     const bool ok = i < n;
@@ -148,14 +149,16 @@ __global__ void gather_rows_by_key_kernel(const TX* __restrict__ x, int64_t N, i
 }
 
 __global__ void cvq_update_kernel(float* __restrict__ W, const float* __restrict__ anchors, float anchor_scale,
-                                  float* __restrict__ prob, const float* __restrict__ counts, float total, int64_t K,
-                                  int D, float decay, float omd, float eps) {
+                                  float* __restrict__ prob, const int64_t* __restrict__ counts,
+                                  const int64_t* __restrict__ total_ptr, int64_t K, int D, float decay, float omd,
+                                  float eps) {
+  const float total = (float)*total_ptr;  // int64 -> fp32, then a true division like `bin_count / numel`
   // one warp per code row; lane 0 owns the probability update
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t k = warp; k < K; k += nwarps) {
-    const float freq = __fdiv_rn(counts[k], total);
+    const float freq = __fdiv_rn((float)counts[k], total);
     const float p = __fadd_rn(__fmul_rn(prob[k], decay), __fmul_rn(freq, omd));
     // decay_k = 1 - exp(-p*K*10/(1-decay) - eps)      cvqvae/quantizer_callback.py:98-101
     float t = __fmul_rn(__fmul_rn(-p, (float)K), 10.f);
@@ -224,12 +227,13 @@ int vqb_scatter_stats(const void* x, int x_dtype, int64_t N, int D, int normaliz
   return VQB_OK;
 }
 
-int vqb_bincount_accumulate(const int64_t* quant, int64_t n, int64_t* counts, int64_t K, void* stream) {
+int vqb_bincount_accumulate(const int64_t* quant, int64_t n, int64_t* counts, int64_t K, int add_total,
+                            void* stream) {
   VQB_REQUIRE(quant && counts, "vqb_bincount_accumulate: null pointer");
   if (n <= 0) return VQB_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  bincount_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(quant, n, (unsigned long long*)counts, K);
+  bincount_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(quant, n, (unsigned long long*)counts, K, add_total);
   VQB_LAUNCH_OK();
   return VQB_OK;
 }
@@ -263,10 +267,11 @@ int vqb_gather_rows_by_key(const void* x, int x_dtype, int64_t N, int D, const u
   return VQB_OK;
 }
 
-int vqb_cvq_update(float* W, const float* anchors, float anchor_scale, float* prob, const float* counts, float total,
-                   int64_t K, int D, float decay, float one_minus_decay, float eps, void* stream) {
-  VQB_REQUIRE(W && anchors && prob && counts, "vqb_cvq_update: null pointer");
-  VQB_REQUIRE(K >= 1 && D >= 1 && total > 0.f, "vqb_cvq_update: bad shape");
+int vqb_cvq_update(float* W, const float* anchors, float anchor_scale, float* prob, const int64_t* counts,
+                   const int64_t* total, int64_t K, int D, float decay, float one_minus_decay, float eps,
+                   void* stream) {
+  VQB_REQUIRE(W && anchors && prob && counts && total, "vqb_cvq_update: null pointer");
+  VQB_REQUIRE(K >= 1 && D >= 1, "vqb_cvq_update: bad shape");
   int blocks = (int)((K * 32 + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   cvq_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, anchors, anchor_scale, prob, counts, total, K, D,

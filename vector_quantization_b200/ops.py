@@ -18,7 +18,7 @@ from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, VQB_BF16, VQB_F32, FSQParams, c
 __all__ = [
     'Operand', 'pack_rows', 'assign', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
-    'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'fsq_params', 'fsq_forward', 'fsq_backward',
+    'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
     'fsq_decode', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
 ]
 
@@ -47,6 +47,24 @@ def _p(t: torch.Tensor | None):
 
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+LAUNCHES = 0     # kernels launched through the C-ABI (bench.py reports it as gpu_launches)
+PROFILE = None   # when a list: (name, start_event, end_event) per launch, on the launching stream
+
+
+def _call(name: str, fn, *args) -> None:
+    global LAUNCHES
+    if PROFILE is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        status = fn(*args)
+        b.record()
+        PROFILE.append((name, a, b))
+    else:
+        status = fn(*args)
+    LAUNCHES += 1
+    check(status, name)
 
 
 @dataclass
@@ -80,9 +98,8 @@ def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None 
     h = torch.empty((rows_pad,), dtype=torch.float32, device=src.device) if want_half_sqnorm else None
     if writeback is not None:
         assert writeback.dtype == torch.float32 and writeback.shape == src.shape
-    check(lib.vqb_pack_rows(_p(src), _dt(src), rows, D, int(normalize), planes, _p(dst), _p(h), _p(writeback),
-                            _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _stream()),
-          'vqb_pack_rows')
+    _call('vqb_pack_rows', lib.vqb_pack_rows, _p(src), _dt(src), rows, D, int(normalize), planes, _p(dst), _p(h), _p(writeback),
+                            _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _stream())
     return Operand(dst, rows, D, planes, h)
 
 
@@ -101,8 +118,8 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
     if l2:
         assert b.half_sqnorm is not None, 'L2 assignment needs the packed operand to carry half_sqnorm'
         h = b.half_sqnorm
-    check(lib.vqb_assign(_p(a.planes), a.nplanes, a.rows, _p(b.planes), b.nplanes, b.rows, a.dim, _p(h),
-                         index_offset, _p(keys), backend, _stream()), 'vqb_assign')
+    _call('vqb_assign', lib.vqb_assign, _p(a.planes), a.nplanes, a.rows, _p(b.planes), b.nplanes, b.rows, a.dim, _p(h),
+                         index_offset, _p(keys), backend, _stream())
     return keys
 
 
@@ -112,14 +129,14 @@ def unpack_keys(keys: torch.Tensor, index_offset: int = 0, want_score: bool = Fa
     n = keys.numel()
     idx = torch.empty((n,), dtype=torch.int64, device=keys.device)
     score = torch.empty((n,), dtype=torch.float32, device=keys.device) if want_score else None
-    check(lib.vqb_unpack_keys(_p(keys), n, index_offset, _p(idx), _p(score), _stream()), 'vqb_unpack_keys')
+    _call('vqb_unpack_keys', lib.vqb_unpack_keys, _p(keys), n, index_offset, _p(idx), _p(score), _stream())
     return (idx, score) if want_score else idx
 
 
 def keys_flip_sign(keys: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _cuda(keys)
-    check(lib.vqb_keys_flip_sign(_p(keys), keys.numel(), _stream()), 'vqb_keys_flip_sign')
+    _call('vqb_keys_flip_sign', lib.vqb_keys_flip_sign, _p(keys), keys.numel(), _stream())
     return keys
 
 
@@ -145,9 +162,8 @@ def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor, *, wa
     z = torch.empty((N, D), dtype=out_dtype, device=x.device)
     mse4 = torch.empty((4,), dtype=torch.float32, device=x.device)
     partials, ticket = _loss_ws(x.device)
-    check(lib.vqb_gather_ste_loss(_p(x), _dt(x), N, D, _p(W), W.shape[0], _p(quant), _p(z), _dt(z),
-                                  int(want_norm), _p(mse4), _p(partials), _p(ticket), _stream()),
-          'vqb_gather_ste_loss')
+    _call('vqb_gather_ste_loss', lib.vqb_gather_ste_loss, _p(x), _dt(x), N, D, _p(W), W.shape[0], _p(quant), _p(z), _dt(z),
+                                  int(want_norm), _p(mse4), _p(partials), _p(ticket), _stream())
     return z, mse4
 
 
@@ -158,8 +174,8 @@ def quantize_backward(g_z: torch.Tensor, x: torch.Tensor, W: torch.Tensor, quant
     N, D = x.shape
     gx = torch.empty_like(x)
     gW = torch.zeros_like(W) if need_gW else None
-    check(lib.vqb_quantize_backward(_p(g_z), _dt(g_z), _p(x), _dt(x), _p(W), W.shape[0], _p(quant), N, D, _p(g4),
-                                    int(want_norm), _p(gx), _dt(gx), _p(gW), _stream()), 'vqb_quantize_backward')
+    _call('vqb_quantize_backward', lib.vqb_quantize_backward, _p(g_z), _dt(g_z), _p(x), _dt(x), _p(W), W.shape[0], _p(quant), N, D, _p(g4),
+                                    int(want_norm), _p(gx), _dt(gx), _p(gW), _stream())
     return gx, gW
 
 
@@ -167,8 +183,7 @@ def l2norm_forward(x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> t
     lib = _lib.load()
     _cuda(x)
     y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    check(lib.vqb_l2norm_forward(_p(x), _dt(x), x.shape[0], x.shape[1], _p(y), _dt(y), _stream()),
-          'vqb_l2norm_forward')
+    _call('vqb_l2norm_forward', lib.vqb_l2norm_forward, _p(x), _dt(x), x.shape[0], x.shape[1], _p(y), _dt(y), _stream())
     return y
 
 
@@ -176,8 +191,8 @@ def l2norm_backward(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _cuda(gy, x)
     gx = torch.empty_like(x)
-    check(lib.vqb_l2norm_backward(_p(gy), _dt(gy), _p(x), _dt(x), x.shape[0], x.shape[1], _p(gx), _dt(gx),
-                                  _stream()), 'vqb_l2norm_backward')
+    _call('vqb_l2norm_backward', lib.vqb_l2norm_backward, _p(gy), _dt(gy), _p(x), _dt(x), x.shape[0], x.shape[1], _p(gx), _dt(gx),
+                                  _stream())
     return gx
 
 
@@ -188,17 +203,20 @@ def scatter_stats(x: torch.Tensor, quant: torch.Tensor, K: int, *, normalize_x: 
     _cuda(x, quant, out)
     N, D = x.shape
     stats = out if out is not None else torch.zeros((K * D + K,), dtype=torch.float32, device=x.device)
-    check(lib.vqb_scatter_stats(_p(x), _dt(x), N, D, int(normalize_x), _p(quant), _p(stats), K, _stream()),
-          'vqb_scatter_stats')
+    _call('vqb_scatter_stats', lib.vqb_scatter_stats, _p(x), _dt(x), N, D, int(normalize_x), _p(quant), _p(stats), K, _stream())
     return stats
 
 
-def bincount_accumulate(quant: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+def bincount_accumulate(quant: torch.Tensor, counts: torch.Tensor, K: int | None = None,
+                        total_slot: bool = False) -> torch.Tensor:
+    """counts[:K] += bincount(quant); with total_slot, counts has K+1 entries and counts[K] += numel."""
     lib = _lib.load()
     _cuda(quant, counts)
     assert quant.dtype == torch.int64 and counts.dtype == torch.int64
-    check(lib.vqb_bincount_accumulate(_p(quant), quant.numel(), _p(counts), counts.numel(), _stream()),
-          'vqb_bincount_accumulate')
+    K = counts.numel() - int(total_slot) if K is None else K
+    assert counts.numel() >= K + int(total_slot)
+    flat = quant.reshape(-1)
+    _call('vqb_bincount_accumulate', lib.vqb_bincount_accumulate, _p(flat), flat.numel(), _p(counts), K, int(total_slot), _stream())
     return counts
 
 
@@ -210,8 +228,7 @@ def kmeans_ema_update(stats: torch.Tensor, W: torch.Tensor, decay: float) -> tor
     lib = _lib.load()
     _cuda(stats, W)
     K, D = W.shape
-    check(lib.vqb_kmeans_ema_update(_p(stats), _p(W), K, D, _f32(decay), _f32(1 - decay), _stream()),
-          'vqb_kmeans_ema_update')
+    _call('vqb_kmeans_ema_update', lib.vqb_kmeans_ema_update, _p(stats), _p(W), K, D, _f32(decay), _f32(1 - decay), _stream())
     return W
 
 
@@ -221,18 +238,29 @@ def gather_rows_by_key(x: torch.Tensor, keys: torch.Tensor, index_offset: int = 
     N, D = x.shape
     K = keys.numel()
     out = torch.empty((K, D), dtype=torch.float32, device=x.device)
-    check(lib.vqb_gather_rows_by_key(_p(x), _dt(x), N, D, _p(keys), K, index_offset, _p(out), _stream()),
-          'vqb_gather_rows_by_key')
+    _call('vqb_gather_rows_by_key', lib.vqb_gather_rows_by_key, _p(x), _dt(x), N, D, _p(keys), K, index_offset, _p(out), _stream())
     return out
 
 
-def cvq_update(W: torch.Tensor, anchors: torch.Tensor, prob: torch.Tensor, counts: torch.Tensor, total: float, *,
-               decay: float, eps: float, anchor_scale: float = 1.0) -> None:
+def cvq_update(W: torch.Tensor, anchors: torch.Tensor, prob: torch.Tensor, counts: torch.Tensor,
+               total: torch.Tensor, *, decay: float, eps: float, anchor_scale: float = 1.0) -> None:
+    """counts: int64 [K]; total: int64 [1] device tensor (both already all-reduced)."""
     lib = _lib.load()
-    _cuda(W, anchors, prob, counts)
+    _cuda(W, anchors, prob, counts, total)
+    assert counts.dtype == torch.int64 and total.dtype == torch.int64
     K, D = W.shape
-    check(lib.vqb_cvq_update(_p(W), _p(anchors), anchor_scale, _p(prob), _p(counts), float(total), K, D,
-                             _f32(decay), _f32(1 - decay), _f32(eps), _stream()), 'vqb_cvq_update')
+    _call('vqb_cvq_update', lib.vqb_cvq_update, _p(W), _p(anchors), anchor_scale, _p(prob), _p(counts), _p(total), K, D,
+                             _f32(decay), _f32(1 - decay), _f32(eps), _stream())
+
+
+def embedding_gather(W: torch.Tensor, quant: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(W, quant)
+    assert W.dtype == torch.float32 and quant.dtype == torch.int64
+    flat = quant.reshape(-1).contiguous()
+    out = torch.empty((flat.numel(), W.shape[1]), dtype=torch.float32, device=W.device)
+    _call('vqb_embedding_gather', lib.vqb_embedding_gather, _p(W), W.shape[0], W.shape[1], _p(flat), flat.numel(), _p(out), _stream())
+    return out.reshape(*quant.shape, W.shape[1])
 
 
 # ---- FSQ -------------------------------------------------------------------------------------
@@ -270,8 +298,7 @@ def fsq_forward(x: torch.Tensor, p: FSQParams, out_dtype: torch.dtype | None = N
     assert D == p.D
     zq = torch.empty((N, D), dtype=out_dtype or x.dtype, device=x.device)
     idx = torch.empty((N,), dtype=torch.int32, device=x.device)
-    check(lib.vqb_fsq_forward(_p(x), _dt(x), N, ctypes.byref(p), _p(zq), _dt(zq), _p(idx), _stream()),
-          'vqb_fsq_forward')
+    _call('vqb_fsq_forward', lib.vqb_fsq_forward, _p(x), _dt(x), N, ctypes.byref(p), _p(zq), _dt(zq), _p(idx), _stream())
     return zq, idx
 
 
@@ -279,8 +306,8 @@ def fsq_backward(gz: torch.Tensor, x: torch.Tensor, p: FSQParams) -> torch.Tenso
     lib = _lib.load()
     _cuda(gz, x)
     gx = torch.empty_like(x)
-    check(lib.vqb_fsq_backward(_p(gz), _dt(gz), _p(x), _dt(x), x.shape[0], ctypes.byref(p), _p(gx), _dt(gx),
-                               _stream()), 'vqb_fsq_backward')
+    _call('vqb_fsq_backward', lib.vqb_fsq_backward, _p(gz), _dt(gz), _p(x), _dt(x), x.shape[0], ctypes.byref(p), _p(gx), _dt(gx),
+                               _stream())
     return gx
 
 
@@ -290,5 +317,5 @@ def fsq_decode(index: torch.Tensor, p: FSQParams) -> torch.Tensor:
     index = index.to(torch.int32) if index.dtype != torch.int32 else index
     flat = index.reshape(-1).contiguous()
     z = torch.empty((flat.numel(), p.D), dtype=torch.float32, device=index.device)
-    check(lib.vqb_fsq_decode(_p(flat), flat.numel(), ctypes.byref(p), _p(z), _stream()), 'vqb_fsq_decode')
+    _call('vqb_fsq_decode', lib.vqb_fsq_decode, _p(flat), flat.numel(), ctypes.byref(p), _p(z), _stream())
     return z.reshape(*index.shape, p.D)

@@ -1,0 +1,290 @@
+"""Quantizer modules under the reference's registry names, config keys and forward contract
+(SURVEY.md §8b):  forward(x [N, D], memo) -> (z [N, D], loss [], memo)  with
+memo['x'], memo['quant'] (int64 [N]; int32 for FSQ), memo['encode'], memo['decode'], memo['loss'][name].
+
+Reference:
+    BaseQuantizer            vq/tasks/image_tokenization/models/quantizers/base.py:26-182
+    VectorQuantizer          vq/algorithms/vq/quantizers.py:19-117
+    VQGANQuantizer           vq/algorithms/vqgan/quantizer.py:11-21
+    VQKDQuantizer            vq/algorithms/vqkd/quantizers/base.py:11-15
+    ScalarQuantizer          vq/algorithms/sq/quantizers.py:9-11
+    FiniteScalarQuantizer    vq/algorithms/fsq/quantizers.py:74-150
+The arithmetic runs in the sm_100a kernels of libvqb200.so: tensors must live on a CUDA device and the
+library must be present — there is no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+from typing import Mapping, Sequence
+
+import torch
+from torch import nn
+
+from . import functional as Fq
+from . import ops, parallel
+from ._lib import VQBError
+from .callbacks import ComposedCallback
+from .distances import BaseDistance
+from .registry import (Config, InitRegistry, ModelRegistry, ModuleDict, VQITQuantizerCallbackRegistry,
+                       VQITQuantizerDistanceRegistry, VQITQuantizerLossRegistry, VQITQuantizerRegistry,
+                       build_module_dict, get_config)
+
+__all__ = ['BaseQuantizer', 'VectorQuantizer', 'VQGANQuantizer', 'VQKDQuantizer', 'ScalarQuantizer',
+           'FiniteScalarQuantizer']
+
+
+def get_memo(memo: dict, key: str) -> dict:
+    """vq/utils/misc.py:30-38."""
+    if key not in memo:
+        memo[key] = dict()
+    assert isinstance(memo[key], dict)
+    return memo[key]
+
+
+def _check_tokens(x: torch.Tensor, dim: int) -> torch.Tensor:
+    if not x.is_cuda:
+        raise VQBError('vector_quantization_b200 quantizers run on CUDA (sm_100a) tensors only; no CPU fallback')
+    if x.dim() != 2 or x.shape[1] != dim:
+        raise ValueError(f'expected tokens of shape [N, {dim}] ("b c h w -> (b h w) c"), got {tuple(x.shape)}')
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f'tokens must be float32 or bfloat16, got {x.dtype}')
+    return x.contiguous()
+
+
+class BaseQuantizer(nn.Module):
+
+    def __init__(self, *args, callbacks: ComposedCallback, losses: ModuleDict, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self._callbacks = callbacks
+        self._losses = losses
+        self._callbacks.bind(self)
+
+    @classmethod
+    def build_pre_hook(cls, config: Mapping, registry, item) -> Mapping:
+        config['callbacks'] = VQITQuantizerCallbackRegistry.build(
+            Config(type='ComposedCallback', callbacks=config.get('callbacks', [])))
+        config['losses'] = build_module_dict(VQITQuantizerLossRegistry, get_config(config, 'losses'))
+        return config
+
+    @property
+    def embedding_dim(self) -> int:
+        raise NotImplementedError
+
+    @property
+    def codebook_size(self) -> int:
+        raise NotImplementedError
+
+    @property
+    def embeddings(self) -> torch.Tensor:
+        raise NotImplementedError
+
+    def _init_weights(self, config: Mapping) -> bool:
+        return True
+
+    def init_weights(self, config: Mapping) -> bool:
+        config = Config(config)
+        before = config.pop('before_init_weights', Config())
+        after = config.pop('after_init_weights', Config())
+        self._callbacks.before_init_weights(before)
+        recursive = self._init_weights(config)
+        return self._callbacks.after_init_weights(after, recursive)
+
+    # -- template (reference base.py:123-182) --------------------------------------------------------
+    def _encode(self, x: torch.Tensor, memo: dict):
+        raise NotImplementedError
+
+    def encode(self, x: torch.Tensor, memo: dict):
+        x = self._callbacks.before_encode(x, memo)
+        enc = get_memo(memo, 'encode')
+        if '_codebook_operand' in memo:  # packed by a normalising callback in the same pass
+            enc['_codebook_operand'] = memo.pop('_codebook_operand')
+        quant, memo['encode'] = self._encode(x, enc)
+        quant = self._callbacks.after_encode(x, quant, memo)
+        return x, quant, memo
+
+    def _decode(self, quant: torch.Tensor, memo: dict):
+        raise NotImplementedError
+
+    def decode(self, quant: torch.Tensor, memo: dict):
+        quant = self._callbacks.before_decode(quant, memo)
+        z, memo['decode'] = self._decode(quant, get_memo(memo, 'decode'))
+        z = self._callbacks.after_decode(z, memo)
+        return z, memo
+
+    def forward(self, x: torch.Tensor, memo: dict):
+        raise NotImplementedError
+
+
+@VQITQuantizerRegistry.register_()
+class VectorQuantizer(BaseQuantizer):
+    """distance -> arg-min -> (codebook update callbacks) -> gather -> losses -> straight-through, as three
+    kernel launches: pack+assign (tcgen05, no N x K matrix), [stats/update], fused gather+STE+loss."""
+
+    def __init__(self, *args, embedding: nn.Embedding, distance: BaseDistance, precision: str = 'exact',
+                 **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        if precision not in Fq.PRECISION_PLANES:
+            raise ValueError(f'precision must be one of {sorted(Fq.PRECISION_PLANES)}')
+        self._embedding = embedding
+        self._distance = distance
+        self.precision = precision
+
+    @classmethod
+    def build_pre_hook(cls, config, registry, item):
+        config = super().build_pre_hook(config, registry, item)
+        config['embedding'] = ModelRegistry.build_or_return(config['embedding'])
+        config['distance'] = VQITQuantizerDistanceRegistry.build_or_return(config['distance'])
+        return config
+
+    @property
+    def embedding(self) -> nn.Embedding:
+        return self._embedding
+
+    @property
+    def distance(self) -> BaseDistance:
+        return self._distance
+
+    @property
+    def embedding_dim(self) -> int:
+        return self._embedding.embedding_dim
+
+    @property
+    def codebook_size(self) -> int:
+        return self._embedding.num_embeddings
+
+    @property
+    def embeddings(self) -> torch.Tensor:
+        return self._embedding.weight.clone()
+
+    def _init_weights(self, config) -> bool:
+        InitRegistry.build(config)(self._embedding.weight)
+        return False
+
+    def _weight(self) -> torch.Tensor:
+        W = self._embedding.weight
+        if W.dtype != torch.float32:
+            raise TypeError('the codebook (nn.Embedding weight) must be float32, as in the reference')
+        if not W.is_cuda:
+            raise VQBError('the codebook must live on a CUDA device; there is no CPU fallback')
+        return W
+
+    @torch.no_grad()
+    def _encode(self, x: torch.Tensor, memo: dict):
+        x = _check_tokens(x.detach(), self.embedding_dim)
+        W = self._weight().data
+        metric = self._distance.metric
+        book = memo.pop('_codebook_operand', None)
+        if book is None:
+            book = Fq.pack_codebook(W, metric, precision=self.precision)
+        keys = Fq.nearest_code(x, book, metric, precision=self.precision)
+        quant = ops.unpack_keys(keys)
+        memo['keys'] = keys
+        if self.training and self._callbacks.needs_column_nearest:
+            offset = parallel.rank() * x.shape[0] if self._callbacks.column_nearest_global else 0
+            memo['column_keys'] = Fq.column_nearest(x, book, metric, precision=self.precision, index_offset=offset)
+        return quant, memo
+
+    def _decode(self, quant: torch.Tensor, memo: dict):
+        """Decode-only gather (decode_from_quant); any index shape.  Inference path: no autograd."""
+        return ops.embedding_gather(self._weight().data, quant.contiguous()), memo
+
+    def _loss_terms(self):
+        want_norm = False
+        for loss in self._losses.values():
+            want_norm = want_norm or loss.needs_norm
+        return want_norm
+
+    def forward(self, x: torch.Tensor, memo: dict):
+        for hook in ('before_decode', 'after_decode', 'before_loss', 'after_loss'):
+            if self._callbacks.overrides(hook):
+                raise NotImplementedError(f'callbacks overriding {hook} are not supported by the fused decode/loss path')
+        x = _check_tokens(x, self.embedding_dim)
+        x, quant, memo = self.encode(x, memo)
+        memo.update(x=x, quant=quant)
+        z, mse4 = Fq.quantize_ste_loss(x, self._weight(), quant, self._loss_terms())
+        memo['decode'] = get_memo(memo, 'decode')
+        loss_memo = get_memo(memo, 'loss')
+        loss = None
+        for name, module in self._losses.items():
+            value = module.from_mse4(mse4)
+            loss_memo[name] = value
+            loss = value if loss is None else loss + value
+        if loss is None:
+            loss = mse4.new_zeros([])
+        return z, loss, memo
+
+
+@VQITQuantizerRegistry.register_()
+class VQGANQuantizer(VectorQuantizer):
+
+    def _init_weights(self, config) -> bool:
+        if dict(config) == dict(type='vqgan'):
+            config = Config(type='uniform_', a=-1.0 / self.codebook_size, b=1.0 / self.codebook_size)
+        return super()._init_weights(config)
+
+
+@VQITQuantizerRegistry.register_()
+class VQKDQuantizer(VectorQuantizer):
+
+    def _init_weights(self, config) -> bool:
+        return False
+
+
+@VQITQuantizerRegistry.register_()
+class ScalarQuantizer(BaseQuantizer):
+    pass
+
+
+@VQITQuantizerRegistry.register_()
+class FiniteScalarQuantizer(ScalarQuantizer):
+    """tanh bound -> round (STE) -> mixed-radix index, one kernel (fsq/quantizers.py:108-126)."""
+
+    def __init__(self, *args, eps: float = 1e-3, num_scalars_per_channel: Sequence[int], **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        levels = tuple(int(v) for v in num_scalars_per_channel)
+        self._eps = eps
+        self._levels = levels
+        self._params = ops.fsq_params(levels, eps)
+        max_per_digit = torch.tensor(levels, dtype=torch.int)
+        cumprod = torch.tensor((1,) + levels[:-1]).cumprod(0)
+        self._codebook_size = int(max_per_digit.prod().item())
+        quant = torch.arange(self._codebook_size).unsqueeze(-1)
+        digits = (quant // cumprod) % max_per_digit
+        self.register_buffer('_embeddings', digits / (max_per_digit // 2) - 1)  # implicit codebook table, :90-93
+
+    @property
+    def embedding_dim(self) -> int:
+        return len(self._levels)
+
+    @property
+    def codebook_size(self) -> int:
+        return self._codebook_size
+
+    @property
+    def embeddings(self) -> torch.Tensor:
+        return self.get_buffer('_embeddings')
+
+    def _encode(self, x: torch.Tensor, memo: dict):
+        x = _check_tokens(x, self.embedding_dim)
+        zq, quant = Fq.fsq_quantize(x, self._params)
+        memo['z'] = zq
+        return quant, memo
+
+    def _decode(self, quant: torch.Tensor, memo: dict):
+        if 'z' in memo:
+            return memo['z'], memo
+        if not quant.is_cuda:
+            raise VQBError('FSQ decode runs on CUDA tensors only; there is no CPU fallback')
+        return ops.fsq_decode(quant.contiguous(), self._params), memo
+
+    def decode(self, quant: torch.Tensor, memo: dict):
+        enc, dec = get_memo(memo, 'encode'), get_memo(memo, 'decode')
+        if 'z' in enc:
+            dec['z'] = enc['z']
+        return super().decode(quant, memo)
+
+    def forward(self, x: torch.Tensor, memo: dict):
+        x, quant, memo = self.encode(x, memo)
+        memo.update(x=x, quant=quant)
+        z, memo = self.decode(quant, memo)
+        memo['loss'] = get_memo(memo, 'loss')
+        return z, x.new_zeros([]), memo
