@@ -1,0 +1,132 @@
+"""Host-side logic that needs no GPU: registries/configs, state-dict key compatibility, loss term tables,
+callback dispatch order, key packing, failure modes."""
+import pytest
+import torch
+
+import vector_quantization_b200 as vqb
+from vector_quantization_b200 import parallel
+from vector_quantization_b200.callbacks import BaseCallback, ComposedCallback
+
+
+def emb(K, D):
+    return dict(type='torch_nn_modules_sparse_Embedding', num_embeddings=K, embedding_dim=D)
+
+
+VQGAN = dict(type='VQGANQuantizer', embedding=emb(64, 8), distance=dict(type='L2Distance'),
+             losses=dict(vqgan_loss=dict(type='VQGANLoss')), init_weights=dict(type='vqgan'))
+VQKD = dict(type='VQKDQuantizer', embedding=emb(64, 8), distance=dict(type='CosineDistance'),
+            callbacks=[dict(type='VQKDCallback', ema=dict())],
+            losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True))))
+CLUSTER = dict(type='VQGANQuantizer', embedding=emb(64, 8), distance=dict(type='CosineDistance'),
+               callbacks=[dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='NearestAnchor', sync=True))],
+               losses=dict(vqgan_loss=dict(type='CodebookLoss')), init_weights=dict(type='vqgan'))
+
+
+def test_registry_names_of_the_reference_are_all_present():
+    R = vqb.registry
+    for n in ('VectorQuantizer', 'VQGANQuantizer', 'VQKDQuantizer', 'FiniteScalarQuantizer', 'ScalarQuantizer'):
+        assert n in R.VQITQuantizerRegistry
+    for n in ('ComposedCallback', 'NormalizeCallback', 'CVQVAECallback', 'VQKDCallback'):
+        assert n in R.VQITQuantizerCallbackRegistry
+    for n in ('CodebookLoss', 'CommitmentLoss', 'VQGANLoss', 'EntropyLoss'):
+        assert n in R.VQITQuantizerLossRegistry
+    for n in ('L2Distance', 'CosineDistance'):
+        assert n in R.VQITQuantizerDistanceRegistry
+    for n in ('NearestAnchor', 'MultinomialAnchor', 'CachedAnchor'):
+        assert n in R.AnchorRegistry
+
+
+def test_state_dict_keys_match_reference_checkpoints():
+    # tools/convert_checkpoints.py:239-243 (VQGAN) and :321-322 (VQ-KD) in the reference
+    q = vqb.build_quantizer(VQGAN)
+    assert set(q.state_dict()) == {
+        '_embedding.weight', '_losses.vqgan_loss._weight._steps', '_losses.vqgan_loss._codebook._weight._steps',
+        '_losses.vqgan_loss._codebook._mse._weight._steps', '_losses.vqgan_loss._commitment._weight._steps',
+        '_losses.vqgan_loss._commitment._mse._weight._steps'}
+    q = vqb.build_quantizer(VQKD)
+    assert set(q.state_dict()) == {'_embedding.weight', '_losses.commitment_loss._weight._steps',
+                                   '_losses.commitment_loss._mse._weight._steps'}
+    q = vqb.build_quantizer(CLUSTER)
+    assert '_probability' in q.state_dict() and q.state_dict()['_probability'].shape == (64,)
+    q = vqb.build_quantizer(dict(type='FiniteScalarQuantizer', num_scalars_per_channel=[8, 8, 8, 5, 5, 5]))
+    assert list(q.state_dict()) == ['_embeddings'] and q.codebook_size == 64000 and q.embedding_dim == 6
+
+
+def test_vqgan_init_is_uniform_pm_one_over_k():
+    q = vqb.build_quantizer(VQGAN)
+    w = q.embedding.weight
+    assert float(w.abs().max()) <= 1 / 64 and float(w.std()) > 0
+
+
+def test_loss_term_tables():
+    q = vqb.build_quantizer(VQGAN)
+    assert q._losses['vqgan_loss'].terms() == {0: 1.0, 1: 0.25}       # codebook + 0.25 * commitment
+    q = vqb.build_quantizer(VQKD)
+    assert q._losses['commitment_loss'].terms() == {3: 1.0} and q._loss_terms() is True
+    q = vqb.build_quantizer(CLUSTER)
+    assert q._losses['vqgan_loss'].terms() == {0: 1.0}
+    mse4 = torch.tensor([2.0, 2.0, 8.0, 8.0])
+    q = vqb.build_quantizer(dict(VQGAN, losses=dict(l=dict(type='VQGANLoss', beta=0.5))))
+    assert float(q._losses['l'].from_mse4(mse4)) == 3.0
+
+
+def test_callback_flags_and_lazy_init_hook():
+    q = vqb.build_quantizer(VQKD)
+    assert len(q._forward_pre_hooks) == 1 and not q._callbacks.needs_column_nearest
+    q = vqb.build_quantizer(CLUSTER)
+    assert q._callbacks.needs_column_nearest and q._callbacks.column_nearest_global
+    q = vqb.build_quantizer(dict(CLUSTER, callbacks=[dict(type='CVQVAECallback', ema=dict(decay=0.9),
+                                                          anchor=dict(type='NearestAnchor'))]))
+    assert not q._callbacks.column_nearest_global
+    assert next(iter(q._callbacks))._ema.decay == 0.9
+
+
+def test_composed_callback_priority_order():
+    calls = []
+
+    class A(BaseCallback):
+        def before_encode(self, x, memo):
+            calls.append('A')
+            return x
+
+    class B(BaseCallback):
+        def before_encode(self, x, memo):
+            calls.append('B')
+            return x
+
+    cc = ComposedCallback(priorities=[dict(), dict(before_encode=5)], callbacks=[A(), B()])
+    cc.before_encode(torch.zeros(1), {})
+    assert calls == ['B', 'A'] and cc.overrides('before_encode') and not cc.overrides('after_loss')
+
+
+def test_unsupported_components_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        vqb.L2Distance()(torch.zeros(2, 2), torch.zeros(2, 2))
+    q = vqb.build_quantizer(VQGAN)
+    with pytest.raises(vqb._lib.VQBError):          # CPU tensors: no fallback
+        q(torch.zeros(4, 8), {})
+    with pytest.raises(vqb._lib.VQBError):
+        vqb.ops.pack_rows(torch.zeros(4, 8))
+
+
+def test_key_packing_orders_like_the_device_keys():
+    s = torch.tensor([-3.5, -0.0, 0.0, 1e-30, 0.25, 7.0, float('inf'), -float('inf')])
+    idx = torch.arange(8)
+    k = parallel.pack_keys_host(s, idx)
+    # smaller key == better: compare as unsigned
+    ku = [(int(v) + (1 << 64)) % (1 << 64) for v in k]
+    order = sorted(range(8), key=lambda i: ku[i])
+    assert [float(s[i]) for i in order][:2] == [float('inf'), 7.0] and order[-1] == 7
+    # equal scores: lower index wins
+    k2 = parallel.pack_keys_host(torch.tensor([1.0, 1.0]), torch.tensor([9, 3]))
+    ku2 = [(int(v) + (1 << 64)) % (1 << 64) for v in k2]
+    assert ku2[1] < ku2[0]
+    sc, ix = parallel.unpack_keys_host(k)
+    assert torch.equal(ix, idx) and torch.equal(sc[[0, 4, 5]], s[[0, 4, 5]])
+
+
+def test_shard_range_covers_everything_once():
+    for total, w in ((262144, 8), (1000, 3), (5, 8)):
+        spans = [parallel.shard_range(total, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

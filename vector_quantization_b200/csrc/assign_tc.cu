@@ -144,16 +144,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogue helper: arg-max over a 32-column chunk held in registers
+// epilogue helpers
 // ---------------------------------------------------------------------------------------------
-template <bool USE_SIDE>
-__device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], const float* __restrict__ side,
-                                             uint32_t col_base, int n_valid, float& best, uint32_t& best_idx) {
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// arg-max over a 32-column chunk held in registers.  USE_SIDE: score = acc - side[col] (L2);
+// MASK: columns >= n_valid (zero-padded operand rows of the last code tile) are excluded.
+template <bool USE_SIDE, bool MASK>
+__device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t side_saddr, uint32_t col_base,
+                                             int n_valid, float& best, uint32_t& best_idx) {
   float s[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     if constexpr (USE_SIDE) {
-      const float4 h = *reinterpret_cast<const float4*>(side + j);  // warp-wide broadcast
+      const float4 h = lds128(side_saddr + j * 4);  // warp-wide broadcast
       s[j] = __uint_as_float(r[j]) - h.x;
       s[j + 1] = __uint_as_float(r[j + 1]) - h.y;
       s[j + 2] = __uint_as_float(r[j + 2]) - h.z;
@@ -165,7 +173,7 @@ __device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], const floa
       s[j + 3] = __uint_as_float(r[j + 3]);
     }
   }
-  if (n_valid < 32) {  // last, partial code tile (warp-uniform): zero-padded operand rows must not win
+  if constexpr (MASK) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j >= n_valid) s[j] = -INFINITY;
@@ -186,20 +194,53 @@ __device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], const floa
   }
 }
 
+// One 128-column half of a 128 x 256 accumulator: four 32-column chunks, TMEM loads double-buffered so
+// that the load of chunk c+1 is in flight while chunk c is reduced.  The accumulator is released to the
+// MMA warp as soon as the last load has landed in registers.
+template <bool USE_SIDE, bool MASK>
+__device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr, uint32_t gcol0, int64_t b_rows,
+                                            uint64_t* tmem_empty_bar, int lane, float& best, uint32_t& best_idx) {
+  uint32_t ra[32], rb[32];
+  auto nv = [&](int c) -> int {
+    if constexpr (!MASK) return 32;
+    const int64_t left = b_rows - (int64_t)(gcol0 + 32 * c);
+    return left >= 32 ? 32 : (left < 0 ? 0 : (int)left);
+  };
+  tmem_ld32(taddr, ra);
+  tmem_ld_wait(ra);
+  tmem_ld32(taddr + 32, rb);
+  chunk_argmax<USE_SIDE, MASK>(ra, side_saddr, gcol0, nv(0), best, best_idx);
+  tmem_ld_wait(rb);
+  tmem_ld32(taddr + 64, ra);
+  chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), best, best_idx);
+  tmem_ld_wait(ra);
+  tmem_ld32(taddr + 96, rb);
+  chunk_argmax<USE_SIDE, MASK>(ra, side_saddr + 256, gcol0 + 64, nv(2), best, best_idx);
+  tmem_ld_wait(rb);
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tmem_empty_bar);  // all four loads are in registers: TMEM buffer is free
+  chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 384, gcol0 + 96, nv(3), best, best_idx);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BK>
+// WHOLE = true : one pipeline stage holds every operand plane of one (row tile, code tile) work item
+//                (Dp == BK <= 64): one barrier wait, all term MMAs back to back, two commits per tile.
+// WHOLE = false: classic k-blocked ring, one stage = one BK-wide slab of one plane pair (large D).
+template <int BK, bool WHOLE>
 __global__ void __launch_bounds__(kThreads, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const TermTable terms, int kblocks, int nstages, int64_t a_rows, int64_t a_rows_pad,
-                 int64_t b_rows, int64_t b_rows_pad, const float* __restrict__ b_half_sqnorm, int64_t b_index_offset,
-                 unsigned long long* __restrict__ keys) {
+                 const __grid_constant__ TermTable terms, int pa, int pb, int kblocks, int nstages, int64_t a_rows,
+                 int64_t a_rows_pad, int64_t b_rows, int64_t b_rows_pad, const float* __restrict__ b_half_sqnorm,
+                 int64_t b_index_offset, unsigned long long* __restrict__ keys) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
-  // carve: [stages][A|B] | side[2][256] | barriers | tmem ptr        (base re-aligned to 1024 B)
+  constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
+  const uint32_t stage_bytes = WHOLE ? (uint32_t)pa * kABytes + (uint32_t)pb * kBBytes : kABytes + kBBytes;
+  // carve: [stages] | side[2][256] | barriers | tmem ptr        (base re-aligned to 1024 B)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* side_smem = reinterpret_cast<float*>(smem + (size_t)nstages * kStageBytes);
+  float* side_smem = reinterpret_cast<float*>(smem + (size_t)nstages * stage_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(side_smem + 2 * BN);
   uint64_t* empty_bar = full_bar + nstages;
   uint64_t* tmem_full = empty_bar + nstages;
@@ -210,7 +251,6 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int64_t a_tiles = (a_rows + BM - 1) / BM, b_tiles = (b_rows + BN - 1) / BN;
   const int64_t total = a_tiles * b_tiles;
   const int64_t t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
-  const int nv = terms.n * kblocks;  // virtual k-blocks per tile
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -232,24 +272,39 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one thread) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int64_t at = t0 / b_tiles, bt = t0 - at * b_tiles;
       for (int64_t t = t0; t < t1; ++t) {
-        const int64_t at = t / b_tiles, bt = t - at * b_tiles;
-        for (int v = 0; v < nv; ++v) {
-          const int term = v / kblocks, kb = v - term * kblocks;
+        const int a_row = (int)(at * BM), b_row = (int)(bt * BN);
+        if constexpr (WHOLE) {
           mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_arrive_expect_tx(full_bar + stage, kStageBytes);
-          uint8_t* sa = smem + (size_t)stage * kStageBytes;
-          tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, (int)(terms.a[term] * a_rows_pad + at * BM));
-          tma_load_2d(sa + kABytes, &tmap_b, full_bar + stage, kb * BK, (int)(terms.b[term] * b_rows_pad + bt * BN));
-          if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1;
+          mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          for (int p = 0; p < pa; ++p)
+            tma_load_2d(sa + p * kABytes, &tmap_a, full_bar + stage, 0, (int)(p * a_rows_pad) + a_row);
+          uint8_t* sb = sa + pa * kABytes;
+          for (int p = 0; p < pb; ++p)
+            tma_load_2d(sb + p * kBBytes, &tmap_b, full_bar + stage, 0, (int)(p * b_rows_pad) + b_row);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        } else {
+#pragma unroll 1
+          for (int term = 0; term < terms.n; ++term) {
+            const int arow = (int)(terms.a[term] * a_rows_pad) + a_row, brow = (int)(terms.b[term] * b_rows_pad) + b_row;
+#pragma unroll 1
+            for (int kb = 0; kb < kblocks; ++kb) {
+              mbar_wait(empty_bar + stage, phase ^ 1);
+              mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
+              uint8_t* sa = smem + (size_t)stage * stage_bytes;
+              tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, arow);
+              tma_load_2d(sa + kABytes, &tmap_b, full_bar + stage, kb * BK, brow);
+              if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
           }
         }
+        if (++bt == b_tiles) { bt = 0; ++at; }
       }
     }
   } else if (warp == 1) {
@@ -257,6 +312,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=256, M=128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int64_t local = 0;
@@ -266,20 +322,36 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(tmem_empty + buf, (use & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
-        for (int v = 0; v < nv; ++v) {
+        if constexpr (WHOLE) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes);
-          const uint64_t adesc = make_smem_desc<BK>(sa), bdesc = make_smem_desc<BK>(sa + kABytes);
+          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t sb = sa + (uint32_t)pa * kABytes;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (v | k) != 0);
+          for (int term = 0; term < kMaxTerms; ++term) {
+            if (term < terms.n) {
+              const uint64_t adesc = make_smem_desc<BK>(sa + (uint32_t)terms.a[term] * kABytes);
+              const uint64_t bdesc = make_smem_desc<BK>(sb + (uint32_t)terms.b[term] * kBBytes);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (term | k) != 0);
+            }
           }
           umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
-          if (++stage == nstages) {
-            stage = 0;
-            phase ^= 1;
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        } else {
+          const int nv = terms.n * kblocks;
+#pragma unroll 1
+          for (int v = 0; v < nv; ++v) {
+            mbar_wait(full_bar + stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+            const uint64_t adesc = make_smem_desc<BK>(sa), bdesc = make_smem_desc<BK>(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (v | k) != 0);
+            umma_commit(empty_bar + stage);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
         umma_commit(tmem_full + buf);  // accumulator complete -> epilogue
@@ -292,6 +364,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = ew >> 2;       // 128-column half of the accumulator
     const int etid = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const bool use_side = b_half_sqnorm != nullptr;  // uniform for the whole launch
+    const uint32_t side_base = smem_u32(side_smem);
     float best = -INFINITY;
     uint32_t best_idx = 0xffffffffu;
     int64_t cur_at = -1;
@@ -301,8 +375,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (cur_at >= 0 && row < a_rows && best_idx != 0xffffffffu)
         atomicMin(keys + row, make_key(best, best_idx + (uint32_t)b_index_offset));
     };
+    int64_t at = t0 / b_tiles, bt = t0 - at * b_tiles;
     for (int64_t t = t0; t < t1; ++t, ++local) {
-      const int64_t at = t / b_tiles, bt = t - at * b_tiles;
       if (at != cur_at) {
         flush();
         cur_at = at;
@@ -311,34 +385,27 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       const int buf = (int)(local & 1);
       const uint32_t use = (uint32_t)(local >> 1);
-      const bool use_side = b_half_sqnorm != nullptr;  // uniform for the whole launch
-      float* side = side_smem + buf * BN;
       if (use_side) {
         // 256 epilogue threads <-> 256 codes of this tile (the side vector is padded to rows_pad with +inf).
         // The barrier also orders "everyone finished the tile that used this buffer two tiles ago".
-        side[etid] = __ldg(b_half_sqnorm + bt * BN + etid);
+        side_smem[buf * BN + etid] = __ldg(b_half_sqnorm + bt * BN + etid);
         named_bar_sync(1, kEpiThreads);
       }
       mbar_wait(tmem_full + buf, use & 1);
       tc_fence_after();
       const uint32_t col0 = (uint32_t)(half * 128);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        const uint32_t col = col0 + (uint32_t)c * 32;
-        tmem_ld32(tmem_base + lane_addr + (uint32_t)buf * BN + col, r);
-        tmem_ld_wait(r);
-        const uint32_t gcol = (uint32_t)(bt * BN) + col;
-        const int64_t left = b_rows - (int64_t)gcol;
-        const int n_valid = left >= 32 ? 32 : (left < 0 ? 0 : (int)left);
-        if (use_side)
-          chunk_argmax<true>(r, side + col, gcol, n_valid, best, best_idx);
-        else
-          chunk_argmax<false>(r, side + col, gcol, n_valid, best, best_idx);
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * BN + col0;
+      const uint32_t side_saddr = side_base + (uint32_t)(buf * BN + col0) * 4;
+      const uint32_t gcol0 = (uint32_t)(bt * BN) + col0;
+      const bool partial = (bt + 1) * BN > b_rows;
+      if (!partial) {
+        if (use_side) tile_argmax<true, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, best, best_idx);
+        else tile_argmax<false, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, best, best_idx);
+      } else {
+        if (use_side) tile_argmax<true, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, best, best_idx);
+        else tile_argmax<false, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, best, best_idx);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + buf);
+      if (++bt == b_tiles) { bt = 0; ++at; }
     }
     flush();
   }
@@ -411,28 +478,28 @@ static TermTable make_terms(int pa, int pb) {
   return t;
 }
 
-template <int BK>
+template <int BK, bool WHOLE>
 static int launch(const void* a_planes, int pa, int64_t a_rows, const void* b_planes, int pb, int64_t b_rows, int Dp,
                   const float* h, int64_t off, unsigned long long* keys, cudaStream_t st) {
   const int64_t a_pad = vqb_operand_rows_pad(a_rows), b_pad = vqb_operand_rows_pad(b_rows);
   CUtensorMap ma, mb;
   if (int e = make_operand_map(&ma, a_planes, pa * a_pad, Dp, BK, BM)) return e;
   if (int e = make_operand_map(&mb, b_planes, pb * b_pad, Dp, BK, BN)) return e;
-  constexpr uint32_t stage_bytes = (BM + BN) * BK * 2;
+  const uint32_t stage_bytes = WHOLE ? (uint32_t)(pa * BM + pb * BN) * BK * 2 : (uint32_t)(BM + BN) * BK * 2;
   int nstages = (int)(196608 / stage_bytes);
   if (nstages > 8) nstages = 8;
   const size_t smem_bytes = 1024 + (size_t)nstages * stage_bytes + 2 * BN * sizeof(float) + (2 * nstages + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    VQB_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<BK, WHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const TermTable terms = make_terms(pa, pb);
   const int64_t total = ((a_rows + BM - 1) / BM) * ((b_rows + BN - 1) / BN);
   int grid = sm_count();
   if (total < grid) grid = (int)total;
-  assign_tc_kernel<BK><<<grid, kThreads, smem_bytes, st>>>(ma, mb, terms, Dp / BK, nstages, a_rows, a_pad, b_rows,
-                                                           b_pad, h, off, keys);
+  assign_tc_kernel<BK, WHOLE><<<grid, kThreads, smem_bytes, st>>>(ma, mb, terms, pa, pb, Dp / BK, nstages, a_rows, a_pad,
+                                                                  b_rows, b_pad, h, off, keys);
   VQB_LAUNCH_OK();
   return VQB_OK;
 }
@@ -440,9 +507,14 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, const void* b_pl
 int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, const void* b_planes, int pb, int64_t b_rows,
                      int D, const float* h, int64_t off, unsigned long long* keys, cudaStream_t st) {
   const int Dp = (int)vqb_operand_dp(D);
-  if (Dp == 16) return launch<16>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st);
-  if (Dp == 32) return launch<32>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st);
-  return launch<64>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st);
+  // whole-tile stages need at least a double buffer of all planes of one work item in shared memory
+  const bool whole = Dp <= 64 && (size_t)(pa * BM + pb * BN) * Dp * 2 * 2 <= 196608;
+#define VQB_LAUNCH(BK_, W_) return launch<BK_, W_>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st)
+  if (Dp == 16) { if (whole) VQB_LAUNCH(16, true); VQB_LAUNCH(16, false); }
+  if (Dp == 32) { if (whole) VQB_LAUNCH(32, true); VQB_LAUNCH(32, false); }
+  if (whole) VQB_LAUNCH(64, true);
+  VQB_LAUNCH(64, false);
+#undef VQB_LAUNCH
 }
 
 }  // namespace vqb

@@ -66,3 +66,24 @@ def shard_range(total: int, r: int | None = None, w: int | None = None) -> tuple
     per = (total + w - 1) // w
     lo = min(total, r * per)
     return lo, min(total, lo + per)
+
+
+# ---- host-side mirror of the device key packing (csrc/common.cuh make_key); used by the gloo tests -------
+def pack_keys_host(score: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """int64 tensor holding (~orderable(score) << 32) | index, bit-identical to the kernels' keys."""
+    u = score.to(torch.float32).view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    neg = (u >> 31) & 1
+    o = torch.where(neg.bool(), (~u) & 0xFFFFFFFF, u | 0x80000000)
+    hi = (~o) & 0xFFFFFFFF
+    packed = (hi << 32) | (index.to(torch.int64) & 0xFFFFFFFF)
+    return packed  # bit 63 may be set: the int64 is the two's-complement view of the uint64 key
+
+
+def unpack_keys_host(keys: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    idx = keys & 0xFFFFFFFF
+    o = (~(keys >> 32)) & 0xFFFFFFFF
+    neg = ((o >> 31) & 1) == 0
+    u = torch.where(neg, (~o) & 0xFFFFFFFF, o & 0x7FFFFFFF)
+    score = u.to(torch.int32 if False else torch.int64)
+    score = torch.where(score >= 2 ** 31, score - 2 ** 32, score).to(torch.int32).view(torch.float32)
+    return score, idx
