@@ -33,7 +33,10 @@ cases = [  # name, N, K, D, metric, x dtype, planes_x, planes_e
     ('cfg5/8 cos D768 1x1', 65536, 32768, 768, 'cos', torch.bfloat16, 1, 1),
 ]
 out = []
+flt = sys.argv[1] if len(sys.argv) > 1 else ''
 for name, N, K, D, metric, dt, px, pe in cases:
+    if flt not in name:
+        continue
     x = torch.randn(N, D, device=dev).to(dt)
     E = torch.randn(K, D, device=dev)
     cos = metric == 'cos'

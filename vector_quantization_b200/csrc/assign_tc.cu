@@ -14,6 +14,7 @@
 //                            (warp-2)/4 the 128-column half of the 256-wide accumulator).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -22,8 +23,6 @@ namespace vqb {
 constexpr int BM = 128;           // rows per tile (UMMA M)
 constexpr int BN = 256;           // codes per tile (UMMA N)
 constexpr int UMMA_K = 16;        // bf16
-constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
 constexpr int kMaxTerms = 6;
 constexpr uint32_t kTmemCols = 512;  // two 256-column accumulators
 
@@ -152,11 +151,34 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
-// arg-max over a 32-column chunk held in registers.  USE_SIDE: score = acc - side[col] (L2);
-// MASK: columns >= n_valid (zero-padded operand rows of the last code tile) are excluded.
+// Predicated 128-byte stash of one thread's 32 chunk scores: shared layout [8 float4][32 lanes] per warp
+// (lane-contiguous 16 B => conflict-free); only lanes whose running best just improved store.
+__device__ __forceinline__ void stash_chunk(uint32_t pred, uint32_t saddr, const float (&s)[32]) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
+      "@p st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n\t"
+      "@p st.shared.v4.f32 [%1+512], {%6, %7, %8, %9};\n\t"
+      "@p st.shared.v4.f32 [%1+1024], {%10, %11, %12, %13};\n\t"
+      "@p st.shared.v4.f32 [%1+1536], {%14, %15, %16, %17};\n\t"
+      "@p st.shared.v4.f32 [%1+2048], {%18, %19, %20, %21};\n\t"
+      "@p st.shared.v4.f32 [%1+2560], {%22, %23, %24, %25};\n\t"
+      "@p st.shared.v4.f32 [%1+3072], {%26, %27, %28, %29};\n\t"
+      "@p st.shared.v4.f32 [%1+3584], {%30, %31, %32, %33};\n\t}"
+      ::"r"(pred), "r"(saddr), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]), "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7]),
+      "f"(s[8]), "f"(s[9]), "f"(s[10]), "f"(s[11]), "f"(s[12]), "f"(s[13]), "f"(s[14]), "f"(s[15]), "f"(s[16]),
+      "f"(s[17]), "f"(s[18]), "f"(s[19]), "f"(s[20]), "f"(s[21]), "f"(s[22]), "f"(s[23]), "f"(s[24]), "f"(s[25]),
+      "f"(s[26]), "f"(s[27]), "f"(s[28]), "f"(s[29]), "f"(s[30]), "f"(s[31])
+      : "memory");
+}
+
+// Branch-free running arg-max over a 32-column chunk held in registers: the thread keeps only
+// (best score, first column of the chunk that produced it) and stashes that chunk's 32 scores; the
+// position inside the chunk is resolved once per row tile at flush time (resolve_index).
+// USE_SIDE: score = acc - side[col] (L2);  MASK: columns >= n_valid (zero-padded rows of the last code
+// tile) are excluded.
 template <bool USE_SIDE, bool MASK>
 __device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t side_saddr, uint32_t col_base,
-                                             int n_valid, float& best, uint32_t& best_idx) {
+                                             int n_valid, uint32_t stash_saddr, float& best, uint32_t& best_col) {
   float s[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -184,43 +206,116 @@ __device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t s
   m[10] = fmaxf(s[30], s[31]);
   const float m0 = fmax3(m[0], m[1], m[2]), m1 = fmax3(m[3], m[4], m[5]), m2 = fmax3(m[6], m[7], m[8]);
   const float mx = fmax3(fmax3(m0, m1, m2), m[9], m[10]);
-  if (mx > best) {  // strict: an equal score later in the scan never displaces a lower index
-    int j = 31;
-#pragma unroll
-    for (int jj = 30; jj >= 0; --jj)
-      if (s[jj] == mx) j = jj;
-    best = mx;
-    best_idx = col_base + (uint32_t)j;
-  }
+  const bool better = mx > best;  // strict: an equal score later in the scan never displaces an earlier chunk
+  best = fmaxf(best, mx);
+  best_col = better ? col_base : best_col;
+  // warp-uniform skip: after the first few code tiles most chunks improve no row of the warp
+  if (__any_sync(0xffffffffu, better)) stash_chunk((uint32_t)better, stash_saddr, s);
 }
 
-// One 128-column half of a 128 x 256 accumulator: four 32-column chunks, TMEM loads double-buffered so
-// that the load of chunk c+1 is in flight while chunk c is reduced.  The accumulator is released to the
-// MMA warp as soon as the last load has landed in registers.
-template <bool USE_SIDE, bool MASK>
-__device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr, uint32_t gcol0, int64_t b_rows,
-                                            uint64_t* tmem_empty_bar, int lane, float& best, uint32_t& best_idx) {
+// first position of `best` inside the stashed winning chunk (lowest index wins ties, like torch.argmin)
+__device__ __forceinline__ uint32_t resolve_index(uint32_t stash_saddr, float best) {
+  int j = 31;
+#pragma unroll
+  for (int q = 7; q >= 0; --q) {
+    const float4 v = lds128(stash_saddr + q * 512);
+    if (v.w == best) j = 4 * q + 3;
+    if (v.z == best) j = 4 * q + 2;
+    if (v.y == best) j = 4 * q + 1;
+    if (v.x == best) j = 4 * q;
+  }
+  return (uint32_t)j;
+}
+
+// One warp's NCH x 32 columns of a 128 x 256 accumulator; TMEM loads are double-buffered so that the load
+// of chunk c+1 is in flight while chunk c is reduced.  The accumulator is released to the MMA warp as soon
+// as the last load has landed in registers.
+template <bool USE_SIDE, bool MASK, int NCH>
+__device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr, uint32_t gcol0, int b_rows,
+                                            uint64_t* tmem_empty_bar, int lane, uint32_t stash_saddr, float& best,
+                                            uint32_t& best_col) {
   uint32_t ra[32], rb[32];
   auto nv = [&](int c) -> int {
     if constexpr (!MASK) return 32;
-    const int64_t left = b_rows - (int64_t)(gcol0 + 32 * c);
-    return left >= 32 ? 32 : (left < 0 ? 0 : (int)left);
+    const int left = b_rows - (int)(gcol0 + 32 * c);
+    return left >= 32 ? 32 : (left < 0 ? 0 : left);
+  };
+  auto release = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar);  // every load of this warp is in registers
   };
   tmem_ld32(taddr, ra);
   tmem_ld_wait(ra);
   tmem_ld32(taddr + 32, rb);
-  chunk_argmax<USE_SIDE, MASK>(ra, side_saddr, gcol0, nv(0), best, best_idx);
+  chunk_argmax<USE_SIDE, MASK>(ra, side_saddr, gcol0, nv(0), stash_saddr, best, best_col);
   tmem_ld_wait(rb);
-  tmem_ld32(taddr + 64, ra);
-  chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), best, best_idx);
-  tmem_ld_wait(ra);
-  tmem_ld32(taddr + 96, rb);
-  chunk_argmax<USE_SIDE, MASK>(ra, side_saddr + 256, gcol0 + 64, nv(2), best, best_idx);
-  tmem_ld_wait(rb);
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(tmem_empty_bar);  // all four loads are in registers: TMEM buffer is free
-  chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 384, gcol0 + 96, nv(3), best, best_idx);
+  if constexpr (NCH == 2) {
+    release();
+    chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), stash_saddr, best, best_col);
+  } else {
+    tmem_ld32(taddr + 64, ra);
+    chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), stash_saddr, best, best_col);
+    tmem_ld_wait(ra);
+    tmem_ld32(taddr + 96, rb);
+    chunk_argmax<USE_SIDE, MASK>(ra, side_saddr + 256, gcol0 + 64, nv(2), stash_saddr, best, best_col);
+    tmem_ld_wait(rb);
+    release();
+    chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 384, gcol0 + 96, nv(3), stash_saddr, best, best_col);
+  }
+}
+
+// Epilogue role: NEW warps; warp%4 selects the TMEM lane quarter, (warp-2)/4 the column slice.
+template <bool USE_SIDE, int NEW>
+__device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_base, uint8_t* stash_smem,
+                                              float* side_smem, uint64_t* tmem_full, uint64_t* tmem_empty, int t0,
+                                              int t1, int b_tiles, int a_rows, int b_rows,
+                                              const float* __restrict__ b_half_sqnorm, uint32_t b_index_offset,
+                                              unsigned long long* __restrict__ keys) {
+  constexpr int NCH = 8 / (NEW / 4);           // 32-column chunks per warp per tile: 4 (8 warps) or 2 (16 warps)
+  const int ew = warp - 2;
+  const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32): the only ones this warp may read
+  const uint32_t col0 = (uint32_t)(ew >> 2) * (NCH * 32);
+  const int etid = threadIdx.x - 64;
+  const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
+  const uint32_t side_base = smem_u32(side_smem) + col0 * 4;
+  const uint32_t stash_saddr = smem_u32(stash_smem) + (uint32_t)ew * 4096 + (uint32_t)lane * 16;
+  const int row_in_tile = quarter * 32 + lane;
+  const bool last_partial = b_tiles * BN > b_rows;
+  float best = -INFINITY;
+  uint32_t best_col = 0xffffffffu;
+  int at = t0 / b_tiles, bt = t0 - at * b_tiles;
+  uint32_t buf = 0, par0 = 0, par1 = 0;        // accumulator buffer and its per-buffer phase parity
+  for (int t = t0; t < t1; ++t) {
+    if constexpr (USE_SIDE) {
+      // NEW*32 epilogue threads stage the 256 side terms of this code tile (vector padded to rows_pad with +inf).
+      // The barrier also orders "everyone finished the tile that used this buffer two tiles ago".
+      if (etid < BN) side_smem[buf * BN + etid] = __ldg(b_half_sqnorm + bt * BN + etid);
+      named_bar_sync(1, NEW * 32);
+    }
+    mbar_wait(tmem_full + buf, buf ? par1 : par0);
+    tc_fence_after();
+    const uint32_t taddr = taddr0 + buf * BN;
+    const uint32_t side_saddr = side_base + buf * (BN * 4);
+    const uint32_t gcol0 = (uint32_t)(bt * BN) + col0;
+    if (last_partial && bt == b_tiles - 1)
+      tile_argmax<USE_SIDE, true, NCH>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+    else
+      tile_argmax<USE_SIDE, false, NCH>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+    if (buf) par1 ^= 1; else par0 ^= 1;
+    buf ^= 1;
+    if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish
+      const int row = at * BM + row_in_tile;
+      if (row < a_rows && best_col != 0xffffffffu) {
+        const uint32_t idx = best_col + resolve_index(stash_saddr, best);
+        atomicMin(keys + row, make_key(best, idx + b_index_offset));
+      }
+      best = -INFINITY;
+      best_col = 0xffffffffu;
+      bt = 0;
+      ++at;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -229,8 +324,8 @@ __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr,
 // WHOLE = true : one pipeline stage holds every operand plane of one (row tile, code tile) work item
 //                (Dp == BK <= 64): one barrier wait, all term MMAs back to back, two commits per tile.
 // WHOLE = false: classic k-blocked ring, one stage = one BK-wide slab of one plane pair (large D).
-template <int BK, bool WHOLE>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BK, bool WHOLE, int NEW>
+__global__ void __launch_bounds__(64 + NEW * 32, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ TermTable terms, int pa, int pb, int kblocks, int nstages, int64_t a_rows,
                  int64_t a_rows_pad, int64_t b_rows, int64_t b_rows_pad, const float* __restrict__ b_half_sqnorm,
@@ -238,9 +333,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
   const uint32_t stage_bytes = WHOLE ? (uint32_t)pa * kABytes + (uint32_t)pb * kBBytes : kABytes + kBBytes;
-  // carve: [stages] | side[2][256] | barriers | tmem ptr        (base re-aligned to 1024 B)
+  // carve: [stages] | stash[NEW warps][4 KB] | side[2][256] | barriers | tmem ptr   (base re-aligned to 1024 B)
+  constexpr uint32_t kStashBytes = NEW * 4096;  // winning-chunk stash: [warp][8 float4][32 lanes]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* side_smem = reinterpret_cast<float*>(smem + (size_t)nstages * stage_bytes);
+  uint8_t* stash_smem = smem + (size_t)nstages * stage_bytes;
+  float* side_smem = reinterpret_cast<float*>(stash_smem + kStashBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(side_smem + 2 * BN);
   uint64_t* empty_bar = full_bar + nstages;
   uint64_t* tmem_full = empty_bar + nstages;
@@ -261,7 +358,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, kEpiThreads / 32);
+      mbar_init(tmem_empty + i, NEW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -359,55 +456,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue: fused arg-max =====================
-    const int ew = warp - 2;
-    const int quarter = warp & 3;   // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
-    const int half = ew >> 2;       // 128-column half of the accumulator
-    const int etid = threadIdx.x - 64;
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const bool use_side = b_half_sqnorm != nullptr;  // uniform for the whole launch
-    const uint32_t side_base = smem_u32(side_smem);
-    float best = -INFINITY;
-    uint32_t best_idx = 0xffffffffu;
-    int64_t cur_at = -1;
-    int64_t local = 0;
-    auto flush = [&]() {
-      const int64_t row = cur_at * BM + quarter * 32 + lane;
-      if (cur_at >= 0 && row < a_rows && best_idx != 0xffffffffu)
-        atomicMin(keys + row, make_key(best, best_idx + (uint32_t)b_index_offset));
-    };
-    int64_t at = t0 / b_tiles, bt = t0 - at * b_tiles;
-    for (int64_t t = t0; t < t1; ++t, ++local) {
-      if (at != cur_at) {
-        flush();
-        cur_at = at;
-        best = -INFINITY;
-        best_idx = 0xffffffffu;
-      }
-      const int buf = (int)(local & 1);
-      const uint32_t use = (uint32_t)(local >> 1);
-      if (use_side) {
-        // 256 epilogue threads <-> 256 codes of this tile (the side vector is padded to rows_pad with +inf).
-        // The barrier also orders "everyone finished the tile that used this buffer two tiles ago".
-        side_smem[buf * BN + etid] = __ldg(b_half_sqnorm + bt * BN + etid);
-        named_bar_sync(1, kEpiThreads);
-      }
-      mbar_wait(tmem_full + buf, use & 1);
-      tc_fence_after();
-      const uint32_t col0 = (uint32_t)(half * 128);
-      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * BN + col0;
-      const uint32_t side_saddr = side_base + (uint32_t)(buf * BN + col0) * 4;
-      const uint32_t gcol0 = (uint32_t)(bt * BN) + col0;
-      const bool partial = (bt + 1) * BN > b_rows;
-      if (!partial) {
-        if (use_side) tile_argmax<true, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, best, best_idx);
-        else tile_argmax<false, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, best, best_idx);
-      } else {
-        if (use_side) tile_argmax<true, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, best, best_idx);
-        else tile_argmax<false, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, best, best_idx);
-      }
-      if (++bt == b_tiles) { bt = 0; ++at; }
-    }
-    flush();
+    if (b_half_sqnorm != nullptr)
+      epilogue_loop<true, NEW>(warp, lane, tmem_base, stash_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,
+                               (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys);
+    else
+      epilogue_loop<false, NEW>(warp, lane, tmem_base, stash_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,
+                                (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys);
   }
 
   tc_fence_before();
@@ -478,27 +532,28 @@ static TermTable make_terms(int pa, int pb) {
   return t;
 }
 
-template <int BK, bool WHOLE>
+template <int BK, bool WHOLE, int NEW>
 static int launch(const void* a_planes, int pa, int64_t a_rows, const void* b_planes, int pb, int64_t b_rows, int Dp,
                   const float* h, int64_t off, unsigned long long* keys, cudaStream_t st) {
   const int64_t a_pad = vqb_operand_rows_pad(a_rows), b_pad = vqb_operand_rows_pad(b_rows);
   CUtensorMap ma, mb;
   if (int e = make_operand_map(&ma, a_planes, pa * a_pad, Dp, BK, BM)) return e;
   if (int e = make_operand_map(&mb, b_planes, pb * b_pad, Dp, BK, BN)) return e;
+  constexpr uint32_t kStashBytes = NEW * 4096;
   const uint32_t stage_bytes = WHOLE ? (uint32_t)(pa * BM + pb * BN) * BK * 2 : (uint32_t)(BM + BN) * BK * 2;
-  int nstages = (int)(196608 / stage_bytes);
+  int nstages = (int)((196608 - kStashBytes) / stage_bytes);
   if (nstages > 8) nstages = 8;
-  const size_t smem_bytes = 1024 + (size_t)nstages * stage_bytes + 2 * BN * sizeof(float) + (2 * nstages + 4) * 8 + 16;
+  const size_t smem_bytes = 1024 + (size_t)nstages * stage_bytes + kStashBytes + 2 * BN * sizeof(float) + (2 * nstages + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<BK, WHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    VQB_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<BK, WHOLE, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const TermTable terms = make_terms(pa, pb);
   const int64_t total = ((a_rows + BM - 1) / BM) * ((b_rows + BN - 1) / BN);
   int grid = sm_count();
   if (total < grid) grid = (int)total;
-  assign_tc_kernel<BK, WHOLE><<<grid, kThreads, smem_bytes, st>>>(ma, mb, terms, pa, pb, Dp / BK, nstages, a_rows, a_pad,
+  assign_tc_kernel<BK, WHOLE, NEW><<<grid, 64 + NEW * 32, smem_bytes, st>>>(ma, mb, terms, pa, pb, Dp / BK, nstages, a_rows, a_pad,
                                                                   b_rows, b_pad, h, off, keys);
   VQB_LAUNCH_OK();
   return VQB_OK;
@@ -507,9 +562,23 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, const void* b_pl
 int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, const void* b_planes, int pb, int64_t b_rows,
                      int D, const float* h, int64_t off, unsigned long long* keys, cudaStream_t st) {
   const int Dp = (int)vqb_operand_dp(D);
+  // 8 epilogue warps (2 per SM sub-partition) measured faster than 16 on B200 for every shape (the extra
+  // warps add per-tile barrier traffic without raising TMEM-load or ALU throughput); VQB_EPILOGUE_WARPS=16
+  // keeps the alternative reachable for experiments.
+  static int new_override = -1;
+  if (new_override < 0) {
+    const char* e = getenv("VQB_EPILOGUE_WARPS");
+    new_override = e ? atoi(e) : 0;
+  }
+  const int nwarps = new_override == 16 ? 16 : 8;
+  const size_t stash = (size_t)nwarps * 4096;
   // whole-tile stages need at least a double buffer of all planes of one work item in shared memory
-  const bool whole = Dp <= 64 && (size_t)(pa * BM + pb * BN) * Dp * 2 * 2 <= 196608;
-#define VQB_LAUNCH(BK_, W_) return launch<BK_, W_>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st)
+  const bool whole = Dp <= 64 && (size_t)(pa * BM + pb * BN) * Dp * 2 * 2 <= 196608 - stash;
+#define VQB_LAUNCH(BK_, W_)                                                                                         \
+  do {                                                                                                              \
+    if (nwarps == 16) return launch<BK_, W_, 16>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st); \
+    return launch<BK_, W_, 8>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st);                    \
+  } while (0)
   if (Dp == 16) { if (whole) VQB_LAUNCH(16, true); VQB_LAUNCH(16, false); }
   if (Dp == 32) { if (whole) VQB_LAUNCH(32, true); VQB_LAUNCH(32, false); }
   if (whole) VQB_LAUNCH(64, true);
