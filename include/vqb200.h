@@ -76,11 +76,14 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D,
  *      keys[i] = (~orderable(score) << 32) | (uint32)(j + b_index_offset)
  * with 64-bit atomicMin, so several launches (codebook shards) and several GPUs (packed
  * min-loc all-reduce) compose.  keys must be initialised to all-ones.
+ * `*_plane_rows` is the row stride between planes: 0 = the padded default of vqb_pack_rows; a bf16 [rows, D]
+ * tensor with D == vqb_operand_dp(D) is already a valid one-plane operand and can be passed ZERO-COPY with
+ * plane_rows = rows (TMA zero-fills the out-of-bounds rows of the last tile).
  * backend VQB_BACKEND_TCGEN05: TMA -> smem -> tcgen05.mma (TMEM accumulators) -> fused argmax
  * epilogue; VQB_BACKEND_SIMT: fp32 CUDA-core kernel with the same contract (cross-check).
  */
-int vqb_assign(const void* a_planes, int a_nplanes, int64_t a_rows,
-               const void* b_planes, int b_nplanes, int64_t b_rows,
+int vqb_assign(const void* a_planes, int a_nplanes, int64_t a_rows, int64_t a_plane_rows,
+               const void* b_planes, int b_nplanes, int64_t b_rows, int64_t b_plane_rows,
                int D, const float* b_half_sqnorm, int64_t b_index_offset,
                unsigned long long* keys, int backend, void* stream);
 
@@ -103,9 +106,13 @@ int vqb_keys_flip_sign(unsigned long long* keys, int64_t n, void* stream);
  */
 int64_t vqb_loss_partials_count(void);
 int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D,
+                        int normalize_x,               /* 1: the quantizer sees F.normalize(x) (NormalizeCallback, normalize.py:24) */
                         const float* W, int64_t K,
-                        const int64_t* quant,          /* [N] */
-                        void* z_ste_out, int out_dtype, /* [N,D] value x + (W[q] - x) */
+                        const int64_t* quant,          /* [N] indices, or NULL when `keys` is given */
+                        const unsigned long long* keys, int64_t key_index_offset, /* packed keys of vqb_assign */
+                        int64_t* quant_out,            /* optional [N]: the unpacked indices (memo['quant']) */
+                        float* x_norm_out,             /* optional [N,D]: F.normalize(x) (memo['x']) */
+                        float* z_ste_out,              /* [N,D] fp32 value x' + (W[q] - x'), x' = (normalised) x */
                         int want_norm_mse,
                         float* mse4_out, float* partials, unsigned int* ticket, void* stream);
 
@@ -117,11 +124,12 @@ int vqb_embedding_gather(const float* W, int64_t K, int D, const int64_t* quant,
 /* Backward of the above (closed form):
  *   gx = g_zste + g4[1]*2(x-z)/(ND) + J_n(x)^T [ g4[3]*2(n(x)-n(z))/(ND) ]
  *   gW[q] += g4[0]*2(z-x)/(ND) + J_n(z)^T [ g4[2]*2(n(z)-n(x))/(ND) ]     (fp32 atomics; gW pre-zeroed or NULL)
- * g4 is a DEVICE pointer to the 4 upstream loss gradients. */
-int vqb_quantize_backward(const void* g_zste, int g_dtype, const void* x, int x_dtype,
+ * g4 is a DEVICE pointer to the 4 upstream loss gradients.  With normalize_x the chain through
+ * F.normalize is applied as well: gx = J_n(x)^T g_x' (the backward of NormalizeCallback.before_encode). */
+int vqb_quantize_backward(const float* g_zste, const void* x, int x_dtype, int normalize_x,
                           const float* W, int64_t K, const int64_t* quant, int64_t N, int D,
                           const float* g4, int want_norm_mse,
-                          void* gx_out, int gx_dtype, float* gW_accum, void* stream);
+                          void* gx_out /* x dtype */, float* gW_accum, void* stream);
 
 /* ---- row l2-normalisation (NormalizeCallback.before_encode on x) ------------------------ *
  * vq/algorithms/vq/callbacks/normalize.py:24  — forward y = x / max(||x||, 1e-12); backward

@@ -137,9 +137,12 @@ def test_assign_sharded_codebook_min_combine(dev):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('normalize_x', [False, True], ids=['raw', 'normx'])
 @pytest.mark.parametrize('N,K,D,norm', [(1000, 64, 32, False), (777, 100, 256, True), (4096, 512, 8, True),
-                                        (333, 50, 20, False)])
-def test_gather_ste_loss_and_backward(dev, dtype, N, K, D, norm):
+                                        (333, 50, 20, False), (130, 40, 768, True), (257, 30, 5, True)])
+def test_gather_ste_loss_and_backward(dev, dtype, normalize_x, N, K, D, norm):
+    """Fused forward (token normalise + key unpack + gather + STE + MSE terms) and closed-form backward
+    (incl. the chain through F.normalize) against autograd on the oracle."""
     g = torch.Generator().manual_seed(7)
     x = torch.randn(N, D, generator=g).to(dtype)
     W = torch.randn(K, D, generator=g)
@@ -149,7 +152,8 @@ def test_gather_ste_loss_and_backward(dev, dtype, N, K, D, norm):
     if not norm:
         g4[2:] = 0
     # oracle (fp32 on up-cast inputs), autograd for the gradients
-    xo = x.float().clone().requires_grad_(True)
+    xin = x.float().clone().requires_grad_(True)
+    xo = O.normalize(xin) if normalize_x else xin
     Wo = W.clone().requires_grad_(True)
     z = O.decode(Wo, q)
     cb, cm = O.codebook_loss(z, xo), O.commitment_loss(z, xo)
@@ -159,20 +163,45 @@ def test_gather_ste_loss_and_backward(dev, dtype, N, K, D, norm):
     total.backward()
 
     xd, Wd, qd = x.to(dev), W.to(dev), q.to(dev)
-    z_k, mse4 = ops.gather_ste_loss(xd, Wd, qd, want_norm=norm)
-    assert torch.equal(z_k.cpu(), z_ste.detach()), 'z_ste must be bit-exact: x + (W[q] - x)'
+    from vector_quantization_b200 import parallel
+    keys = parallel.pack_keys_host(torch.randn(N, generator=g), q + 7).to(dev)   # packed keys, index offset 7
+    z_k, mse4, q_out, xn = ops.gather_ste_loss(xd, Wd, keys=keys, key_offset=7, normalize_x=normalize_x,
+                                               want_norm=norm, want_quant=True, want_xnorm=normalize_x)
+    assert torch.equal(q_out.cpu(), q)
+    if normalize_x:
+        torch.testing.assert_close(xn.cpu(), xo.detach(), rtol=2e-6, atol=1e-7)
+        torch.testing.assert_close(z_k.cpu(), z_ste.detach(), rtol=1e-5, atol=1e-6)
+    else:
+        assert torch.equal(z_k.cpu(), z_ste.detach()), 'z_ste must be bit-exact: x + (W[q] - x)'
     ref4 = torch.stack([cb, cm, cbn, cmn]).detach()
     if not norm:
         ref4[2:] = mse4.cpu()[2:]
     torch.testing.assert_close(mse4.cpu(), ref4, rtol=1e-5, atol=1e-8)
-    # deterministic reduction: a second launch returns the same bits
-    _, mse4b = ops.gather_ste_loss(xd, Wd, qd, want_norm=norm)
+    # deterministic reduction: a second launch (indices instead of keys) returns the same bits
+    _, mse4b, _, _ = ops.gather_ste_loss(xd, Wd, quant=qd, normalize_x=normalize_x, want_norm=norm)
     assert torch.equal(mse4, mse4b)
 
-    gx, gW = ops.quantize_backward(gz.to(dev), xd, Wd, qd, g4.to(dev), want_norm=norm, need_gW=True)
-    tol = dict(rtol=1e-4, atol=1e-6) if dtype == torch.float32 else dict(rtol=2 ** -7, atol=1e-3)
-    torch.testing.assert_close(gx.float().cpu(), xo.grad, **tol)
+    gx, gW = ops.quantize_backward(gz.to(dev), xd, Wd, qd, g4.to(dev), normalize_x=normalize_x, want_norm=norm,
+                                   need_gW=True)
+    tol = dict(rtol=1e-4, atol=2e-6) if dtype == torch.float32 else dict(rtol=2 ** -7, atol=2e-3)
+    torch.testing.assert_close(gx.float().cpu(), xin.grad, **tol)
     torch.testing.assert_close(gW.cpu(), Wo.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_assign_zero_copy_bf16_tokens(dev):
+    """A contiguous bf16 [N, D] tensor with D in {16, 32, 64k} is passed to the TMA descriptor as is."""
+    for N, K, D in ((1000, 512, 32), (300, 700, 64), (513, 256, 16)):
+        x, E = O.synthetic_latents(N, K, D, seed=N, normalized_codebook=True)
+        xb = x.to(torch.bfloat16)
+        q_ref, d = O.encode('Cosine', xb.float(), E)
+        tok = ops.as_operand(xb.to(dev))
+        assert tok is not None and tok.planes.data_ptr() != 0 and tok.plane_rows == N
+        book = ops.pack_rows(E.to(dev), normalize=True)
+        for backend in (ops.BACKEND_TCGEN05, ops.BACKEND_SIMT):
+            keys = ops.new_keys(N, dev)
+            ops.assign(tok, book, keys, l2=False, backend=backend)
+            _check_indices(d, q_ref, ops.unpack_keys(keys).cpu(), what=f'zero-copy {N}x{K}x{D}')
+    assert ops.as_operand(torch.zeros(8, 20, dtype=torch.bfloat16, device=dev)) is None
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])

@@ -197,16 +197,19 @@ class UpdateMixin(BaseCallback):
 @VQITQuantizerCallbackRegistry.register_()
 class NormalizeCallback(UpdateMixin, BaseCallback):
     """x <- normalize(x);  weight.data <- normalize(weight)  every forward, train and eval.
-    One kernel normalises the codebook in place AND emits the bf16 operand planes (+0.5|e|^2) that the
-    assignment kernel reads, so the per-forward codebook rewrite costs no extra pass."""
+    Neither costs a pass of its own: the codebook is normalised in place by the kernel that also emits the
+    bf16 operand planes (+0.5|e|^2) for the assignment (flag `_normalize_codebook`, consumed by
+    `VectorQuantizer._encode`), and inside `forward` the token normalisation is deferred into the fused
+    gather/STE/loss kernel and its backward (flag `_normalize_x`); a standalone `encode()` call
+    normalises eagerly with the l2norm kernel."""
 
     def before_encode(self, x, memo):
         x = super().before_encode(x, memo)
-        x = Fq.l2_normalize(x)
-        vq = self.vector_quantizer
-        memo['_codebook_operand'] = Fq.pack_codebook(vq.embedding.weight.data, vq.distance.metric,
-                                                     precision=vq.precision, writeback_normalized=True)
-        return x
+        memo['_normalize_codebook'] = True
+        if memo.pop('_lazy_normalize', False):
+            memo['_normalize_x'] = True   # x stays raw; F.normalize is applied inside the fused kernels
+            return x
+        return Fq.l2_normalize(x)
 
 
 class LazyInitWeightsMixin(BaseCallback):
@@ -256,8 +259,10 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
                 indices = random.sample(range(xn.shape[0]), K)
                 W.copy_(ops.embedding_gather(xn, torch.tensor(indices, device=x.device)))
                 for _ in range(iters):
+                    keys = ops.new_keys(xn.shape[0], xn.device)
                     book = Fq.pack_codebook(W, vq.distance.metric, precision=vq.precision, writeback_normalized=True)
-                    quant = ops.unpack_keys(Fq.nearest_code(xn, book, vq.distance.metric, precision=vq.precision))
+                    quant = ops.unpack_keys(Fq.nearest_code(xn, book, vq.distance.metric, precision=vq.precision,
+                                                            keys=keys, keys_are_reset=True))
                     stats = ops.scatter_stats(xn, quant, K)
                     ops.kmeans_ema_update(stats, W, 0.0)  # decay 0: W <- normalize(centroids | old row if unused)
         if world > 1:

@@ -7,9 +7,9 @@
 
 namespace vqb {
 
-int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, const void* b_planes, int pb, int64_t b_rows,
-                     int D, const float* b_half_sqnorm, int64_t b_index_offset, unsigned long long* keys,
-                     cudaStream_t st);
+int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_plane_rows, const void* b_planes, int pb,
+                     int64_t b_rows, int64_t b_plane_rows, int D, const float* b_half_sqnorm, int64_t b_index_offset,
+                     unsigned long long* keys, cudaStream_t st);
 
 constexpr int SA = 128;  // A rows per block (one per thread)
 constexpr int SB = 32;   // B rows per inner tile
@@ -50,11 +50,11 @@ __global__ void __launch_bounds__(SA) assign_simt_kernel(const __nv_bfloat16* __
       __syncthreads();
       for (int i = t; i < SA * SD; i += SA) {
         const int r = i / SD, d = i % SD;
-        As[r][d] = (d0 + d < Dp) ? load_planes(A, pa, a_rows_pad * Dp, (row0 + r) * Dp + d0 + d) : 0.f;
+        As[r][d] = (d0 + d < Dp && row0 + r < a_rows_pad) ? load_planes(A, pa, a_rows_pad * Dp, (row0 + r) * Dp + d0 + d) : 0.f;
       }
       for (int i = t; i < SB * SD; i += SA) {
         const int r = i / SD, d = i % SD;
-        Bs[r][d] = (d0 + d < Dp) ? load_planes(B, pb, b_rows_pad * Dp, (j0 + r) * Dp + d0 + d) : 0.f;
+        Bs[r][d] = (d0 + d < Dp && j0 + r < b_rows_pad) ? load_planes(B, pb, b_rows_pad * Dp, (j0 + r) * Dp + d0 + d) : 0.f;
       }
       __syncthreads();
       float a[SD];
@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(SA) assign_simt_kernel(const __nv_bfloat16* __
 
 using namespace vqb;
 
-extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, const void* b_planes, int pb,
-                          int64_t b_rows, int D, const float* b_half_sqnorm, int64_t b_index_offset,
-                          unsigned long long* keys, int backend, void* stream) {
+extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, int64_t a_plane_rows, const void* b_planes,
+                          int pb, int64_t b_rows, int64_t b_plane_rows, int D, const float* b_half_sqnorm,
+                          int64_t b_index_offset, unsigned long long* keys, int backend, void* stream) {
   VQB_REQUIRE(a_planes && b_planes && keys, "vqb_assign: null pointer");
   VQB_REQUIRE(a_rows >= 1 && b_rows >= 1 && D >= 1, "vqb_assign: bad shape a_rows=%lld b_rows=%lld D=%d",
               (long long)a_rows, (long long)b_rows, D);
@@ -93,8 +93,14 @@ extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, const vo
   VQB_REQUIRE(b_rows + b_index_offset < 0xffffffffll && b_index_offset >= 0,
               "vqb_assign: column index does not fit 32 bits");
   cudaStream_t st = (cudaStream_t)stream;
+  if (a_plane_rows <= 0) a_plane_rows = vqb_operand_rows_pad(a_rows);
+  if (b_plane_rows <= 0) b_plane_rows = vqb_operand_rows_pad(b_rows);
+  VQB_REQUIRE(a_plane_rows >= a_rows && b_plane_rows >= b_rows, "vqb_assign: plane stride smaller than the row count");
+  VQB_REQUIRE(b_half_sqnorm == nullptr || b_plane_rows % 256 == 0,
+              "vqb_assign: the L2 side vector needs the padded operand layout of vqb_pack_rows");
   if (backend == VQB_BACKEND_TCGEN05)
-    return assign_tc_launch(a_planes, pa, a_rows, b_planes, pb, b_rows, D, b_half_sqnorm, b_index_offset, keys, st);
+    return assign_tc_launch(a_planes, pa, a_rows, a_plane_rows, b_planes, pb, b_rows, b_plane_rows, D, b_half_sqnorm,
+                            b_index_offset, keys, st);
   VQB_REQUIRE(backend == VQB_BACKEND_SIMT, "vqb_assign: unknown backend %d", backend);
   const int Dp = (int)vqb_operand_dp(D);
   const int64_t a_tiles = (a_rows + SA - 1) / SA;
@@ -104,9 +110,9 @@ extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, const vo
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
   dim3 grid((unsigned)a_tiles, (unsigned)splits);
-  assign_simt_kernel<<<grid, SA, 0, st>>>((const __nv_bfloat16*)a_planes, pa, a_rows, vqb_operand_rows_pad(a_rows),
-                                          (const __nv_bfloat16*)b_planes, pb, b_rows, vqb_operand_rows_pad(b_rows),
-                                          Dp, b_half_sqnorm, b_index_offset, keys);
+  assign_simt_kernel<<<grid, SA, 0, st>>>((const __nv_bfloat16*)a_planes, pa, a_rows, a_plane_rows,
+                                          (const __nv_bfloat16*)b_planes, pb, b_rows, b_plane_rows, Dp, b_half_sqnorm,
+                                          b_index_offset, keys);
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

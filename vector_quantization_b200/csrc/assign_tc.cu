@@ -533,9 +533,9 @@ static TermTable make_terms(int pa, int pb) {
 }
 
 template <int BK, bool WHOLE, int NEW>
-static int launch(const void* a_planes, int pa, int64_t a_rows, const void* b_planes, int pb, int64_t b_rows, int Dp,
-                  const float* h, int64_t off, unsigned long long* keys, cudaStream_t st) {
-  const int64_t a_pad = vqb_operand_rows_pad(a_rows), b_pad = vqb_operand_rows_pad(b_rows);
+static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, const void* b_planes, int pb,
+                  int64_t b_rows, int64_t b_pad, int Dp, const float* h, int64_t off, unsigned long long* keys,
+                  cudaStream_t st) {
   CUtensorMap ma, mb;
   if (int e = make_operand_map(&ma, a_planes, pa * a_pad, Dp, BK, BM)) return e;
   if (int e = make_operand_map(&mb, b_planes, pb * b_pad, Dp, BK, BN)) return e;
@@ -559,8 +559,9 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, const void* b_pl
   return VQB_OK;
 }
 
-int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, const void* b_planes, int pb, int64_t b_rows,
-                     int D, const float* h, int64_t off, unsigned long long* keys, cudaStream_t st) {
+int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, const void* b_planes, int pb,
+                     int64_t b_rows, int64_t b_pad, int D, const float* h, int64_t off, unsigned long long* keys,
+                     cudaStream_t st) {
   const int Dp = (int)vqb_operand_dp(D);
   // 8 epilogue warps (2 per SM sub-partition) measured faster than 16 on B200 for every shape (the extra
   // warps add per-tile barrier traffic without raising TMEM-load or ALU throughput); VQB_EPILOGUE_WARPS=16
@@ -576,8 +577,8 @@ int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, const void* b
   const bool whole = Dp <= 64 && (size_t)(pa * BM + pb * BN) * Dp * 2 * 2 <= 196608 - stash;
 #define VQB_LAUNCH(BK_, W_)                                                                                         \
   do {                                                                                                              \
-    if (nwarps == 16) return launch<BK_, W_, 16>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st); \
-    return launch<BK_, W_, 8>(a_planes, pa, a_rows, b_planes, pb, b_rows, Dp, h, off, keys, st);                    \
+    if (nwarps == 16) return launch<BK_, W_, 16>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, off, keys, st); \
+    return launch<BK_, W_, 8>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, off, keys, st);                   \
   } while (0)
   if (Dp == 16) { if (whole) VQB_LAUNCH(16, true); VQB_LAUNCH(16, false); }
   if (Dp == 32) { if (whole) VQB_LAUNCH(32, true); VQB_LAUNCH(32, false); }

@@ -1,5 +1,11 @@
-// Codebook gather + straight-through estimator + MSE-loss reduction (forward, one pass) and the
-// closed-form backward.  HBM-bound: per token reads x row + codebook row + index, writes z row.
+// Codebook gather + straight-through estimator + MSE-loss reduction (forward, ONE pass) and the closed-form
+// backward, with the token l2-normalisation of NormalizeCallback/VQKDCallback and the key->index unpack
+// fused in.  HBM-bound: per token the forward reads the x row, the codebook row (L2-resident) and the
+// 8-byte key, and writes the z row (+ the normalised x row and the int64 index when requested).
+//
+// Layout: G lanes cooperate on one token row, each lane owns V contiguous elements per step (V = 8:
+// 128-bit loads for bf16, 2 x 128-bit for fp32) and keeps its slice of the row in registers, so every
+// element is read from memory exactly once although the math needs two passes (norms, then outputs).
 #include <math.h>
 
 #include "common.cuh"
@@ -8,10 +14,42 @@ namespace vqb {
 
 constexpr int kMaxPartials = 4096;
 
-static inline int lanes_per_row_q(int D) {
-  int g = 1;
-  while (g < 32 && g * 4 < D) g <<= 1;
-  return g;
+// ---- V-wide row slice load/store -------------------------------------------------------------
+template <typename T, int V>
+__device__ __forceinline__ void load_slice(const T* __restrict__ p, int d0, int D, float (&v)[V]) {
+  if constexpr (V == 8 && sizeof(T) == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p + d0), b = *reinterpret_cast<const float4*>(p + d0 + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else if constexpr (V == 8 && sizeof(T) == 2) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p + d0);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = (d0 + i < D) ? to_f32<T>(p[d0 + i]) : 0.f;
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_slice(T* __restrict__ p, int d0, int D, const float (&v)[V]) {
+  if constexpr (V == 8 && sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p + d0) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + d0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else if constexpr (V == 8 && sizeof(T) == 2) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p + d0) = raw;
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      if (d0 + i < D) p[d0 + i] = from_f32<T>(v[i]);
+  }
 }
 
 // block-wide deterministic sum of two values; result valid in thread 0
@@ -32,11 +70,20 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* sh /* >= 2
   }
 }
 
-template <typename TX, typename TO, int G>
-__global__ void __launch_bounds__(256) gather_ste_loss_kernel(
-    const TX* __restrict__ x, int64_t N, int D, const float* __restrict__ W, int64_t K,
-    const int64_t* __restrict__ quant, TO* __restrict__ z_out, int want_norm, float* __restrict__ mse4,
-    float* __restrict__ partials, unsigned int* __restrict__ ticket) {
+__device__ __forceinline__ int64_t row_index(const int64_t* __restrict__ quant,
+                                             const unsigned long long* __restrict__ keys, int64_t n,
+                                             int64_t key_offset, int64_t K) {
+  int64_t q = quant ? quant[n] : (int64_t)key_index(keys[n]) - key_offset;
+  return q < 0 ? 0 : (q >= K ? K - 1 : q);  // never read out of bounds on a corrupt index
+}
+
+// ---- forward -----------------------------------------------------------------------------------
+template <typename TX, int G, int V, int NV>
+__global__ void __launch_bounds__(256) quantize_forward_kernel(
+    const TX* __restrict__ x, int64_t N, int D, int normalize_x, const float* __restrict__ W, int64_t K,
+    const int64_t* __restrict__ quant, const unsigned long long* __restrict__ keys, int64_t key_offset,
+    int64_t* __restrict__ quant_out, float* __restrict__ xn_out, float* __restrict__ z_out, int want_norm,
+    float* __restrict__ mse4, float* __restrict__ partials, unsigned int* __restrict__ ticket) {
   __shared__ float sh[16];
   __shared__ bool is_last;
   const int lane = threadIdx.x % G;
@@ -46,33 +93,67 @@ __global__ void __launch_bounds__(256) gather_ste_loss_kernel(
     const int64_t n_raw = base + threadIdx.x / G;  // warp-uniform trip count: shuffles need every lane
     const bool valid = n_raw < N;
     const int64_t n = valid ? n_raw : N - 1;
-    int64_t q = quant[n];
-    q = q < 0 ? 0 : (q >= K ? K - 1 : q);  // never read out of bounds on a corrupt index
+    const int64_t q = row_index(quant, keys, n, key_offset, K);
     const float* __restrict__ wrow = W + q * D;
     const TX* __restrict__ xrow = x + n * D;
+    float xr[NV][V], wr[NV][V];
     float sxx = 0.f, sww = 0.f;
-    for (int d = lane; d < D; d += G) {
-      const float xv = to_f32<TX>(xrow[d]);
-      const float wv = __ldg(wrow + d);
-      const float diff = __fsub_rn(wv, xv);
-      if (valid) {
-        z_out[n * D + d] = from_f32<TO>(__fadd_rn(xv, diff));  // ste value: x + (z - x)
-        sse = fmaf(diff, diff, sse);
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int d0 = (it * G + lane) * V;
+      if (d0 < D) {
+        load_slice<TX, V>(xrow, d0, D, xr[it]);
+        load_slice<float, V>(wrow, d0, D, wr[it]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) xr[it][i] = wr[it][i] = 0.f;
       }
-      sxx = fmaf(xv, xv, sxx);
-      sww = fmaf(wv, wv, sww);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        sxx = fmaf(xr[it][i], xr[it][i], sxx);
+        sww = fmaf(wr[it][i], wr[it][i], sww);
+      }
     }
+    if (normalize_x) {  // x <- F.normalize(x): the quantizer's view of the token from here on
+      sxx = group_sum<G>(sxx);
+      const float den = fmaxf(sqrtf(sxx), kNormEps);
+      float s2 = 0.f;
+#pragma unroll
+      for (int it = 0; it < NV; ++it)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          xr[it][i] = __fdiv_rn(xr[it][i], den);
+          s2 = fmaf(xr[it][i], xr[it][i], s2);
+        }
+      sxx = s2;
+    }
+    float dx = 1.f, dw = 1.f;
     if (want_norm) {
       sxx = group_sum<G>(sxx);
       sww = group_sum<G>(sww);
-      const float dx = fmaxf(sqrtf(sxx), kNormEps), dw = fmaxf(sqrtf(sww), kNormEps);
-      for (int d = lane; d < D; d += G) {
-        const float u = __fdiv_rn(to_f32<TX>(xrow[d]), dx);
-        const float v = __fdiv_rn(__ldg(wrow + d), dw);
-        const float diff = v - u;
-        if (valid) sse_n = fmaf(diff, diff, sse_n);
+      dx = fmaxf(sqrtf(sxx), kNormEps);
+      dw = fmaxf(sqrtf(sww), kNormEps);
+    }
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int d0 = (it * G + lane) * V;
+      float zr[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float diff = __fsub_rn(wr[it][i], xr[it][i]);
+        zr[i] = __fadd_rn(xr[it][i], diff);  // ste value: x + (z - x)
+        if (valid) sse = fmaf(diff, diff, sse);
+        if (want_norm) {
+          const float dn = __fdiv_rn(wr[it][i], dw) - __fdiv_rn(xr[it][i], dx);
+          if (valid) sse_n = fmaf(dn, dn, sse_n);
+        }
+      }
+      if (valid && d0 < D) {
+        store_slice<float, V>(z_out + n * D, d0, D, zr);
+        if (xn_out) store_slice<float, V>(xn_out + n * D, d0, D, xr[it]);
       }
     }
+    if (quant_out && valid && lane == 0) quant_out[n] = q;
   }
   block_sum2(sse, sse_n, sh);
   if (threadIdx.x == 0) {
@@ -103,66 +184,119 @@ __global__ void __launch_bounds__(256) gather_ste_loss_kernel(
   }
 }
 
-template <typename TG, typename TX, typename TO, int G>
+// ---- backward ----------------------------------------------------------------------------------
+// With y = F.normalize(x_in) when normalize_x (else y = x_in), z = W[q], u = n(y), v = n(z):
+//   g_y = g_zste + c_cm (y - z) + J_n(y)^T [c_cmn (u - v)]         c_* = g4[*] * 2 / (N D)
+//   g_z = c_cb (z - y) + J_n(z)^T [c_cbn (v - u)]                   -> atomically added to gW[q]
+//   g_x_in = J_n(x_in)^T g_y  when normalize_x, else g_y            J_n(a)^T g = (g - (g.n(a)) n(a)) / |a|
+template <typename TX, int G, int V, int NV>
 __global__ void __launch_bounds__(256) quantize_backward_kernel(
-    const TG* __restrict__ gz, const TX* __restrict__ x, const float* __restrict__ W, int64_t K,
+    const float* __restrict__ gz, const TX* __restrict__ x, int normalize_x, const float* __restrict__ W, int64_t K,
     const int64_t* __restrict__ quant, int64_t N, int D, const float* __restrict__ g4, int want_norm,
-    TO* __restrict__ gx, float* __restrict__ gW) {
+    TX* __restrict__ gx, float* __restrict__ gW) {
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
   const float scale = 2.f / ((float)N * (float)D);
   const float c_cb = g4[0] * scale, c_cm = g4[1] * scale;
   const float c_cbn = want_norm ? g4[2] * scale : 0.f, c_cmn = want_norm ? g4[3] * scale : 0.f;
   for (int64_t base = blockIdx.x * rows_per_block; base < N; base += (int64_t)gridDim.x * rows_per_block) {
-    const int64_t n_raw = base + threadIdx.x / G;  // warp-uniform trip count: shuffles need every lane
+    const int64_t n_raw = base + threadIdx.x / G;
     const bool valid = n_raw < N;
     const int64_t n = valid ? n_raw : N - 1;
-    int64_t q = quant[n];
-    q = q < 0 ? 0 : (q >= K ? K - 1 : q);
+    const int64_t q = row_index(quant, nullptr, n, 0, K);
     const float* __restrict__ wrow = W + q * D;
     const TX* __restrict__ xrow = x + n * D;
-    float dx = 1.f, dw = 1.f, uu = 0.f, vv = 0.f, uv = 0.f;
-    bool cx = false, cw = false;
-    if (want_norm) {
-      float sxx = 0.f, sww = 0.f, sxw = 0.f;
-      for (int d = lane; d < D; d += G) {
-        const float xv = to_f32<TX>(xrow[d]);
-        const float wv = __ldg(wrow + d);
-        sxx = fmaf(xv, xv, sxx);
-        sww = fmaf(wv, wv, sww);
-        sxw = fmaf(xv, wv, sxw);
+    float yr[NV][V], wr[NV][V], gr[NV][V];
+    float sxx = 0.f, sww = 0.f;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int d0 = (it * G + lane) * V;
+      if (d0 < D) {
+        load_slice<TX, V>(xrow, d0, D, yr[it]);
+        load_slice<float, V>(wrow, d0, D, wr[it]);
+        load_slice<float, V>(gz + n * D, d0, D, gr[it]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) yr[it][i] = wr[it][i] = gr[it][i] = 0.f;
       }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        sxx = fmaf(yr[it][i], yr[it][i], sxx);
+        sww = fmaf(wr[it][i], wr[it][i], sww);
+      }
+    }
+    float den_in = 1.f;
+    bool clamp_in = false;
+    if (normalize_x) {
+      sxx = group_sum<G>(sxx);
+      const float nrm = sqrtf(sxx);
+      clamp_in = nrm < kNormEps;
+      den_in = fmaxf(nrm, kNormEps);
+      float s2 = 0.f;
+#pragma unroll
+      for (int it = 0; it < NV; ++it)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          yr[it][i] = __fdiv_rn(yr[it][i], den_in);
+          s2 = fmaf(yr[it][i], yr[it][i], s2);
+        }
+      sxx = s2;
+    }
+    float dy = 1.f, dw = 1.f, uu = 0.f, vv = 0.f, uv = 0.f;
+    bool cy = false, cw = false;
+    if (want_norm) {
+      float syw = 0.f;
+#pragma unroll
+      for (int it = 0; it < NV; ++it)
+#pragma unroll
+        for (int i = 0; i < V; ++i) syw = fmaf(yr[it][i], wr[it][i], syw);
       sxx = group_sum<G>(sxx);
       sww = group_sum<G>(sww);
-      sxw = group_sum<G>(sxw);
-      const float nx = sqrtf(sxx), nw = sqrtf(sww);
-      cx = nx < kNormEps;
+      syw = group_sum<G>(syw);
+      const float ny = sqrtf(sxx), nw = sqrtf(sww);
+      cy = ny < kNormEps;
       cw = nw < kNormEps;
-      dx = fmaxf(nx, kNormEps);
+      dy = fmaxf(ny, kNormEps);
       dw = fmaxf(nw, kNormEps);
-      uu = sxx / (dx * dx);
+      uu = sxx / (dy * dy);
       vv = sww / (dw * dw);
-      uv = sxw / (dx * dw);
+      uv = syw / (dy * dw);
     }
-    for (int d = lane; d < D; d += G) {
-      const float xv = to_f32<TX>(xrow[d]);
-      const float wv = __ldg(wrow + d);
-      float g_x = to_f32<TG>(gz[n * D + d]) + c_cm * (xv - wv);
-      float g_w = c_cb * (wv - xv);
-      if (want_norm) {
-        const float u = xv / dx, v = wv / dw;
-        // J_n(x)^T g_u with g_u = c (u - v):  (g_u - (g_u.u) u) / dx   (projection dropped when clamped)
-        const float gu = c_cmn * (u - v);
-        const float gu_dot_u = c_cmn * (uu - uv);
-        g_x += (gu - (cx ? 0.f : gu_dot_u * u)) / dx;
-        const float gv = c_cbn * (v - u);
-        const float gv_dot_v = c_cbn * (vv - uv);
-        g_w += (gv - (cw ? 0.f : gv_dot_v * v)) / dw;
+    // g_y (overwrites gr) and the codebook-row gradient
+    float gy_dot_y = 0.f;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int d0 = (it * G + lane) * V;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float yv = yr[it][i], wv = wr[it][i];
+        float g_y = gr[it][i] + c_cm * (yv - wv);
+        float g_w = c_cb * (wv - yv);
+        if (want_norm) {
+          const float u = yv / dy, v = wv / dw;
+          const float gu = c_cmn * (u - v), gu_dot_u = c_cmn * (uu - uv);
+          g_y += (gu - (cy ? 0.f : gu_dot_u * u)) / dy;
+          const float gv = c_cbn * (v - u), gv_dot_v = c_cbn * (vv - uv);
+          g_w += (gv - (cw ? 0.f : gv_dot_v * v)) / dw;
+        }
+        gr[it][i] = g_y;
+        gy_dot_y = fmaf(g_y, yv, gy_dot_y);
+        if (gW && valid && d0 + i < D) atomicAdd(gW + q * D + d0 + i, g_w);
       }
-      if (valid) {
-        gx[n * D + d] = from_f32<TO>(g_x);
-        if (gW) atomicAdd(gW + q * D + d, g_w);
-      }
+    }
+    if (normalize_x) {
+      gy_dot_y = group_sum<G>(gy_dot_y);
+      const float inv = 1.f / den_in;
+      const float proj = clamp_in ? 0.f : gy_dot_y;
+#pragma unroll
+      for (int it = 0; it < NV; ++it)
+#pragma unroll
+        for (int i = 0; i < V; ++i) gr[it][i] = (gr[it][i] - proj * yr[it][i]) * inv;
+    }
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int d0 = (it * G + lane) * V;
+      if (valid && d0 < D) store_slice<TX, V>(gx + n * D, d0, D, gr[it]);
     }
   }
 }
@@ -201,65 +335,90 @@ static inline int grid_for(int64_t rows, int rows_per_block) {
   return (int)blocks;
 }
 
-#define VQB_DISPATCH_G(G_, ...)                  \
-  switch (G_) {                                  \
-    case 1: { constexpr int G = 1; __VA_ARGS__; } break;   \
-    case 2: { constexpr int G = 2; __VA_ARGS__; } break;   \
-    case 4: { constexpr int G = 4; __VA_ARGS__; } break;   \
-    case 8: { constexpr int G = 8; __VA_ARGS__; } break;   \
-    case 16: { constexpr int G = 16; __VA_ARGS__; } break; \
-    default: { constexpr int G = 32; __VA_ARGS__; } break; \
-  }
+// row geometry: V elements per lane per step, G lanes per row, NV steps (G*V*NV >= D)
+struct RowGeom {
+  int V, G, NV;
+};
+static inline bool row_geom(int D, RowGeom* g) {
+  g->V = (D % 8 == 0) ? 8 : 1;
+  const int slices = (D + g->V - 1) / g->V;
+  g->G = 1;
+  while (g->G < 32 && g->G < slices) g->G <<= 1;
+  int nv = 1;
+  while (nv * g->G < slices) nv <<= 1;
+  g->NV = nv;
+  return g->NV <= 8;
+}
 
 }  // namespace vqb
 
 using namespace vqb;
 
+#define VQB_GEOM_CASE(V_, G_, NV_, ...)                 \
+  if (geom.V == V_ && geom.G == G_ && geom.NV == NV_) { \
+    constexpr int V = V_, G = G_, NV = NV_;             \
+    __VA_ARGS__;                                        \
+    launched = true;                                    \
+  }
+// vector path: D multiple of 8 (<= 2048); scalar path: any D <= 256
+#define VQB_DISPATCH_GEOM(...)                                                                                    \
+  VQB_GEOM_CASE(8, 1, 1, __VA_ARGS__) VQB_GEOM_CASE(8, 2, 1, __VA_ARGS__) VQB_GEOM_CASE(8, 4, 1, __VA_ARGS__)     \
+  VQB_GEOM_CASE(8, 8, 1, __VA_ARGS__) VQB_GEOM_CASE(8, 16, 1, __VA_ARGS__) VQB_GEOM_CASE(8, 32, 1, __VA_ARGS__)   \
+  VQB_GEOM_CASE(8, 32, 2, __VA_ARGS__) VQB_GEOM_CASE(8, 32, 4, __VA_ARGS__) VQB_GEOM_CASE(8, 32, 8, __VA_ARGS__)  \
+  VQB_GEOM_CASE(1, 1, 1, __VA_ARGS__) VQB_GEOM_CASE(1, 2, 1, __VA_ARGS__) VQB_GEOM_CASE(1, 4, 1, __VA_ARGS__)     \
+  VQB_GEOM_CASE(1, 8, 1, __VA_ARGS__) VQB_GEOM_CASE(1, 16, 1, __VA_ARGS__) VQB_GEOM_CASE(1, 32, 1, __VA_ARGS__)   \
+  VQB_GEOM_CASE(1, 32, 2, __VA_ARGS__) VQB_GEOM_CASE(1, 32, 4, __VA_ARGS__) VQB_GEOM_CASE(1, 32, 8, __VA_ARGS__)
+
 extern "C" {
 
 int64_t vqb_loss_partials_count(void) { return 2 * kMaxPartials; }
 
-int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D, const float* W, int64_t K,
-                        const int64_t* quant, void* z_out, int out_dtype, int want_norm, float* mse4,
+int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D, int normalize_x, const float* W, int64_t K,
+                        const int64_t* quant, const unsigned long long* keys, int64_t key_index_offset,
+                        int64_t* quant_out, float* x_norm_out, float* z_out, int want_norm, float* mse4,
                         float* partials, unsigned int* ticket, void* stream) {
-  VQB_REQUIRE(x && W && quant && z_out && mse4 && partials && ticket, "vqb_gather_ste_loss: null pointer");
+  VQB_REQUIRE(x && W && z_out && mse4 && partials && ticket, "vqb_gather_ste_loss: null pointer");
+  VQB_REQUIRE((quant != nullptr) != (keys != nullptr), "vqb_gather_ste_loss: pass exactly one of quant / keys");
   VQB_REQUIRE(N >= 1 && D >= 1 && K >= 1, "vqb_gather_ste_loss: bad shape N=%lld D=%d K=%lld", (long long)N, D,
               (long long)K);
+  RowGeom geom;
+  VQB_REQUIRE(row_geom(D, &geom), "vqb_gather_ste_loss: D=%d unsupported (multiple of 8 up to 2048, or any D <= 256)", D);
   cudaStream_t st = (cudaStream_t)stream;
-  const int g = lanes_per_row_q(D);
-  const int blocks = grid_for(N, 256 / g);
+  const int blocks = grid_for(N, 256 / geom.G);
   VQB_REQUIRE(blocks <= kMaxPartials, "vqb_gather_ste_loss: grid too large");
-#define LAUNCH(TX, TO)                                                                                          \
-  VQB_DISPATCH_G(g, (gather_ste_loss_kernel<TX, TO, G><<<blocks, 256, 0, st>>>(                                 \
-                        (const TX*)x, N, D, W, K, quant, (TO*)z_out, want_norm, mse4, partials, ticket)))
-  if (x_dtype == VQB_F32 && out_dtype == VQB_F32) { LAUNCH(float, float); }
-  else if (x_dtype == VQB_BF16 && out_dtype == VQB_F32) { LAUNCH(__nv_bfloat16, float); }
-  else if (x_dtype == VQB_BF16 && out_dtype == VQB_BF16) { LAUNCH(__nv_bfloat16, __nv_bfloat16); }
-  else if (x_dtype == VQB_F32 && out_dtype == VQB_BF16) { LAUNCH(float, __nv_bfloat16); }
-  else { VQB_REQUIRE(false, "vqb_gather_ste_loss: bad dtype"); }
-#undef LAUNCH
+  bool launched = false;
+  if (x_dtype == VQB_F32) {
+    VQB_DISPATCH_GEOM((quantize_forward_kernel<float, G, V, NV><<<blocks, 256, 0, st>>>(
+        (const float*)x, N, D, normalize_x, W, K, quant, keys, key_index_offset, quant_out, x_norm_out, z_out,
+        want_norm, mse4, partials, ticket)))
+  } else if (x_dtype == VQB_BF16) {
+    VQB_DISPATCH_GEOM((quantize_forward_kernel<__nv_bfloat16, G, V, NV><<<blocks, 256, 0, st>>>(
+        (const __nv_bfloat16*)x, N, D, normalize_x, W, K, quant, keys, key_index_offset, quant_out, x_norm_out, z_out,
+        want_norm, mse4, partials, ticket)))
+  }
+  VQB_REQUIRE(launched, "vqb_gather_ste_loss: unsupported dtype/geometry");
   VQB_LAUNCH_OK();
   return VQB_OK;
 }
 
-int vqb_quantize_backward(const void* gz, int g_dtype, const void* x, int x_dtype, const float* W, int64_t K,
+int vqb_quantize_backward(const float* gz, const void* x, int x_dtype, int normalize_x, const float* W, int64_t K,
                           const int64_t* quant, int64_t N, int D, const float* g4, int want_norm, void* gx,
-                          int gx_dtype, float* gW, void* stream) {
+                          float* gW, void* stream) {
   VQB_REQUIRE(gz && x && W && quant && g4 && gx, "vqb_quantize_backward: null pointer");
   VQB_REQUIRE(N >= 1 && D >= 1 && K >= 1, "vqb_quantize_backward: bad shape");
-  VQB_REQUIRE(x_dtype == gx_dtype, "vqb_quantize_backward: gx dtype must equal x dtype");
+  RowGeom geom;
+  VQB_REQUIRE(row_geom(D, &geom), "vqb_quantize_backward: D=%d unsupported", D);
   cudaStream_t st = (cudaStream_t)stream;
-  const int g = lanes_per_row_q(D);
-  const int blocks = grid_for(N, 256 / g);
-#define LAUNCH(TG, TX)                                                                                   \
-  VQB_DISPATCH_G(g, (quantize_backward_kernel<TG, TX, TX, G><<<blocks, 256, 0, st>>>(                    \
-                        (const TG*)gz, (const TX*)x, W, K, quant, N, D, g4, want_norm, (TX*)gx, gW)))
-  if (g_dtype == VQB_F32 && x_dtype == VQB_F32) { LAUNCH(float, float); }
-  else if (g_dtype == VQB_F32 && x_dtype == VQB_BF16) { LAUNCH(float, __nv_bfloat16); }
-  else if (g_dtype == VQB_BF16 && x_dtype == VQB_BF16) { LAUNCH(__nv_bfloat16, __nv_bfloat16); }
-  else if (g_dtype == VQB_BF16 && x_dtype == VQB_F32) { LAUNCH(__nv_bfloat16, float); }
-  else { VQB_REQUIRE(false, "vqb_quantize_backward: bad dtype"); }
-#undef LAUNCH
+  const int blocks = grid_for(N, 256 / geom.G);
+  bool launched = false;
+  if (x_dtype == VQB_F32) {
+    VQB_DISPATCH_GEOM((quantize_backward_kernel<float, G, V, NV><<<blocks, 256, 0, st>>>(
+        gz, (const float*)x, normalize_x, W, K, quant, N, D, g4, want_norm, (float*)gx, gW)))
+  } else if (x_dtype == VQB_BF16) {
+    VQB_DISPATCH_GEOM((quantize_backward_kernel<__nv_bfloat16, G, V, NV><<<blocks, 256, 0, st>>>(
+        gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g4, want_norm, (__nv_bfloat16*)gx, gW)))
+  }
+  VQB_REQUIRE(launched, "vqb_quantize_backward: unsupported dtype/geometry");
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

@@ -55,15 +55,26 @@ def pack_codebook(W: torch.Tensor, metric: str, *, precision: str = 'exact', wri
 
 @torch.no_grad()
 def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precision: str = 'exact',
-                 keys: torch.Tensor | None = None, index_offset: int = 0,
-                 tokens: ops.Operand | None = None) -> torch.Tensor:
+                 keys: torch.Tensor | None = None, index_offset: int = 0, normalize_tokens: bool = False,
+                 tokens: ops.Operand | None = None, keys_are_reset: bool = False) -> torch.Tensor:
     """Packed (score,index) keys [N] of the nearest code of every token (row arg-min of the distance).
-    Cosine arg-min is invariant to the token norm, so raw tokens are packed (one exact plane for bf16)."""
-    if tokens is None:
-        tokens = ops.pack_rows(x, planes=_planes_for(x, False, precision))
+    Cosine arg-min is invariant to the token norm, so raw tokens are used: zero-copy for bf16 tokens
+    whose D needs no padding, one exact plane otherwise.  L2 on normalised tokens (LlamaGen) packs the
+    normalised planes."""
+    cos = metric == 'Cosine'
     if keys is None:
-        keys = ops.new_keys(x.shape[0], x.device)
-    return ops.assign(tokens, codebook, keys, l2=metric == 'L2', index_offset=index_offset)
+        keys = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
+        keys_are_reset = False
+    if tokens is None:
+        norm = normalize_tokens and not cos
+        tokens = None if norm else ops.as_operand(x)
+        if tokens is None:
+            tokens = ops.pack_rows(x, normalize=norm, planes=_planes_for(x, norm, precision),
+                                   reset_keys=None if keys_are_reset else keys)
+            keys_are_reset = True
+    if not keys_are_reset:
+        keys.fill_(-1)
+    return ops.assign(tokens, codebook, keys, l2=not cos, index_offset=index_offset)
 
 
 @torch.no_grad()
@@ -81,30 +92,42 @@ def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, preci
 class _QuantizeSTELoss(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, x, W, quant, want_norm):
-        z, mse4 = ops.gather_ste_loss(x, W, quant, want_norm=want_norm, out_dtype=torch.float32)
+    def forward(ctx, x, W, index, index_is_keys, key_offset, normalize_x, want_norm):
+        z, mse4, quant, xn = ops.gather_ste_loss(
+            x, W, quant=None if index_is_keys else index, keys=index if index_is_keys else None,
+            key_offset=key_offset, normalize_x=normalize_x, want_norm=want_norm, want_quant=index_is_keys,
+            want_xnorm=normalize_x)
+        if quant is None:
+            quant = index
         ctx.save_for_backward(x, W, quant)
-        ctx.want_norm = want_norm
-        ctx.mark_non_differentiable(quant)
-        return z, mse4
+        ctx.cfg = (normalize_x, want_norm)
+        if xn is None:
+            xn = x.detach()
+        ctx.mark_non_differentiable(quant, xn)
+        return z, mse4, quant, xn
 
     @staticmethod
-    def backward(ctx, gz, g4):
+    def backward(ctx, gz, g4, _gq, _gxn):
         x, W, quant = ctx.saved_tensors
+        normalize_x, want_norm = ctx.cfg
         if gz is None:
             gz = torch.zeros(x.shape, dtype=torch.float32, device=x.device)
         if g4 is None:
             g4 = torch.zeros(4, dtype=torch.float32, device=x.device)
-        need_gW = ctx.needs_input_grad[1]
-        gx, gW = ops.quantize_backward(gz.contiguous(), x, W, quant, g4.contiguous().float(),
-                                       want_norm=ctx.want_norm, need_gW=need_gW)
-        return (gx if ctx.needs_input_grad[0] else None), gW, None, None
+        gx, gW = ops.quantize_backward(gz.contiguous().float(), x, W, quant, g4.contiguous().float(),
+                                       normalize_x=normalize_x, want_norm=want_norm,
+                                       need_gW=ctx.needs_input_grad[1])
+        return (gx if ctx.needs_input_grad[0] else None), gW, None, None, None, None, None
 
 
-def quantize_ste_loss(x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor, want_norm: bool):
-    """-> (z_ste [N,D] fp32 with value x + (W[q] - x) and gradient to x only,
-           mse4 [4] = {codebook, commitment, codebook(norm), commitment(norm)} MSE terms)."""
-    return _QuantizeSTELoss.apply(x.contiguous(), W, quant, bool(want_norm))
+def quantize_ste_loss(x: torch.Tensor, W: torch.Tensor, index: torch.Tensor, want_norm: bool, *,
+                      index_is_keys: bool = False, key_offset: int = 0, normalize_x: bool = False):
+    """One kernel: [x' = F.normalize(x)] -> gather W[q] -> straight-through -> MSE terms.
+    -> (z_ste [N,D] fp32: value x' + (W[q] - x'), gradient to x only;
+        mse4 [4] = {codebook, commitment, codebook(norm), commitment(norm)};
+        quant int64 [N] (unpacked from the keys when index_is_keys);  x' (detached; x itself if not normalised))"""
+    return _QuantizeSTELoss.apply(x.contiguous(), W, index, bool(index_is_keys), int(key_offset),
+                                  bool(normalize_x), bool(want_norm))
 
 
 class _FSQ(torch.autograd.Function):

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, VQB_BF16, VQB_F32, FSQParams, check
 
 __all__ = [
-    'Operand', 'pack_rows', 'assign', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
+    'Operand', 'as_operand', 'pack_rows', 'assign', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
     'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
     'fsq_decode', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
@@ -75,6 +75,7 @@ class Operand:
     dim: int
     nplanes: int
     half_sqnorm: torch.Tensor | None = None
+    plane_rows: int = 0  # row stride between planes; 0 = padded default, rows = zero-copy view of a bf16 tensor
 
 
 def operand_shape(rows: int, D: int) -> tuple[int, int]:
@@ -118,8 +119,8 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
     if l2:
         assert b.half_sqnorm is not None, 'L2 assignment needs the packed operand to carry half_sqnorm'
         h = b.half_sqnorm
-    _call('vqb_assign', lib.vqb_assign, _p(a.planes), a.nplanes, a.rows, _p(b.planes), b.nplanes, b.rows, a.dim, _p(h),
-                         index_offset, _p(keys), backend, _stream())
+    _call('vqb_assign', lib.vqb_assign, _p(a.planes), a.nplanes, a.rows, a.plane_rows, _p(b.planes), b.nplanes, b.rows,
+          b.plane_rows, a.dim, _p(h), index_offset, _p(keys), backend, _stream())
     return keys
 
 
@@ -152,30 +153,45 @@ def _loss_ws(device):
     return _WS[key]
 
 
-def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor, *, want_norm: bool,
-                    out_dtype: torch.dtype = torch.float32):
-    """(z_ste [N,D], mse4 [4]) — see vqb_gather_ste_loss."""
+def as_operand(x: torch.Tensor) -> Operand | None:
+    """Zero-copy one-plane operand view of a contiguous bf16 [rows, D] tensor whose D needs no padding."""
+    if x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 2 and x.data_ptr() % 16 == 0:
+        rows, D = x.shape
+        if operand_shape(rows, D)[1] == D:
+            return Operand(x, rows, D, 1, None, plane_rows=rows)
+    return None
+
+
+def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, *, quant: torch.Tensor | None = None,
+                    keys: torch.Tensor | None = None, key_offset: int = 0, normalize_x: bool = False,
+                    want_norm: bool, want_quant: bool = False, want_xnorm: bool = False):
+    """Fused gather + STE + loss (+ token normalisation, + key unpack) — see vqb_gather_ste_loss.
+    -> (z_ste [N,D] fp32, mse4 [4], quant int64 [N] | None, x_normalised [N,D] fp32 | None)"""
     lib = _lib.load()
-    _cuda(x, W, quant)
-    assert W.dtype == torch.float32 and quant.dtype == torch.int64
+    _cuda(x, W, quant, keys)
+    assert W.dtype == torch.float32 and (quant is None) != (keys is None)
     N, D = x.shape
-    z = torch.empty((N, D), dtype=out_dtype, device=x.device)
+    z = torch.empty((N, D), dtype=torch.float32, device=x.device)
     mse4 = torch.empty((4,), dtype=torch.float32, device=x.device)
+    qo = torch.empty((N,), dtype=torch.int64, device=x.device) if want_quant else None
+    xn = torch.empty((N, D), dtype=torch.float32, device=x.device) if want_xnorm else None
     partials, ticket = _loss_ws(x.device)
-    _call('vqb_gather_ste_loss', lib.vqb_gather_ste_loss, _p(x), _dt(x), N, D, _p(W), W.shape[0], _p(quant), _p(z), _dt(z),
-                                  int(want_norm), _p(mse4), _p(partials), _p(ticket), _stream())
-    return z, mse4
+    _call('vqb_gather_ste_loss', lib.vqb_gather_ste_loss, _p(x), _dt(x), N, D, int(normalize_x), _p(W), W.shape[0],
+          _p(quant), _p(keys), key_offset, _p(qo), _p(xn), _p(z), int(want_norm), _p(mse4), _p(partials), _p(ticket),
+          _stream())
+    return z, mse4, qo, xn
 
 
 def quantize_backward(g_z: torch.Tensor, x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor,
-                      g4: torch.Tensor, *, want_norm: bool, need_gW: bool):
+                      g4: torch.Tensor, *, normalize_x: bool = False, want_norm: bool, need_gW: bool):
     lib = _lib.load()
     _cuda(g_z, x, W, quant, g4)
+    assert g_z.dtype == torch.float32 and g4.dtype == torch.float32
     N, D = x.shape
     gx = torch.empty_like(x)
     gW = torch.zeros_like(W) if need_gW else None
-    _call('vqb_quantize_backward', lib.vqb_quantize_backward, _p(g_z), _dt(g_z), _p(x), _dt(x), _p(W), W.shape[0], _p(quant), N, D, _p(g4),
-                                    int(want_norm), _p(gx), _dt(gx), _p(gW), _stream())
+    _call('vqb_quantize_backward', lib.vqb_quantize_backward, _p(g_z), _p(x), _dt(x), int(normalize_x), _p(W),
+          W.shape[0], _p(quant), N, D, _p(g4), int(want_norm), _p(gx), _p(gW), _stream())
     return gx, gW
 
 

@@ -95,8 +95,11 @@ class BaseQuantizer(nn.Module):
     def encode(self, x: torch.Tensor, memo: dict):
         x = self._callbacks.before_encode(x, memo)
         enc = get_memo(memo, 'encode')
-        if '_codebook_operand' in memo:  # packed by a normalising callback in the same pass
-            enc['_codebook_operand'] = memo.pop('_codebook_operand')
+        for flag in ('_normalize_codebook', '_normalize_x', '_lazy_unpack'):  # requests of the callbacks / forward
+            if flag in memo:
+                enc[flag] = memo[flag]
+        memo.pop('_normalize_codebook', None)
+        memo.pop('_lazy_unpack', None)
         quant, memo['encode'] = self._encode(x, enc)
         quant = self._callbacks.after_encode(x, quant, memo)
         return x, quant, memo
@@ -169,19 +172,24 @@ class VectorQuantizer(BaseQuantizer):
 
     @torch.no_grad()
     def _encode(self, x: torch.Tensor, memo: dict):
+        """Nearest code per token.  Launches: codebook pack (normalise-in-place + operand planes + key reset),
+        [token pack unless zero-copy], tcgen05 assignment, [key unpack unless deferred to the gather kernel]."""
         x = _check_tokens(x.detach(), self.embedding_dim)
         W = self._weight().data
         metric = self._distance.metric
-        book = memo.pop('_codebook_operand', None)
-        if book is None:
-            book = Fq.pack_codebook(W, metric, precision=self.precision)
-        keys = Fq.nearest_code(x, book, metric, precision=self.precision)
-        quant = ops.unpack_keys(keys)
+        keys = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
+        book = Fq.pack_codebook(W, metric, precision=self.precision,
+                                writeback_normalized=memo.pop('_normalize_codebook', False), reset_keys=keys)
+        normalize_tokens = memo.pop('_normalize_x', False)
+        Fq.nearest_code(x, book, metric, precision=self.precision, keys=keys, keys_are_reset=True,
+                        normalize_tokens=normalize_tokens)
         memo['keys'] = keys
         if self.training and self._callbacks.needs_column_nearest:
             offset = parallel.rank() * x.shape[0] if self._callbacks.column_nearest_global else 0
             memo['column_keys'] = Fq.column_nearest(x, book, metric, precision=self.precision, index_offset=offset)
-        return quant, memo
+        if memo.pop('_lazy_unpack', False):
+            return keys, memo            # forward(): the fused gather kernel unpacks the indices
+        return ops.unpack_keys(keys), memo
 
     def _decode(self, quant: torch.Tensor, memo: dict):
         """Decode-only gather (decode_from_quant); any index shape.  Inference path: no autograd."""
@@ -198,9 +206,17 @@ class VectorQuantizer(BaseQuantizer):
             if self._callbacks.overrides(hook):
                 raise NotImplementedError(f'callbacks overriding {hook} are not supported by the fused decode/loss path')
         x = _check_tokens(x, self.embedding_dim)
-        x, quant, memo = self.encode(x, memo)
-        memo.update(x=x, quant=quant)
-        z, mse4 = Fq.quantize_ste_loss(x, self._weight(), quant, self._loss_terms())
+        # Callbacks that update the codebook in after_encode (training) need int64 indices before the gather;
+        # otherwise the packed keys go straight into the fused kernel, which also emits memo['quant'].
+        lazy_unpack = not (self.training and self._callbacks.overrides('after_encode'))
+        memo['_lazy_normalize'] = True
+        memo['_lazy_unpack'] = lazy_unpack
+        x, index, memo = self.encode(x, memo)
+        memo.pop('_lazy_normalize', None)
+        normalize_x = memo.pop('_normalize_x', False)
+        z, mse4, quant, xn = Fq.quantize_ste_loss(x, self._weight(), index, self._loss_terms(),
+                                                  index_is_keys=lazy_unpack, normalize_x=normalize_x)
+        memo.update(x=xn if normalize_x else x, quant=quant)
         memo['decode'] = get_memo(memo, 'decode')
         loss_memo = get_memo(memo, 'loss')
         loss = None
