@@ -350,7 +350,17 @@ def main():
                      d2h_bytes_per_step=d2h),
             gpu_launches=launches_per_step * args.steps)))
     if world > 1:
+        # graphs that captured NCCL collectives must be gone before the communicator is torn down; a watchdog
+        # guarantees that a stuck teardown cannot hang the launcher after the result line has been printed
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        graphs = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == '__main__':

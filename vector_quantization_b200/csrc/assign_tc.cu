@@ -123,6 +123,11 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -145,6 +150,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // ---------------------------------------------------------------------------------------------
 // epilogue helpers
 // ---------------------------------------------------------------------------------------------
+#ifdef VQB_TIMELINE  // developer build: clock64 timeline of the first tiles of CTA 0 (tools/timeline.py)
+__device__ long long g_ts[3][64][4];
+#define TS(role, tile, ev) do { if (blockIdx.x == 0 && (tile) < 64) g_ts[role][tile][ev] = clock64(); } while (0)
+#else
+#define TS(role, tile, ev) do { } while (0)
+#endif
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -177,9 +188,7 @@ __device__ __forceinline__ void stash_chunk(uint32_t pred, uint32_t saddr, const
 // USE_SIDE: score = acc - side[col] (L2);  MASK: columns >= n_valid (zero-padded rows of the last code
 // tile) are excluded.
 template <bool USE_SIDE, bool MASK>
-__device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t side_saddr, uint32_t col_base,
-                                             int n_valid, uint32_t stash_saddr, float& best, uint32_t& best_col) {
-  float s[32];
+__device__ __forceinline__ void chunk_scores(const uint32_t (&r)[32], uint32_t side_saddr, int n_valid, float (&s)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     if constexpr (USE_SIDE) {
@@ -200,17 +209,41 @@ __device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t s
     for (int j = 0; j < 32; ++j)
       if (j >= n_valid) s[j] = -INFINITY;
   }
+}
+__device__ __forceinline__ float chunk_max(const float (&s)[32]) {
   float m[11];
 #pragma unroll
   for (int j = 0; j < 10; ++j) m[j] = fmax3(s[3 * j], s[3 * j + 1], s[3 * j + 2]);
   m[10] = fmaxf(s[30], s[31]);
   const float m0 = fmax3(m[0], m[1], m[2]), m1 = fmax3(m[3], m[4], m[5]), m2 = fmax3(m[6], m[7], m[8]);
-  const float mx = fmax3(fmax3(m0, m1, m2), m[9], m[10]);
+  return fmax3(fmax3(m0, m1, m2), m[9], m[10]);
+}
+__device__ __forceinline__ void chunk_commit(float mx, const float (&s)[32], uint32_t col_base, uint32_t stash_saddr,
+                                             float& best, uint32_t& best_col) {
   const bool better = mx > best;  // strict: an equal score later in the scan never displaces an earlier chunk
   best = fmaxf(best, mx);
   best_col = better ? col_base : best_col;
   // warp-uniform skip: after the first few code tiles most chunks improve no row of the warp
   if (__any_sync(0xffffffffu, better)) stash_chunk((uint32_t)better, stash_saddr, s);
+}
+template <bool USE_SIDE, bool MASK>
+__device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t side_saddr, uint32_t col_base,
+                                             int n_valid, uint32_t stash_saddr, float& best, uint32_t& best_col) {
+  float s[32];
+  chunk_scores<USE_SIDE, MASK>(r, side_saddr, n_valid, s);
+  chunk_commit(chunk_max(s), s, col_base, stash_saddr, best, best_col);
+}
+// two adjacent chunks at once: the two max trees are independent, which doubles the ILP of the reduction
+template <bool USE_SIDE, bool MASK>
+__device__ __forceinline__ void pair_argmax(const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t side_saddr,
+                                            uint32_t col_base, int nv0, int nv1, uint32_t stash_saddr, float& best,
+                                            uint32_t& best_col) {
+  float s0[32], s1[32];
+  chunk_scores<USE_SIDE, MASK>(r0, side_saddr, nv0, s0);
+  chunk_scores<USE_SIDE, MASK>(r1, side_saddr + 128, nv1, s1);
+  const float mx0 = chunk_max(s0), mx1 = chunk_max(s1);
+  chunk_commit(mx0, s0, col_base, stash_saddr, best, best_col);
+  chunk_commit(mx1, s1, col_base + 32, stash_saddr, best, best_col);
 }
 
 // first position of `best` inside the stashed winning chunk (lowest index wins ties, like torch.argmin)
@@ -227,10 +260,10 @@ __device__ __forceinline__ uint32_t resolve_index(uint32_t stash_saddr, float be
   return (uint32_t)j;
 }
 
-// One warp's NCH x 32 columns of a 128 x 256 accumulator; TMEM loads are double-buffered so that the load
-// of chunk c+1 is in flight while chunk c is reduced.  The accumulator is released to the MMA warp as soon
+// One warp's 4 x 32 columns of a 128 x 256 accumulator; TMEM loads are double-buffered so that the load of
+// chunk c+1 is in flight while chunk c is reduced.  The accumulator is released to the MMA warp as soon
 // as the last load has landed in registers.
-template <bool USE_SIDE, bool MASK, int NCH>
+template <bool USE_SIDE, bool MASK>
 __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr, uint32_t gcol0, int b_rows,
                                             uint64_t* tmem_empty_bar, int lane, uint32_t stash_saddr, float& best,
                                             uint32_t& best_col) {
@@ -240,43 +273,41 @@ __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr,
     const int left = b_rows - (int)(gcol0 + 32 * c);
     return left >= 32 ? 32 : (left < 0 ? 0 : left);
   };
-  auto release = [&]() {
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(tmem_empty_bar);  // every load of this warp is in registers
-  };
   tmem_ld32(taddr, ra);
   tmem_ld_wait(ra);
   tmem_ld32(taddr + 32, rb);
   chunk_argmax<USE_SIDE, MASK>(ra, side_saddr, gcol0, nv(0), stash_saddr, best, best_col);
   tmem_ld_wait(rb);
-  if constexpr (NCH == 2) {
-    release();
-    chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), stash_saddr, best, best_col);
-  } else {
-    tmem_ld32(taddr + 64, ra);
-    chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), stash_saddr, best, best_col);
-    tmem_ld_wait(ra);
-    tmem_ld32(taddr + 96, rb);
-    chunk_argmax<USE_SIDE, MASK>(ra, side_saddr + 256, gcol0 + 64, nv(2), stash_saddr, best, best_col);
-    tmem_ld_wait(rb);
-    release();
-    chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 384, gcol0 + 96, nv(3), stash_saddr, best, best_col);
-  }
+  tmem_ld32(taddr + 64, ra);
+  chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), stash_saddr, best, best_col);
+  tmem_ld_wait(ra);
+  tmem_ld32(taddr + 96, rb);
+  chunk_argmax<USE_SIDE, MASK>(ra, side_saddr + 256, gcol0 + 64, nv(2), stash_saddr, best, best_col);
+  tmem_ld_wait(rb);
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tmem_empty_bar);  // every load of this warp is in registers: buffer is free
+  chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 384, gcol0 + 96, nv(3), stash_saddr, best, best_col);
 }
 
-// Epilogue role: NEW warps; warp%4 selects the TMEM lane quarter, (warp-2)/4 the column slice.
+// Epilogue role.  NEW = 8: one group of 8 warps drains every tile.  NEW = 16: TWO groups of 8 warps, group g
+// owns TMEM accumulator g, i.e. every other tile — while one group reduces tile i from registers the other
+// is already loading tile i+1, which hides the barrier hand-off and TMEM-load latencies that otherwise
+// serialise with the reduction.  Inside a group, warp%4 selects the TMEM lane quarter (hardware rule) and
+// (warp_in_group / 4) the 128-column half.  Each group keeps its own running best per row and publishes it
+// with the 64-bit atomicMin (the combine is associative: same result as a single group).
 template <bool USE_SIDE, int NEW>
 __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_base, uint8_t* stash_smem,
                                               float* side_smem, uint64_t* tmem_full, uint64_t* tmem_empty, int t0,
                                               int t1, int b_tiles, int a_rows, int b_rows,
                                               const float* __restrict__ b_half_sqnorm, uint32_t b_index_offset,
                                               unsigned long long* __restrict__ keys) {
-  constexpr int NCH = 8 / (NEW / 4);           // 32-column chunks per warp per tile: 4 (8 warps) or 2 (16 warps)
+  constexpr int GROUPS = NEW / 8;
   const int ew = warp - 2;
+  const int group = ew >> 3, ewg = ew & 7;
   const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32): the only ones this warp may read
-  const uint32_t col0 = (uint32_t)(ew >> 2) * (NCH * 32);
-  const int etid = threadIdx.x - 64;
+  const uint32_t col0 = (uint32_t)(ewg >> 2) * 128;
+  const int gtid = (threadIdx.x - 64) & 255;   // thread index inside the group
   const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
   const uint32_t side_base = smem_u32(side_smem) + col0 * 4;
   const uint32_t stash_saddr = smem_u32(stash_smem) + (uint32_t)ew * 4096 + (uint32_t)lane * 16;
@@ -285,25 +316,27 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
   float best = -INFINITY;
   uint32_t best_col = 0xffffffffu;
   int at = t0 / b_tiles, bt = t0 - at * b_tiles;
-  uint32_t buf = 0, par0 = 0, par1 = 0;        // accumulator buffer and its per-buffer phase parity
+  uint32_t par0 = 0, par1 = 0;                 // per-accumulator phase parity
   for (int t = t0; t < t1; ++t) {
-    if constexpr (USE_SIDE) {
-      // NEW*32 epilogue threads stage the 256 side terms of this code tile (vector padded to rows_pad with +inf).
-      // The barrier also orders "everyone finished the tile that used this buffer two tiles ago".
-      if (etid < BN) side_smem[buf * BN + etid] = __ldg(b_half_sqnorm + bt * BN + etid);
-      named_bar_sync(1, NEW * 32);
+    const uint32_t buf = (uint32_t)(t - t0) & 1u;
+    if (GROUPS == 1 || buf == (uint32_t)group) {
+      if constexpr (USE_SIDE) {
+        // the group's 256 threads stage the 256 side terms of this code tile (vector padded with +inf);
+        // the barrier also orders "everyone in the group finished the tile that used this buffer before"
+        side_smem[buf * BN + gtid] = __ldg(b_half_sqnorm + bt * BN + gtid);
+        named_bar_sync(1 + group, 256);
+      }
+      mbar_wait(tmem_full + buf, buf ? par1 : par0);
+      tc_fence_after();
+      const uint32_t taddr = taddr0 + buf * BN;
+      const uint32_t side_saddr = side_base + buf * (BN * 4);
+      const uint32_t gcol0 = (uint32_t)(bt * BN) + col0;
+      if (last_partial && bt == b_tiles - 1)
+        tile_argmax<USE_SIDE, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+      else
+        tile_argmax<USE_SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+      if (buf) par1 ^= 1; else par0 ^= 1;
     }
-    mbar_wait(tmem_full + buf, buf ? par1 : par0);
-    tc_fence_after();
-    const uint32_t taddr = taddr0 + buf * BN;
-    const uint32_t side_saddr = side_base + buf * (BN * 4);
-    const uint32_t gcol0 = (uint32_t)(bt * BN) + col0;
-    if (last_partial && bt == b_tiles - 1)
-      tile_argmax<USE_SIDE, true, NCH>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
-    else
-      tile_argmax<USE_SIDE, false, NCH>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
-    if (buf) par1 ^= 1; else par0 ^= 1;
-    buf ^= 1;
     if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish
       const int row = at * BM + row_in_tile;
       if (row < a_rows && best_col != 0xffffffffu) {
@@ -344,7 +377,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t a_tiles = (a_rows + BM - 1) / BM, b_tiles = (b_rows + BN - 1) / BN;
   const int64_t total = a_tiles * b_tiles;
   const int64_t t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
@@ -358,7 +391,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, NEW);
+      mbar_init(tmem_empty + i, 8);  // the 8 warps of the group that drains this accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -369,22 +402,28 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-converged, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       int64_t at = t0 / b_tiles, bt = t0 - at * b_tiles;
       for (int64_t t = t0; t < t1; ++t) {
         const int a_row = (int)(at * BM), b_row = (int)(bt * BN);
         if constexpr (WHOLE) {
+          TS(0, t - t0, 0);
           mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          for (int p = 0; p < pa; ++p)
-            tma_load_2d(sa + p * kABytes, &tmap_a, full_bar + stage, 0, (int)(p * a_rows_pad) + a_row);
-          uint8_t* sb = sa + pa * kABytes;
-          for (int p = 0; p < pb; ++p)
-            tma_load_2d(sb + p * kBBytes, &tmap_b, full_bar + stage, 0, (int)(p * b_rows_pad) + b_row);
+          TS(0, t - t0, 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            for (int p = 0; p < pa; ++p)
+              tma_load_2d(sa + p * kABytes, &tmap_a, full_bar + stage, 0, (int)(p * a_rows_pad) + a_row);
+            uint8_t* sb = sa + pa * kABytes;
+            for (int p = 0; p < pb; ++p)
+              tma_load_2d(sb + p * kBBytes, &tmap_b, full_bar + stage, 0, (int)(p * b_rows_pad) + b_row);
+          }
+          __syncwarp();
+          TS(0, t - t0, 2);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         } else {
 #pragma unroll 1
@@ -393,10 +432,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll 1
             for (int kb = 0; kb < kblocks; ++kb) {
               mbar_wait(empty_bar + stage, phase ^ 1);
-              mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
-              uint8_t* sa = smem + (size_t)stage * stage_bytes;
-              tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, arow);
-              tma_load_2d(sa + kABytes, &tmap_b, full_bar + stage, kb * BK, brow);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, arow);
+                tma_load_2d(sa + kABytes, &tmap_b, full_bar + stage, kb * BK, brow);
+              }
+              __syncwarp();
               if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
           }
@@ -405,8 +447,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-converged, one elected lane issues) =====================
+    {
       // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=256, M=128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t smem_base = smem_u32(smem);
@@ -416,25 +458,32 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int64_t t = t0; t < t1; ++t, ++local) {
         const int buf = (int)(local & 1);
         const uint32_t use = (uint32_t)(local >> 1);
+        TS(1, local, 0);
         mbar_wait(tmem_empty + buf, (use & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
         if constexpr (WHOLE) {
+          TS(1, local, 1);
           mbar_wait(full_bar + stage, phase);
+          TS(1, local, 2);
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)pa * kABytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int term = 0; term < kMaxTerms; ++term) {
-            if (term < terms.n) {
-              const uint64_t adesc = make_smem_desc<BK>(sa + (uint32_t)terms.a[term] * kABytes);
-              const uint64_t bdesc = make_smem_desc<BK>(sb + (uint32_t)terms.b[term] * kBBytes);
+            for (int term = 0; term < kMaxTerms; ++term) {
+              if (term < terms.n) {
+                const uint64_t adesc = make_smem_desc<BK>(sa + (uint32_t)terms.a[term] * kABytes);
+                const uint64_t bdesc = make_smem_desc<BK>(sb + (uint32_t)terms.b[term] * kBBytes);
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (term | k) != 0);
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (term | k) != 0);
+              }
             }
+            umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
+            umma_commit(tmem_full + buf);    // accumulator complete -> epilogue
           }
-          umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         } else {
           const int nv = terms.n * kblocks;
@@ -443,15 +492,19 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(full_bar + stage, phase);
             tc_fence_after();
             const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-            const uint64_t adesc = make_smem_desc<BK>(sa), bdesc = make_smem_desc<BK>(sa + kABytes);
+            if (elect_one()) {
+              const uint64_t adesc = make_smem_desc<BK>(sa), bdesc = make_smem_desc<BK>(sa + kABytes);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
-              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (v | k) != 0);
-            umma_commit(empty_bar + stage);
+              for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (v | k) != 0);
+              umma_commit(empty_bar + stage);
+              if (v == nv - 1) umma_commit(tmem_full + buf);  // accumulator complete -> epilogue
+            }
+            __syncwarp();
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(tmem_full + buf);  // accumulator complete -> epilogue
+        TS(1, local, 3);
       }
     }
   } else {
@@ -563,9 +616,10 @@ int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad
                      int64_t b_rows, int64_t b_pad, int D, const float* h, int64_t off, unsigned long long* keys,
                      cudaStream_t st) {
   const int Dp = (int)vqb_operand_dp(D);
-  // 8 epilogue warps (2 per SM sub-partition) measured faster than 16 on B200 for every shape (the extra
-  // warps add per-tile barrier traffic without raising TMEM-load or ALU throughput); VQB_EPILOGUE_WARPS=16
-  // keeps the alternative reachable for experiments.
+  // One epilogue group (8 warps) is the default: the two-group variant (16 warps, one group per TMEM
+  // accumulator) measured SLOWER on B200 for D = 32 (0.103 vs 0.092 ms at cfg 2) because 576 threads cap the
+  // kernel at 96 registers (spills) and the second 32 KB stash costs a pipeline stage; it only wins for
+  // D = 8.  VQB_EPILOGUE_WARPS=16 keeps it reachable for experiments.
   static int new_override = -1;
   if (new_override < 0) {
     const char* e = getenv("VQB_EPILOGUE_WARPS");
@@ -588,3 +642,9 @@ int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad
 }
 
 }  // namespace vqb
+
+#ifdef VQB_TIMELINE
+extern "C" int vqb_debug_timeline(long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, vqb::g_ts, sizeof(vqb::g_ts));
+}
+#endif
