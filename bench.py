@@ -47,7 +47,16 @@ WORKLOADS = {
                              losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True)))),
                  oracle=dict(distance='Cosine', callback='VQKDCallback',
                              losses={'commitment_loss': dict(type='CommitmentLoss', norm=True)})),
+    # BASELINE.json configs[3]: CVQ-VAE training step with online anchor re-init (usage counters + EMA all-reduce)
+    'cfg4': dict(name='cfg4: CVQ-VAE training step (cosine, usage-EMA, NearestAnchor re-init), fwd + bwd', N=16384,
+                 K=8192, D=256, metric='Cosine', training=True,
+                 config=dict(type='VQGANQuantizer', distance=dict(type='CosineDistance'),
+                             callbacks=[dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='NearestAnchor'))],
+                             losses=dict(vqgan_loss=dict(type='VQGANLoss')), init_weights=dict(type='vqgan')),
+                 oracle=dict(distance='Cosine', callback='CVQVAECallback',
+                             losses={'vqgan_loss': dict(type='VQGANLoss')})),
 }
+# BASELINE.json configs[4] (codebook-sharded 262144 x 768 stress) is `--workload cfg5`, see run_cfg5().
 
 
 def emb(K, D):
@@ -125,9 +134,11 @@ def run_reference(args, wl):
     x, E, gz = synth(N, K, D, SEED)
     spec = O.QuantizerSpec(training=wl['training'], **wl['oracle'])
 
+    prob = torch.zeros(K) if wl['oracle'].get('callback') == 'CVQVAECallback' else None
+
     def step():
         xo = x.float().requires_grad_(True)
-        out = O.quantizer_forward(spec, [xo], E)
+        out = O.quantizer_forward(spec, [xo], E, prob)
         torch.autograd.backward((out['z_ste'][0], out['loss'][0]), (gz, torch.ones([])))
         return out
 
@@ -143,20 +154,85 @@ def run_reference(args, wl):
     return dict(value=value, ms=dt * 1e3, cores=threads, kind='port', sample=sample, steps=steps)
 
 
+def run_cfg5(args, rank, world, local_rank):
+    """Cluster-tokenizer stress: 262144 x 768 codebook sharded by contiguous row blocks over the ranks, 65536
+    CLIP-sized bf16 tokens replicated; step = normalise+pack the local shard, fused tcgen05 arg-min with global
+    code indices, packed (distance, index) min-loc all-reduce, index unpack."""
+    import torch.distributed as dist
+
+    from vector_quantization_b200 import ops, parallel
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    N, K, D = 65536, 262144, 768
+    lo, hi = parallel.shard_range(K, rank, world)
+    g = torch.Generator(device='cpu').manual_seed(SEED)
+    x = torch.randn(N, D, generator=g).to(torch.bfloat16).to(dev)
+    W = torch.randn(hi - lo, D, generator=torch.Generator(device='cpu').manual_seed(SEED + 1 + rank)).to(dev)
+    precision = os.environ.get('VQB_PRECISION', 'exact')
+
+    def step():
+        return parallel.sharded_nearest_code(x, W, 'Cosine', shard_lo=lo, precision=precision)[0]
+
+    ops.LAUNCHES = 0
+    step()
+    launches = ops.LAUNCHES
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = min(args.steps, 20)
+    e0.record()
+    for _ in range(steps):
+        quant = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    terms = {'exact': 3, 'high': 2, 'fast': 1}[precision]
+    if rank == 0:
+        print(json.dumps(dict(
+            metric='quantized tokens/sec', value=N / (ms * 1e-3), unit='tokens/s', n_gpus=world, steps=steps,
+            warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True, scaling='strong', vs_baseline=None,
+            dtype=f'bf16 tokens, fp32 codebook as {terms} exact bf16 plane(s)', data='synthetic',
+            config=dict(workload='cfg5: 262144x768 codebook sharded over the ranks, 65536 tokens replicated, '
+                                 'min-loc all-reduce', parallelism=f'codebook-sharded x{world}', precision=precision,
+                        l2_policy='operands (shard planes >= 150 MB) exceed L2'),
+            roofline=dict(bound='tensor', achieved=2.0 * N * (hi - lo) * D / (ms * 1e-3) / 1e12, unit='TFLOP/s',
+                          note='per-GPU algorithmic 2*N*K_shard*D over the WHOLE step (pack + assign + all-reduce)'),
+            gpu_launches=launches * steps, checksum=int(quant.sum()))))
+        sys.stdout.flush()
+    if world > 1:
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        dist.barrier()
+        dist.destroy_process_group()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS) + ['cfg5'])
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.workload == 'cfg5':
+        return run_cfg5(args, rank, world, local_rank)
+    wl = WORKLOADS[args.workload]
     metric, unit = 'quantized tokens/sec', 'tokens/s'
     base_cfg = dict(workload=wl['name'], tokens_per_gpu=wl['N'], codebook=f'{wl["K"]}x{wl["D"]} fp32 master',
                     token_dtype='bf16', parallelism=f'token-sharded x{world}' if world > 1 else 'single GPU')

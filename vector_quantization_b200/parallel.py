@@ -87,3 +87,30 @@ def unpack_keys_host(keys: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     score = u.to(torch.int32 if False else torch.int64)
     score = torch.where(score >= 2 ** 31, score - 2 ** 32, score).to(torch.int32).view(torch.float32)
     return score, idx
+
+
+# ---- codebook-sharded assignment (new functionality; BASELINE.json configs[4]) -------------
+def sharded_nearest_code(x: torch.Tensor, W_shard: torch.Tensor, metric: str, *, shard_lo: int | None = None,
+                         total_codes: int | None = None, precision: str = 'exact'):
+    """Tokens replicated, codebook rows split in contiguous blocks over the ranks.  Every rank runs the fused
+    tcgen05 arg-min against ITS rows with `b_index_offset = shard_lo` (keys carry GLOBAL code indices), then ONE
+    packed (distance, index) min-loc all-reduce over [N] picks the global nearest code — lowest global index on
+    ties, exactly `argmin` over the concatenated codebook.  Returns (quant int64 [N] global indices, keys)."""
+    from . import functional as Fq
+    from . import ops
+    if shard_lo is None:
+        assert total_codes is not None
+        shard_lo = shard_range(total_codes)[0]
+    keys = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
+    book = Fq.pack_codebook(W_shard, metric, precision=precision, reset_keys=keys)
+    Fq.nearest_code(x, book, metric, precision=precision, keys=keys, keys_are_reset=True, index_offset=shard_lo)
+    all_reduce_min_keys_(keys)
+    return ops.unpack_keys(keys), keys
+
+
+def sharded_decode(keys: torch.Tensor, W_shard: torch.Tensor, shard_lo: int) -> torch.Tensor:
+    """z[n] = W[quant[n]] with W sharded: every rank contributes the rows it owns (zeros elsewhere), summed by
+    one all-reduce (owner-writes + SUM; a reduce-scatter when the tokens are sharded too)."""
+    from . import ops
+    z = ops.gather_rows_by_key(W_shard, keys, shard_lo)   # rows whose global index falls outside the shard are 0
+    return all_reduce_sum_(z)
