@@ -9,33 +9,93 @@ namespace vqb {
 
 constexpr int kFsqTokens = 256;  // tokens per block iteration == threads per block
 
-template <typename TX, typename TO>
+// tanh with ABSOLUTE error <= ~5e-7 from two MUFU ops: 1 - 2 / (1 + exp(2v)).  The quantizer rounds
+// z = (tanh(.) * max_ - odd) / 2 to an integer, so only the absolute error matters: |dz| <= max_/2 * 5e-7 < 2e-6,
+// inside the documented 1e-5 round-half boundary band (libdevice tanhf costs ~4x more instructions and made
+// the kernel issue-bound at 30 % of HBM bandwidth).
+__device__ __forceinline__ float fsq_tanh(float v) {
+  const float e = __expf(2.f * v);              // +inf for large v -> 1 ; 0 for very negative v -> -1
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+// r / half with the exact fp32 quotient: half is a small integer, a power of two for the usual level counts
+__device__ __forceinline__ float fsq_div(float r, float half) {
+  const int h = (int)half;
+  return (h & (h - 1)) == 0 ? r * (1.f / half) : __fdiv_rn(r, half);
+}
+
+// One thread per token, D known at compile time: the D independent tanhf chains of a token are fully unrolled
+// (ILP) with every per-channel constant in registers.  A block stages a contiguous [256 tokens x D] slab through
+// shared memory so that global loads and stores stay coalesced although a token row is only 20-24 bytes.
+template <typename TX, typename TO, int DT>
 __global__ void __launch_bounds__(kFsqTokens) fsq_forward_kernel(const TX* __restrict__ x, int64_t N,
                                                                  const vqb_fsq_params p, TO* __restrict__ zq,
                                                                  int32_t* __restrict__ index) {
-  __shared__ float slab[kFsqTokens * 16];
-  const int D = p.D;
+  __shared__ __align__(16) float slab[kFsqTokens * (DT > 0 ? DT : 16)];
+  const int D = DT > 0 ? DT : p.D;
   for (int64_t base = (int64_t)blockIdx.x * kFsqTokens; base < N; base += (int64_t)gridDim.x * kFsqTokens) {
     const int64_t ntok = min((int64_t)kFsqTokens, N - base);
     const int nelem = (int)ntok * D;
-    for (int i = threadIdx.x; i < nelem; i += kFsqTokens) slab[i] = to_f32<TX>(x[base * D + i]);
+    // 128-bit staging copies for full slabs (256*D*sizeof is a multiple of 16 and the slab base is 16 B aligned)
+    constexpr int VEC = 16 / sizeof(TX);
+    const bool vec_in = ntok == kFsqTokens && ((uintptr_t)x % 16 == 0);
+    if (vec_in) {
+      const uint4* src = reinterpret_cast<const uint4*>(x + base * D);
+      for (int i = threadIdx.x; i < nelem / VEC; i += kFsqTokens) {
+        const uint4 raw = src[i];
+        if constexpr (sizeof(TX) == 4) {
+          *reinterpret_cast<uint4*>(slab + i * 4) = raw;
+        } else {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            slab[i * 8 + 2 * j] = f.x;
+            slab[i * 8 + 2 * j + 1] = f.y;
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < nelem; i += kFsqTokens) slab[i] = to_f32<TX>(x[base * D + i]);
+    }
     __syncthreads();
     if (threadIdx.x < ntok) {
       int code = 0;
-#pragma unroll 1
-      for (int d = 0; d < D; ++d) {
-        const float v = slab[threadIdx.x * D + d];
-        // z = tanh(x + atanh(odd/max_)) * max_ - odd ; z /= 2      fsq/quantizers.py:118-119
-        float z = __fsub_rn(__fmul_rn(tanhf(__fadd_rn(v, p.shift[d])), p.max_[d]), p.odd[d]);
-        z = z * 0.5f;
-        const float r = rintf(z);  // torch.round: half to even; ste value z + (r - z) == r exactly
-        slab[threadIdx.x * D + d] = __fdiv_rn(r, p.half[d]);                     // :123
-        code += ((int)r + (int)p.half[d]) * p.cumprod[d];                        // :124-125, :65-68
+      float out[DT > 0 ? DT : 16];
+#pragma unroll
+      for (int d = 0; d < (DT > 0 ? DT : 16); ++d) {
+        if (DT > 0 || d < D) {
+          const float v = slab[threadIdx.x * D + d];
+          // z = tanh(x + atanh(odd/max_)) * max_ - odd ; z /= 2      fsq/quantizers.py:118-119
+          float z = __fsub_rn(__fmul_rn(fsq_tanh(__fadd_rn(v, p.shift[d])), p.max_[d]), p.odd[d]);
+          z = z * 0.5f;
+          const float r = rintf(z);  // torch.round: half to even; ste value z + (r - z) == r exactly
+          out[d] = fsq_div(r, p.half[d]);                                      // :123
+          code += ((int)r + (int)p.half[d]) * p.cumprod[d];                      // :124-125, :65-68
+        }
       }
+#pragma unroll
+      for (int d = 0; d < (DT > 0 ? DT : 16); ++d)
+        if (DT > 0 || d < D) slab[threadIdx.x * D + d] = out[d];
       if (index) index[base + threadIdx.x] = code;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nelem; i += kFsqTokens) zq[base * D + i] = from_f32<TO>(slab[i]);
+    constexpr int VECO = 16 / sizeof(TO);
+    if (ntok == kFsqTokens && ((uintptr_t)zq % 16 == 0)) {
+      uint4* dst = reinterpret_cast<uint4*>(zq + base * D);
+      for (int i = threadIdx.x; i < nelem / VECO; i += kFsqTokens) {
+        if constexpr (sizeof(TO) == 4) {
+          dst[i] = *reinterpret_cast<const uint4*>(slab + i * 4);
+        } else {
+          uint4 raw;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(slab[i * 8 + 2 * j], slab[i * 8 + 2 * j + 1]);
+          dst[i] = raw;
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < nelem; i += kFsqTokens) zq[base * D + i] = from_f32<TO>(slab[i]);
+    }
     __syncthreads();
   }
 }
@@ -47,7 +107,7 @@ __global__ void __launch_bounds__(256) fsq_backward_kernel(const TG* __restrict_
   const int D = p.D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int d = (int)(i % D);
-    const float t = tanhf(__fadd_rn(to_f32<TX>(x[i]), p.shift[d]));
+    const float t = fsq_tanh(__fadd_rn(to_f32<TX>(x[i]), p.shift[d]));
     // d zq / d x = max_/(2*half) * (1 - tanh^2)   (round is straight-through)
     const float g = to_f32<TG>(gz[i]) / p.half[d] * 0.5f * p.max_[d] * (1.f - t * t);
     gx[i] = from_f32<TX>(g);
@@ -86,14 +146,24 @@ int vqb_fsq_forward(const void* x, int x_dtype, int64_t N, const vqb_fsq_params*
   int64_t blocks64 = (N + kFsqTokens - 1) / kFsqTokens;
   const int blocks = (int)(blocks64 < (int64_t)sm_count() * 8 ? blocks64 : (int64_t)sm_count() * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == VQB_F32 && out_dtype == VQB_F32)
-    fsq_forward_kernel<float, float><<<blocks, kFsqTokens, 0, st>>>((const float*)x, N, *p, (float*)zq, index);
-  else if (x_dtype == VQB_BF16 && out_dtype == VQB_BF16)
-    fsq_forward_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, kFsqTokens, 0, st>>>((const __nv_bfloat16*)x, N, *p, (__nv_bfloat16*)zq, index);
-  else if (x_dtype == VQB_BF16 && out_dtype == VQB_F32)
-    fsq_forward_kernel<__nv_bfloat16, float><<<blocks, kFsqTokens, 0, st>>>((const __nv_bfloat16*)x, N, *p, (float*)zq, index);
-  else
-    VQB_REQUIRE(false, "vqb_fsq_forward: unsupported dtype combination");
+#define VQB_FSQ_LAUNCH(TX, TO, DT)                                                                         \
+  fsq_forward_kernel<TX, TO, DT><<<blocks, kFsqTokens, 0, st>>>((const TX*)x, N, *p, (TO*)zq, index)
+#define VQB_FSQ_D(TX, TO)                                        \
+  switch (p->D) {                                                \
+    case 3: VQB_FSQ_LAUNCH(TX, TO, 3); break;                    \
+    case 4: VQB_FSQ_LAUNCH(TX, TO, 4); break;                    \
+    case 5: VQB_FSQ_LAUNCH(TX, TO, 5); break;                    \
+    case 6: VQB_FSQ_LAUNCH(TX, TO, 6); break;                    \
+    case 7: VQB_FSQ_LAUNCH(TX, TO, 7); break;                    \
+    case 8: VQB_FSQ_LAUNCH(TX, TO, 8); break;                    \
+    default: VQB_FSQ_LAUNCH(TX, TO, 0); break;                   \
+  }
+  if (x_dtype == VQB_F32 && out_dtype == VQB_F32) { VQB_FSQ_D(float, float) }
+  else if (x_dtype == VQB_BF16 && out_dtype == VQB_BF16) { VQB_FSQ_D(__nv_bfloat16, __nv_bfloat16) }
+  else if (x_dtype == VQB_BF16 && out_dtype == VQB_F32) { VQB_FSQ_D(__nv_bfloat16, float) }
+  else { VQB_REQUIRE(false, "vqb_fsq_forward: unsupported dtype combination"); }
+#undef VQB_FSQ_D
+#undef VQB_FSQ_LAUNCH
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

@@ -72,6 +72,92 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
   }
 }
 
+// Vectorised variant for D % 8 == 0 (Dp == D or zero-padded tail): every lane owns 8 contiguous elements per
+// step (128-bit loads/stores), keeps them in registers across the norm reduction, and writes each plane once.
+template <typename T, int G, int NV>
+__global__ void __launch_bounds__(256) pack_rows_vec_kernel(
+    const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
+    __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
+    unsigned long long* __restrict__ keys, int64_t n_keys) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_keys; i += (int64_t)gridDim.x * blockDim.x)
+    keys[i] = ~0ull;
+  const int lane = threadIdx.x % G;
+  const int64_t rows_per_block = blockDim.x / G;
+  for (int64_t r = blockIdx.x * rows_per_block + threadIdx.x / G; r < rows_pad;
+       r += (int64_t)gridDim.x * rows_per_block) {  // rows_pad is a multiple of 256: warp-uniform trip count
+    const bool real = r < rows;
+    float v[NV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int d0 = (it * G + lane) * 8;
+      if (real && d0 < D) {
+        if constexpr (sizeof(T) == 4) {
+          const float4 a = *reinterpret_cast<const float4*>(src + r * D + d0);
+          const float4 b = *reinterpret_cast<const float4*>(src + r * D + d0 + 4);
+          v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w;
+          v[it][4] = b.x; v[it][5] = b.y; v[it][6] = b.z; v[it][7] = b.w;
+        } else {
+          const uint4 raw = *reinterpret_cast<const uint4*>(src + r * D + d0);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+            v[it][2 * i] = f.x;
+            v[it][2 * i + 1] = f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[it][i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss = fmaf(v[it][i], v[it][i], ss);
+    }
+    ss = group_sum<G>(ss);
+    const float denom = normalize ? fmaxf(sqrtf(ss), kNormEps) : 1.f;
+    float ss2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int d0 = (it * G + lane) * 8;
+      if (normalize) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[it][i] = __fdiv_rn(v[it][i], denom);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss2 = fmaf(v[it][i], v[it][i], ss2);
+      if (d0 < Dp) {
+        if (writeback && real && d0 < D) {
+          *reinterpret_cast<float4*>(writeback + r * D + d0) = make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
+          *reinterpret_cast<float4*>(writeback + r * D + d0 + 4) = make_float4(v[it][4], v[it][5], v[it][6], v[it][7]);
+        }
+        float rem[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rem[i] = v[it][i];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          if (p < planes) {
+            uint4 raw;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              h[i] = __floats2bfloat162_rn(rem[2 * i], rem[2 * i + 1]);
+              const float2 back = __bfloat1622float2(h[i]);
+              rem[2 * i] -= back.x;       // exact: v == hi + mid + lo
+              rem[2 * i + 1] -= back.y;
+            }
+            *reinterpret_cast<uint4*>(dst + ((int64_t)p * rows_pad + r) * Dp + d0) = raw;
+          }
+        }
+      }
+    }
+    if (half_sqnorm) {
+      ss2 = group_sum<G>(ss2);
+      if (lane == 0) half_sqnorm[r] = real ? 0.5f * ss2 : INFINITY;
+    }
+  }
+}
+
 template <typename TI, typename TO, int G>
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const TI* __restrict__ x, int64_t rows, int D,
                                                          TO* __restrict__ y) {
@@ -183,6 +269,33 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
   const int64_t rows_pad = vqb_operand_rows_pad(rows);
   const int Dp = (int)vqb_operand_dp(D);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool aligned = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst_planes % 16 == 0) &&
+                       (writeback == nullptr || (uintptr_t)writeback % 16 == 0);
+  if (D % 8 == 0 && Dp <= 2048 && aligned) {  // vector path
+    const int slices = Dp / 8;
+    int gv = 1;
+    while (gv < 32 && gv < slices) gv <<= 1;
+    int nv = 1;
+    while (nv * gv < slices) nv <<= 1;
+    const int rpb = 256 / gv;
+    int64_t blocks64 = (rows_pad + rpb - 1) / rpb;
+    const int blocks = (int)(blocks64 < (int64_t)sm_count() * 8 ? blocks64 : (int64_t)sm_count() * 8);
+#define VQB_PACK_CASE(G_, NV_)                                                                                       \
+    if (gv == G_ && nv == NV_) {                                                                                     \
+      if (src_dtype == VQB_F32)                                                                                      \
+        pack_rows_vec_kernel<float, G_, NV_><<<blocks, 256, 0, st>>>((const float*)src, rows, rows_pad, D, Dp,        \
+            normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys, keys ? n_keys : 0);        \
+      else                                                                                                           \
+        pack_rows_vec_kernel<__nv_bfloat16, G_, NV_><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, rows,         \
+            rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys,            \
+            keys ? n_keys : 0);                                                                                      \
+      VQB_LAUNCH_OK();                                                                                               \
+      return VQB_OK;                                                                                                 \
+    }
+    VQB_PACK_CASE(1, 1) VQB_PACK_CASE(2, 1) VQB_PACK_CASE(4, 1) VQB_PACK_CASE(8, 1) VQB_PACK_CASE(16, 1)
+    VQB_PACK_CASE(32, 1) VQB_PACK_CASE(32, 2) VQB_PACK_CASE(32, 4) VQB_PACK_CASE(32, 8)
+#undef VQB_PACK_CASE
+  }
   const int g = lanes_per_row(Dp);
   VQB_DISPATCH_G(g, launch_rows<G>(rows_pad, [&](int blocks) {
     if (src_dtype == VQB_F32)

@@ -127,12 +127,12 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
         }
       sxx = s2;
     }
-    float dx = 1.f, dw = 1.f;
+    float rdx = 1.f, rdw = 1.f;  // reciprocal norms for the norm=True MSE term (1 ulp vs a true division)
     if (want_norm) {
       sxx = group_sum<G>(sxx);
       sww = group_sum<G>(sww);
-      dx = fmaxf(sqrtf(sxx), kNormEps);
-      dw = fmaxf(sqrtf(sww), kNormEps);
+      rdx = 1.f / fmaxf(sqrtf(sxx), kNormEps);
+      rdw = 1.f / fmaxf(sqrtf(sww), kNormEps);
     }
 #pragma unroll
     for (int it = 0; it < NV; ++it) {
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
         zr[i] = __fadd_rn(xr[it][i], diff);  // ste value: x + (z - x)
         if (valid) sse = fmaf(diff, diff, sse);
         if (want_norm) {
-          const float dn = __fdiv_rn(wr[it][i], dw) - __fdiv_rn(xr[it][i], dx);
+          const float dn = wr[it][i] * rdw - xr[it][i] * rdx;
           if (valid) sse_n = fmaf(dn, dn, sse_n);
         }
       }
@@ -232,12 +232,13 @@ __global__ void __launch_bounds__(256) quantize_backward_kernel(
       const float nrm = sqrtf(sxx);
       clamp_in = nrm < kNormEps;
       den_in = fmaxf(nrm, kNormEps);
+      const float rin = 1.f / den_in;
       float s2 = 0.f;
 #pragma unroll
       for (int it = 0; it < NV; ++it)
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          yr[it][i] = __fdiv_rn(yr[it][i], den_in);
+          yr[it][i] *= rin;
           s2 = fmaf(yr[it][i], yr[it][i], s2);
         }
       sxx = s2;
@@ -256,11 +257,11 @@ __global__ void __launch_bounds__(256) quantize_backward_kernel(
       const float ny = sqrtf(sxx), nw = sqrtf(sww);
       cy = ny < kNormEps;
       cw = nw < kNormEps;
-      dy = fmaxf(ny, kNormEps);
-      dw = fmaxf(nw, kNormEps);
-      uu = sxx / (dy * dy);
-      vv = sww / (dw * dw);
-      uv = syw / (dy * dw);
+      dy = 1.f / fmaxf(ny, kNormEps);   // from here on dy, dw hold the RECIPROCAL norms
+      dw = 1.f / fmaxf(nw, kNormEps);
+      uu = sxx * dy * dy;
+      vv = sww * dw * dw;
+      uv = syw * dy * dw;
     }
     // g_y (overwrites gr) and the codebook-row gradient
     float gy_dot_y = 0.f;
@@ -273,11 +274,11 @@ __global__ void __launch_bounds__(256) quantize_backward_kernel(
         float g_y = gr[it][i] + c_cm * (yv - wv);
         float g_w = c_cb * (wv - yv);
         if (want_norm) {
-          const float u = yv / dy, v = wv / dw;
+          const float u = yv * dy, v = wv * dw;
           const float gu = c_cmn * (u - v), gu_dot_u = c_cmn * (uu - uv);
-          g_y += (gu - (cy ? 0.f : gu_dot_u * u)) / dy;
+          g_y += (gu - (cy ? 0.f : gu_dot_u * u)) * dy;
           const float gv = c_cbn * (v - u), gv_dot_v = c_cbn * (vv - uv);
-          g_w += (gv - (cw ? 0.f : gv_dot_v * v)) / dw;
+          g_w += (gv - (cw ? 0.f : gv_dot_v * v)) * dw;
         }
         gr[it][i] = g_y;
         gy_dot_y = fmaf(g_y, yv, gy_dot_y);
