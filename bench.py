@@ -264,6 +264,8 @@ def main():
     cfg = dict(wl['config'], embedding=emb(K, D))
     q = vqb.build_quantizer(cfg, training=wl['training']).to(dev)
     q._forward_pre_hooks.clear()  # steady-state step (the one-off k-means init is not part of the metric)
+    if args.workload in ('cfg2', 'cfg3'):
+        q.requires_grad_(False)   # VQ-KD freezes the quantizer parameters (reference configs/vqkd/model.py:76-82)
     x0, E, gz0 = synth(N, K, D, SEED + rank)
     with torch.no_grad():
         q.embedding.weight.copy_(synth(N, K, D, SEED)[1])  # identical codebook on every rank

@@ -124,11 +124,13 @@ int vqb_embedding_gather(const float* W, int64_t K, int D, const int64_t* quant,
 /* Backward of the above (closed form):
  *   gx = g_zste + g4[1]*2(x-z)/(ND) + J_n(x)^T [ g4[3]*2(n(x)-n(z))/(ND) ]
  *   gW[q] += g4[0]*2(z-x)/(ND) + J_n(z)^T [ g4[2]*2(n(z)-n(x))/(ND) ]     (fp32 atomics; gW pre-zeroed or NULL)
- * g4 is a DEVICE pointer to the 4 upstream loss gradients.  With normalize_x the chain through
+ * g4[i] are the four DEVICE scalars g_codebook, g_commitment, g_codebook_norm, g_commitment_norm (NULL = 0).  With normalize_x the chain through
  * F.normalize is applied as well: gx = J_n(x)^T g_x' (the backward of NormalizeCallback.before_encode). */
 int vqb_quantize_backward(const float* g_zste, const void* x, int x_dtype, int normalize_x,
                           const float* W, int64_t K, const int64_t* quant, int64_t N, int D,
-                          const float* g4, int want_norm_mse,
+                          const float* g_codebook, const float* g_commitment,           /* DEVICE scalars, NULL = 0 */
+                          const float* g_codebook_norm, const float* g_commitment_norm,
+                          int want_norm_mse,
                           void* gx_out /* x dtype */, float* gW_accum, void* stream);
 
 /* ---- row l2-normalisation (NormalizeCallback.before_encode on x) ------------------------ *

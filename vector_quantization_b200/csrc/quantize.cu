@@ -164,15 +164,15 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x < 32) {
+  if (is_last) {  // whole block, fixed assignment and tree order -> run-to-run deterministic
     __threadfence();
     float a = 0.f, b = 0.f;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) {  // fixed order -> run-to-run deterministic
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
       a += __ldcg(partials + i);
       b += __ldcg(partials + kMaxPartials + i);
     }
-    a = warp_sum(a);
-    b = warp_sum(b);
+    __syncthreads();  // sh is reused
+    block_sum2(a, b, sh);
     if (threadIdx.x == 0) {
       const float inv = 1.f / ((float)N * (float)D);
       mse4[0] = a * inv;
@@ -192,13 +192,14 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
 template <typename TX, int G, int V, int NV>
 __global__ void __launch_bounds__(256) quantize_backward_kernel(
     const float* __restrict__ gz, const TX* __restrict__ x, int normalize_x, const float* __restrict__ W, int64_t K,
-    const int64_t* __restrict__ quant, int64_t N, int D, const float* __restrict__ g4, int want_norm,
+    const int64_t* __restrict__ quant, int64_t N, int D, const float* __restrict__ g_cb,
+    const float* __restrict__ g_cm, const float* __restrict__ g_cbn, const float* __restrict__ g_cmn, int want_norm,
     TX* __restrict__ gx, float* __restrict__ gW) {
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
   const float scale = 2.f / ((float)N * (float)D);
-  const float c_cb = g4[0] * scale, c_cm = g4[1] * scale;
-  const float c_cbn = want_norm ? g4[2] * scale : 0.f, c_cmn = want_norm ? g4[3] * scale : 0.f;
+  const float c_cb = g_cb ? *g_cb * scale : 0.f, c_cm = g_cm ? *g_cm * scale : 0.f;
+  const float c_cbn = (want_norm && g_cbn) ? *g_cbn * scale : 0.f, c_cmn = (want_norm && g_cmn) ? *g_cmn * scale : 0.f;
   for (int64_t base = blockIdx.x * rows_per_block; base < N; base += (int64_t)gridDim.x * rows_per_block) {
     const int64_t n_raw = base + threadIdx.x / G;
     const bool valid = n_raw < N;
@@ -403,9 +404,9 @@ int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D, int normal
 }
 
 int vqb_quantize_backward(const float* gz, const void* x, int x_dtype, int normalize_x, const float* W, int64_t K,
-                          const int64_t* quant, int64_t N, int D, const float* g4, int want_norm, void* gx,
-                          float* gW, void* stream) {
-  VQB_REQUIRE(gz && x && W && quant && g4 && gx, "vqb_quantize_backward: null pointer");
+                          const int64_t* quant, int64_t N, int D, const float* g_cb, const float* g_cm,
+                          const float* g_cbn, const float* g_cmn, int want_norm, void* gx, float* gW, void* stream) {
+  VQB_REQUIRE(gz && x && W && quant && gx, "vqb_quantize_backward: null pointer");
   VQB_REQUIRE(N >= 1 && D >= 1 && K >= 1, "vqb_quantize_backward: bad shape");
   RowGeom geom;
   VQB_REQUIRE(row_geom(D, &geom), "vqb_quantize_backward: D=%d unsupported", D);
@@ -414,10 +415,11 @@ int vqb_quantize_backward(const float* gz, const void* x, int x_dtype, int norma
   bool launched = false;
   if (x_dtype == VQB_F32) {
     VQB_DISPATCH_GEOM((quantize_backward_kernel<float, G, V, NV><<<blocks, 256, 0, st>>>(
-        gz, (const float*)x, normalize_x, W, K, quant, N, D, g4, want_norm, (float*)gx, gW)))
+        gz, (const float*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm, (float*)gx, gW)))
   } else if (x_dtype == VQB_BF16) {
     VQB_DISPATCH_GEOM((quantize_backward_kernel<__nv_bfloat16, G, V, NV><<<blocks, 256, 0, st>>>(
-        gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g4, want_norm, (__nv_bfloat16*)gx, gW)))
+        gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm,
+        (__nv_bfloat16*)gx, gW)))
   }
   VQB_REQUIRE(launched, "vqb_quantize_backward: unsupported dtype/geometry");
   VQB_LAUNCH_OK();

@@ -90,6 +90,8 @@ def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, preci
 
 
 class _QuantizeSTELoss(torch.autograd.Function):
+    """Outputs the four MSE terms as SEPARATE 0-dim tensors so that autograd hands their upstream gradients
+    back as four device scalars (no select_backward / stack kernels between the loss and our backward)."""
 
     @staticmethod
     def forward(ctx, x, W, index, index_is_keys, key_offset, normalize_x, want_norm):
@@ -104,19 +106,18 @@ class _QuantizeSTELoss(torch.autograd.Function):
         if xn is None:
             xn = x.detach()
         ctx.mark_non_differentiable(quant, xn)
-        return z, mse4, quant, xn
+        m0, m1, m2, m3 = mse4.unbind(0)
+        return z, m0, m1, m2, m3, quant, xn
 
     @staticmethod
-    def backward(ctx, gz, g4, _gq, _gxn):
+    def backward(ctx, gz, g0, g1, g2, g3, _gq, _gxn):
         x, W, quant = ctx.saved_tensors
         normalize_x, want_norm = ctx.cfg
         if gz is None:
             gz = torch.zeros(x.shape, dtype=torch.float32, device=x.device)
-        if g4 is None:
-            g4 = torch.zeros(4, dtype=torch.float32, device=x.device)
-        gx, gW = ops.quantize_backward(gz.contiguous().float(), x, W, quant, g4.contiguous().float(),
-                                       normalize_x=normalize_x, want_norm=want_norm,
-                                       need_gW=ctx.needs_input_grad[1])
+        g4 = [None if g is None else g.contiguous().float() for g in (g0, g1, g2, g3)]
+        gx, gW = ops.quantize_backward(gz.contiguous().float(), x, W, quant, g4, normalize_x=normalize_x,
+                                       want_norm=want_norm, need_gW=ctx.needs_input_grad[1])
         return (gx if ctx.needs_input_grad[0] else None), gW, None, None, None, None, None
 
 
@@ -124,10 +125,11 @@ def quantize_ste_loss(x: torch.Tensor, W: torch.Tensor, index: torch.Tensor, wan
                       index_is_keys: bool = False, key_offset: int = 0, normalize_x: bool = False):
     """One kernel: [x' = F.normalize(x)] -> gather W[q] -> straight-through -> MSE terms.
     -> (z_ste [N,D] fp32: value x' + (W[q] - x'), gradient to x only;
-        mse4 [4] = {codebook, commitment, codebook(norm), commitment(norm)};
+        mse4 = (codebook, commitment, codebook(norm), commitment(norm)) as four 0-dim tensors;
         quant int64 [N] (unpacked from the keys when index_is_keys);  x' (detached; x itself if not normalised))"""
-    return _QuantizeSTELoss.apply(x.contiguous(), W, index, bool(index_is_keys), int(key_offset),
-                                  bool(normalize_x), bool(want_norm))
+    z, m0, m1, m2, m3, quant, xn = _QuantizeSTELoss.apply(x.contiguous(), W, index, bool(index_is_keys),
+                                                          int(key_offset), bool(normalize_x), bool(want_norm))
+    return z, (m0, m1, m2, m3), quant, xn
 
 
 class _FSQ(torch.autograd.Function):

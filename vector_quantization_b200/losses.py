@@ -65,7 +65,7 @@ class BaseLoss(nn.Module):
     def needs_norm(self) -> bool:
         return any(i >= CODEBOOK_NORM for i in self.terms())
 
-    def from_mse4(self, mse4: torch.Tensor) -> torch.Tensor:
+    def from_mse4(self, mse4) -> torch.Tensor:
         out = None
         for i, c in self.terms().items():
             t = mse4[i] if c == 1.0 else mse4[i] * c

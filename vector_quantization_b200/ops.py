@@ -182,16 +182,21 @@ def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, *, quant: torch.Tensor | N
     return z, mse4, qo, xn
 
 
-def quantize_backward(g_z: torch.Tensor, x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor,
-                      g4: torch.Tensor, *, normalize_x: bool = False, want_norm: bool, need_gW: bool):
+def quantize_backward(g_z: torch.Tensor, x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor, g4, *,
+                      normalize_x: bool = False, want_norm: bool, need_gW: bool):
+    """g4: a float32 [4] tensor or a sequence of four 0-dim device tensors / None
+    (codebook, commitment, codebook-norm, commitment-norm upstream gradients)."""
     lib = _lib.load()
-    _cuda(g_z, x, W, quant, g4)
-    assert g_z.dtype == torch.float32 and g4.dtype == torch.float32
+    if isinstance(g4, torch.Tensor):
+        g4 = [g4[i] for i in range(4)]
+    _cuda(g_z, x, W, quant, *g4)
+    assert g_z.dtype == torch.float32 and all(g is None or g.dtype == torch.float32 for g in g4)
     N, D = x.shape
     gx = torch.empty_like(x)
     gW = torch.zeros_like(W) if need_gW else None
     _call('vqb_quantize_backward', lib.vqb_quantize_backward, _p(g_z), _p(x), _dt(x), int(normalize_x), _p(W),
-          W.shape[0], _p(quant), N, D, _p(g4), int(want_norm), _p(gx), _p(gW), _stream())
+          W.shape[0], _p(quant), N, D, _p(g4[0]), _p(g4[1]), _p(g4[2]), _p(g4[3]), int(want_norm), _p(gx), _p(gW),
+          _stream())
     return gx, gW
 
 

@@ -225,7 +225,7 @@ class VectorQuantizer(BaseQuantizer):
             loss_memo[name] = value
             loss = value if loss is None else loss + value
         if loss is None:
-            loss = mse4.new_zeros([])
+            loss = mse4[0].new_zeros([])
         return z, loss, memo
 
 
