@@ -369,11 +369,27 @@ def main():
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)  # kernel timed inside a long step -> sustained figure
     flops = 2.0 * N * K * D                              # algorithmic: contraction only, un-padded, one plane
     achieved = flops / (assign_avg * 1e-3) / 1e12
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/, per launch)
+    traffic, ncu_note = None, None
+    try:
+        ncu = json.load(open(ROOT / 'profiles' / 'r1_assign_ncu_summary.json'))
+        if args.workload == 'cfg2':
+            to_b = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            traffic = sum(float(ncu[k]['value']) * to_b[ncu[k]['unit']]
+                          for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+            ncu_note = dict(tensor_pipe_active_pct=float(
+                ncu['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']['value']),
+                source='profiles/r1_assign_ncu_summary.json')
+    except Exception:  # noqa: BLE001
+        pass
     roofline = dict(bound='tensor', kernel='assign_tc_kernel (tcgen05 distance GEMM + fused arg-min)',
                     achieved=achieved, peak=peak_tf, unit='TFLOP/s', frac=achieved / peak_tf,
                     peak_source='MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (B200_PROFILING.md)',
                     kernel_ms=assign_avg, kernel_share_of_step=assign_avg / ms,
-                    epilogue_gelem_per_s=N * K / (assign_avg * 1e-3) / 1e9, traffic=None)
+                    epilogue_gelem_per_s=N * K / (assign_avg * 1e-3) / 1e9, traffic=traffic,
+                    algorithmic_bytes=N * D * 2 + K * D * 2 * 3 + N * 8, ncu=ncu_note,
+                    note='algorithmic flops 2*N*K*D (one plane); the exact mode issues 3 plane MMAs per tile, '
+                         'so the tensor pipe itself is ~3x busier than `frac` (see ncu.tensor_pipe_active_pct)')
 
     # ---- end-to-end: pinned host inputs -> device -> step -> results back to pinned host ----
     xh = x0.pin_memory()

@@ -1,0 +1,124 @@
+"""Parity at BASELINE.json's FULL sizes.
+
+cfg 1 (VQGAN VectorQuantizer forward, 8192 x 256 fp32 codebook, 64 x 16 x 16 latents) is small enough for the
+CPU oracle, so it is compared directly.  For the larger configurations the checks are size-independent
+properties of the quantizer: identity on the codebook itself, idempotence, permutation equivariance,
+agreement of the tensor-core kernel with the CUDA-core cross-check kernel, and shard-combine associativity.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import vector_quantization_b200 as vqb
+from oracle import oracle as O
+from vector_quantization_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def emb(K, D):
+    return dict(type='torch_nn_modules_sparse_Embedding', num_embeddings=K, embedding_dim=D)
+
+
+def test_cfg1_vqgan_full_size_vs_oracle(dev):
+    """BASELINE.json configs[0]: codebook 8192 x 256 fp32, batch 64 x 16 x 16 latents, forward."""
+    N, K, D = 64 * 16 * 16, 8192, 256
+    x, E = O.synthetic_latents(N, K, D, seed=3407)
+    spec = O.QuantizerSpec(distance='L2', losses={'vqgan_loss': dict(type='VQGANLoss')})
+    out = O.quantizer_forward(spec, [x], E)
+    q = vqb.build_quantizer(dict(type='VQGANQuantizer', embedding=emb(K, D), distance=dict(type='L2Distance'),
+                                 losses=dict(vqgan_loss=dict(type='VQGANLoss')), init_weights=dict(type='vqgan'))).to(dev)
+    with torch.no_grad():
+        q.embedding.weight.copy_(E)
+    z, loss, memo = q(x.to(dev), dict())
+    quant = memo['quant'].cpu()
+    rows, gap = O.index_mismatch_report(out['distance'][0], out['quant'][0], quant)
+    assert (gap <= 1e-5 * out['distance'][0][rows, out['quant'][0][rows]].clamp_min(1)).all()
+    assert rows.numel() <= N // 1000
+    same = quant == out['quant'][0]
+    assert torch.equal(z.detach().cpu()[same], out['z_ste'][0].detach()[same])       # bit-exact x + (W[q] - x)
+    torch.testing.assert_close(loss.detach().cpu(), out['loss'][0].detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_cfg1_degenerate_vqgan_init_near_tie_policy(dev):
+    """The reference's real init U(-1/K, 1/K) makes every distance agree to ~1e-4 relative:
+    two fp32 formulations already disagree on ~5 % of the indices.  Every disagreement must be a near-tie."""
+    N, K, D = 4096, 8192, 256
+    g = torch.Generator().manual_seed(1)
+    E = (torch.rand(K, D, generator=g) * 2 - 1) / K
+    x = torch.randn(N, D, generator=g)
+    q_ref, d = O.encode('L2', x, E)
+    a = ops.pack_rows(x.to(dev))
+    b = ops.pack_rows(E.to(dev), want_half_sqnorm=True)
+    keys = ops.new_keys(N, dev)
+    ops.assign(a, b, keys, l2=True)
+    quant = ops.unpack_keys(keys).cpu()
+    rows, gap = O.index_mismatch_report(d, q_ref, quant)
+    assert (gap <= 1e-5 * d[rows, q_ref[rows]].clamp_min(1)).all(), float(gap.max())
+
+
+@pytest.mark.parametrize('K,D,metric', [(8192, 32, 'Cosine'), (16384, 8, 'L2'), (8192, 256, 'Cosine')])
+def test_identity_and_idempotence_at_full_codebook_size(dev, K, D, metric):
+    """Quantizing the codebook rows themselves returns arange(K) and zero loss; quantizing the output again
+    returns the same indices (cfg 2 / 3 / 4 codebook sizes)."""
+    g = torch.Generator().manual_seed(K + D)
+    E = torch.randn(K, D, generator=g)
+    if metric == 'Cosine':
+        E = F.normalize(E)
+    q = vqb.build_quantizer(dict(type='VQGANQuantizer', embedding=emb(K, D), distance=dict(type=f'{metric}Distance'),
+                                 losses=dict(l=dict(type='CommitmentLoss')), init_weights=dict(type='vqgan'))).to(dev)
+    q.eval()
+    with torch.no_grad():
+        q.embedding.weight.copy_(E)
+    z, loss, memo = q(E.to(dev), dict())
+    assert torch.equal(memo['quant'].cpu(), torch.arange(K))
+    assert float(loss.detach()) == 0.0 and torch.equal(z.detach().cpu(), E)
+    z2, loss2, memo2 = q(z.detach(), dict())
+    assert torch.equal(memo2['quant'], memo['quant']) and float(loss2.detach()) == 0.0
+
+
+def test_cfg2_full_size_backends_agree_and_permutation_equivariance(dev):
+    """cfg 2 at full size (65 536 x 8192 x 32, bf16 tokens, fp32 unit-norm codebook): the tcgen05 kernel and the
+    CUDA-core cross-check kernel pick the same codes (scores equal to fp32 rounding), and permuting the tokens
+    permutes the result."""
+    N, K, D = 65536, 8192, 32
+    g = torch.Generator().manual_seed(2)
+    E = F.normalize(torch.randn(K, D, generator=g))
+    x = (E[torch.randint(0, K, (N,), generator=g)] + 0.09 * torch.randn(N, D, generator=g)).to(torch.bfloat16).to(dev)
+    book = ops.pack_rows(E.to(dev), normalize=True)
+    tok = ops.as_operand(x)
+    res = {}
+    for name, backend in (('tc', ops.BACKEND_TCGEN05), ('simt', ops.BACKEND_SIMT)):
+        keys = ops.new_keys(N, dev)
+        ops.assign(tok, book, keys, l2=False, backend=backend)
+        res[name] = ops.unpack_keys(keys, want_score=True)
+    diff = res['tc'][0] != res['simt'][0]
+    assert diff.float().mean() < 1e-3
+    torch.testing.assert_close(res['tc'][1], res['simt'][1], rtol=1e-5, atol=2e-6)
+    # both candidates of a disagreeing row have the same score to fp32 rounding
+    assert (res['tc'][1][diff] - res['simt'][1][diff]).abs().max().item() < 2e-6 if diff.any() else True
+    perm = torch.randperm(N, generator=g).to(dev)
+    keys = ops.new_keys(N, dev)
+    ops.assign(ops.as_operand(x[perm].contiguous()), book, keys, l2=False)
+    assert torch.equal(ops.unpack_keys(keys), res['tc'][0][perm])
+
+
+def test_cfg5_shape_shard_combine_is_associative(dev):
+    """cfg 5 shape (768-d CLIP-sized features): arg-min over 4 codebook shards combined through the packed
+    min-loc keys equals the arg-min over the whole codebook (what the 8-GPU min-loc all-reduce computes)."""
+    N, K, D = 4096, 16384, 768
+    g = torch.Generator().manual_seed(4)
+    E = torch.randn(K, D, generator=g).to(dev)
+    x = torch.randn(N, D, generator=g).to(torch.bfloat16).to(dev)
+    tok = ops.as_operand(x)
+    whole = ops.new_keys(N, dev)
+    ops.assign(tok, ops.pack_rows(E, normalize=True, planes=1), whole, l2=False)
+    sharded = ops.new_keys(N, dev)
+    for r in range(4):
+        lo, hi = r * K // 4, (r + 1) * K // 4
+        ops.assign(tok, ops.pack_rows(E[lo:hi].contiguous(), normalize=True, planes=1), sharded, l2=False, index_offset=lo)
+    assert torch.equal(whole, sharded)
+    # and it is the true nearest code under the same bf16-plane arithmetic (fp32 check on a sample)
+    idx = ops.unpack_keys(whole)[:256].cpu()
+    ref = (F.normalize(x[:256].float()) @ F.normalize(E).to(torch.bfloat16).float().t()).argmax(1).cpu()
+    assert (idx == ref).float().mean() > 0.98
