@@ -365,17 +365,23 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  int64_t b_index_offset, unsigned long long* __restrict__ keys) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
-  const uint32_t stage_bytes = WHOLE ? (uint32_t)pa * kABytes + (uint32_t)pb * kBBytes : kABytes + kBBytes;
-  // carve: [stages] | stash[NEW warps][4 KB] | side[2][256] | barriers | tmem ptr   (base re-aligned to 1024 B)
+  // WHOLE: a stage holds every B plane of one code tile; the row tile's A planes are RESIDENT in one of two
+  // slots (loaded once per row tile, not once per work item).  k-blocked: a stage is one [A slab | B slab] pair.
+  const uint32_t stage_bytes = WHOLE ? (uint32_t)pb * kBBytes : kABytes + kBBytes;
+  const uint32_t a_slot_bytes = WHOLE ? (uint32_t)pa * kABytes : 0u;
+  // carve: [A slots] | [stages] | stash[NEW warps][4 KB] | side[2][256] | barriers | tmem ptr   (1024 B aligned)
   constexpr uint32_t kStashBytes = NEW * 4096;  // winning-chunk stash: [warp][8 float4][32 lanes]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_a + 2 * (size_t)a_slot_bytes;
   uint8_t* stash_smem = smem + (size_t)nstages * stage_bytes;
   float* side_smem = reinterpret_cast<float*>(stash_smem + kStashBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(side_smem + 2 * BN);
   uint64_t* empty_bar = full_bar + nstages;
   uint64_t* tmem_full = empty_bar + nstages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* a_full = tmem_empty + 2;
+  uint64_t* a_empty = a_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t a_tiles = (a_rows + BM - 1) / BM, b_tiles = (b_rows + BN - 1) / BN;
@@ -392,6 +398,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
       mbar_init(tmem_empty + i, 8);  // the 8 warps of the group that drains this accumulator
+      mbar_init(a_full + i, 1);
+      mbar_init(a_empty + i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -407,18 +415,29 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int64_t at = t0 / b_tiles, bt = t0 - at * b_tiles;
+      int64_t cur_at = -1, a_count = 0;
       for (int64_t t = t0; t < t1; ++t) {
         const int a_row = (int)(at * BM), b_row = (int)(bt * BN);
         if constexpr (WHOLE) {
+          if (at != cur_at) {  // new row tile: load its A planes into the next resident slot
+            const int slot = (int)(a_count & 1);
+            mbar_wait(a_empty + slot, (uint32_t)((a_count >> 1) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(a_full + slot, a_slot_bytes);
+              for (int p = 0; p < pa; ++p)
+                tma_load_2d(smem_a + slot * a_slot_bytes + p * kABytes, &tmap_a, a_full + slot, 0,
+                            (int)(p * a_rows_pad) + a_row);
+            }
+            __syncwarp();
+            ++a_count;
+            cur_at = at;
+          }
           TS(0, t - t0, 0);
           mbar_wait(empty_bar + stage, phase ^ 1);
           TS(0, t - t0, 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            for (int p = 0; p < pa; ++p)
-              tma_load_2d(sa + p * kABytes, &tmap_a, full_bar + stage, 0, (int)(p * a_rows_pad) + a_row);
-            uint8_t* sb = sa + pa * kABytes;
+            uint8_t* sb = smem + (size_t)stage * stage_bytes;
             for (int p = 0; p < pb; ++p)
               tma_load_2d(sb + p * kBBytes, &tmap_b, full_bar + stage, 0, (int)(p * b_rows_pad) + b_row);
           }
@@ -455,6 +474,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int64_t local = 0;
+      int64_t a_count_m = 0;
+      const int b_tiles_i = (int)b_tiles;
+      int bt_m = (int)(t0 % b_tiles);
       for (int64_t t = t0; t < t1; ++t, ++local) {
         const int buf = (int)(local & 1);
         const uint32_t use = (uint32_t)(local >> 1);
@@ -463,12 +485,18 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
         if constexpr (WHOLE) {
+          if (bt_m == 0 || t == t0) {  // first tile of a row tile in this CTA's range: its A planes must have landed
+            mbar_wait(a_full + (a_count_m & 1), (uint32_t)((a_count_m >> 1) & 1));
+            ++a_count_m;
+          }
+          const int slot = (int)((a_count_m - 1) & 1);
+          const bool last_of_row_tile = (bt_m == b_tiles_i - 1) || (t + 1 == t1);
           TS(1, local, 1);
           mbar_wait(full_bar + stage, phase);
           TS(1, local, 2);
           tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-          const uint32_t sb = sa + (uint32_t)pa * kABytes;
+          const uint32_t sa = smem_u32(smem_a) + (uint32_t)slot * a_slot_bytes;
+          const uint32_t sb = smem_base + (uint32_t)stage * stage_bytes;
           if (elect_one()) {
 #pragma unroll
             for (int term = 0; term < kMaxTerms; ++term) {
@@ -482,8 +510,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
             umma_commit(tmem_full + buf);    // accumulator complete -> epilogue
+            if (last_of_row_tile) umma_commit(a_empty + slot);  // resident A planes no longer needed
           }
           __syncwarp();
+          if (++bt_m == b_tiles_i) bt_m = 0;
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         } else {
           const int nv = terms.n * kblocks;
@@ -593,10 +623,12 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
   if (int e = make_operand_map(&ma, a_planes, pa * a_pad, Dp, BK, BM)) return e;
   if (int e = make_operand_map(&mb, b_planes, pb * b_pad, Dp, BK, BN)) return e;
   constexpr uint32_t kStashBytes = NEW * 4096;
-  const uint32_t stage_bytes = WHOLE ? (uint32_t)(pa * BM + pb * BN) * BK * 2 : (uint32_t)(BM + BN) * BK * 2;
-  int nstages = (int)((196608 - kStashBytes) / stage_bytes);
+  const uint32_t stage_bytes = WHOLE ? (uint32_t)(pb * BN) * BK * 2 : (uint32_t)(BM + BN) * BK * 2;
+  const uint32_t a_resident = WHOLE ? 2u * (uint32_t)pa * BM * BK * 2 : 0u;
+  int nstages = (int)((196608 - kStashBytes - a_resident) / stage_bytes);
   if (nstages > 8) nstages = 8;
-  const size_t smem_bytes = 1024 + (size_t)nstages * stage_bytes + kStashBytes + 2 * BN * sizeof(float) + (2 * nstages + 4) * 8 + 16;
+  const size_t smem_bytes = 1024 + a_resident + (size_t)nstages * stage_bytes + kStashBytes + 2 * BN * sizeof(float) +
+                            (2 * nstages + 8) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     VQB_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<BK, WHOLE, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -628,7 +660,8 @@ int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad
   const int nwarps = new_override == 16 ? 16 : 8;
   const size_t stash = (size_t)nwarps * 4096;
   // whole-tile stages need at least a double buffer of all planes of one work item in shared memory
-  const bool whole = Dp <= 64 && (size_t)(pa * BM + pb * BN) * Dp * 2 * 2 <= 196608 - stash;
+  // resident-A mode: two A slots plus at least two whole-B-tile stages must fit in shared memory
+  const bool whole = Dp <= 64 && (size_t)(2 * pa * BM + 2 * pb * BN) * Dp * 2 <= 196608 - stash;
 #define VQB_LAUNCH(BK_, W_)                                                                                         \
   do {                                                                                                              \
     if (nwarps == 16) return launch<BK_, W_, 16>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, off, keys, st); \
