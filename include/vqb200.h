@@ -70,7 +70,7 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D,
  * and, with the operands swapped, NearestAnchor's column argmin `d.argmin(0)`
  *                                                           vq/algorithms/cvqvae/anchors.py:83
  * WITHOUT materialising the [a_rows x b_rows] matrix.  For every row i of A it finds
- *      argmax_j  score(i,j) = <A_i, B_j> - half_sqnorm_b[j]        (half_sqnorm_b == NULL -> 0)
+ *      argmax_j  score(i,j) = <A_i, B_j> - b_side[j]   (side_mode 1)   or   <A_i, B_j> * b_side[j]   (side_mode 2)
  * which is argmin_j ||A_i - B_j|| (L2) or argmin_j (1 - cos) when B rows are normalised.
  * Ties resolve to the lowest j (torch.argmin semantics).  The result is min-combined into
  *      keys[i] = (~orderable(score) << 32) | (uint32)(j + b_index_offset)
@@ -84,8 +84,14 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D,
  */
 int vqb_assign(const void* a_planes, int a_nplanes, int64_t a_rows, int64_t a_plane_rows,
                const void* b_planes, int b_nplanes, int64_t b_rows, int64_t b_plane_rows,
-               int D, const float* b_half_sqnorm, int64_t b_index_offset,
+               int D, const float* b_side /* fp32 [vqb_operand_rows_pad(b_rows)] or NULL */,
+               int side_mode /* 0 none, 1: score -= b_side[j] (L2, 0.5|b_j|^2), 2: score *= b_side[j] (1/|b_j|) */,
+               int64_t b_index_offset,
                unsigned long long* keys, int backend, void* stream);
+
+/* out[r] = 1 / max(||x_r||, 1e-12), zero in the padding up to vqb_operand_rows_pad(rows): the side_mode-2 column
+ * scale that lets the column arg-min of NearestAnchor use RAW (un-normalised, one exact bf16 plane) tokens. */
+int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, float* out, void* stream);
 
 /* keys -> int64 indices (and optional fp32 scores); `index_offset` is subtracted. */
 int vqb_unpack_keys(const unsigned long long* keys, int64_t n, int64_t index_offset,

@@ -120,6 +120,29 @@ def test_assign_column_argmin_swapped_operands(dev):
         _check_indices(d.t().contiguous(), idx_ref, idx, what=f'column argmin {metric}')
 
 
+def test_assign_column_argmin_raw_tokens_with_column_scale(dev):
+    """Cosine column arg-min with RAW bf16 tokens (one exact plane, zero-copy) and the 1/|x_n| column scale applied
+    in the epilogue == arg-min over the normalised tokens (what NearestAnchor needs)."""
+    from vector_quantization_b200 import functional as Fq
+    N, K, D = 5000, 700, 32
+    x, E = O.synthetic_latents(N, K, D, seed=13)
+    x = (x * (0.5 + torch.rand(N, 1, generator=torch.Generator().manual_seed(1)) * 4)).to(torch.bfloat16)  # varied norms
+    _, d = O.encode('Cosine', x.float(), E)
+    idx_ref = d.argmin(0)
+    book = ops.pack_rows(E.to(dev), normalize=True)
+    for backend in (ops.BACKEND_TCGEN05, ops.BACKEND_SIMT):
+        raw = ops.as_operand(x.to(dev))
+        raw.inv_norm = ops.row_inv_norm(x.to(dev))
+        keys = ops.new_keys(K, dev)
+        ops.assign(book, raw, keys, l2=False, scale_columns=True, backend=backend)
+        _check_indices(d.t().contiguous(), idx_ref, ops.unpack_keys(keys).cpu(), what='raw-token column argmin')
+    keys = Fq.column_nearest(x.to(dev), book, 'Cosine')
+    _check_indices(d.t().contiguous(), idx_ref, ops.unpack_keys(keys).cpu(), what='column_nearest')
+    inv = ops.row_inv_norm(x.to(dev)).cpu()
+    torch.testing.assert_close(inv[:N], 1 / x.float().norm(dim=1), rtol=2e-6, atol=0)
+    assert (inv[N:] == 0).all()
+
+
 def test_assign_sharded_codebook_min_combine(dev):
     """Two launches over two codebook shards min-combine into the same keys as one launch."""
     N, K, D = 2000, 1024, 32

@@ -42,7 +42,8 @@ SIGNATURES = {
     'vqb_pack_rows': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int64, c_void_p]),
     'vqb_assign': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p,
-                           c_int64, c_void_p, c_int, c_void_p]),
+                           c_int, c_int64, c_void_p, c_int, c_void_p]),
+    'vqb_row_inv_norm': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
     'vqb_unpack_keys': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     'vqb_keys_flip_sign': (c_int, [c_void_p, c_int64, c_void_p]),
     'vqb_loss_partials_count': (c_int64, []),

@@ -8,8 +8,8 @@
 namespace vqb {
 
 int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_plane_rows, const void* b_planes, int pb,
-                     int64_t b_rows, int64_t b_plane_rows, int D, const float* b_half_sqnorm, int64_t b_index_offset,
-                     unsigned long long* keys, cudaStream_t st);
+                     int64_t b_rows, int64_t b_plane_rows, int D, const float* b_side, int side_mode,
+                     int64_t b_index_offset, unsigned long long* keys, cudaStream_t st);
 
 constexpr int SA = 128;  // A rows per block (one per thread)
 constexpr int SB = 32;   // B rows per inner tile
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(SA) assign_simt_kernel(const __nv_bfloat16* __
                                                          int64_t a_rows, int64_t a_rows_pad,
                                                          const __nv_bfloat16* __restrict__ B, int pb,
                                                          int64_t b_rows, int64_t b_rows_pad, int Dp,
-                                                         const float* __restrict__ h, int64_t b_off,
+                                                         const float* __restrict__ h, int side_mode, int64_t b_off,
                                                          unsigned long long* __restrict__ keys) {
   __shared__ float As[SA][SD + 1];
   __shared__ float Bs[SB][SD];
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(SA) assign_simt_kernel(const __nv_bfloat16* __
 #pragma unroll
     for (int j = 0; j < SB; ++j) {
       if (j0 + j < b_rows) {
-        const float s = h ? acc[j] - h[j0 + j] : acc[j];
+        const float s = (h == nullptr || side_mode == 0) ? acc[j] : (side_mode == 1 ? acc[j] - h[j0 + j] : acc[j] * h[j0 + j]);
         if (s > best) {
           best = s;
           best_j = (uint32_t)(j0 + j + b_off);
@@ -85,7 +85,8 @@ using namespace vqb;
 
 extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, int64_t a_plane_rows, const void* b_planes,
                           int pb, int64_t b_rows, int64_t b_plane_rows, int D, const float* b_half_sqnorm,
-                          int64_t b_index_offset, unsigned long long* keys, int backend, void* stream) {
+                          int side_mode, int64_t b_index_offset, unsigned long long* keys, int backend,
+                          void* stream) {
   VQB_REQUIRE(a_planes && b_planes && keys, "vqb_assign: null pointer");
   VQB_REQUIRE(a_rows >= 1 && b_rows >= 1 && D >= 1, "vqb_assign: bad shape a_rows=%lld b_rows=%lld D=%d",
               (long long)a_rows, (long long)b_rows, D);
@@ -96,11 +97,10 @@ extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, int64_t 
   if (a_plane_rows <= 0) a_plane_rows = vqb_operand_rows_pad(a_rows);
   if (b_plane_rows <= 0) b_plane_rows = vqb_operand_rows_pad(b_rows);
   VQB_REQUIRE(a_plane_rows >= a_rows && b_plane_rows >= b_rows, "vqb_assign: plane stride smaller than the row count");
-  VQB_REQUIRE(b_half_sqnorm == nullptr || b_plane_rows % 256 == 0,
-              "vqb_assign: the L2 side vector needs the padded operand layout of vqb_pack_rows");
+  VQB_REQUIRE(side_mode >= 0 && side_mode <= 2, "vqb_assign: side_mode must be 0 (none), 1 (subtract) or 2 (scale)");
   if (backend == VQB_BACKEND_TCGEN05)
     return assign_tc_launch(a_planes, pa, a_rows, a_plane_rows, b_planes, pb, b_rows, b_plane_rows, D, b_half_sqnorm,
-                            b_index_offset, keys, st);
+                            side_mode, b_index_offset, keys, st);
   VQB_REQUIRE(backend == VQB_BACKEND_SIMT, "vqb_assign: unknown backend %d", backend);
   const int Dp = (int)vqb_operand_dp(D);
   const int64_t a_tiles = (a_rows + SA - 1) / SA;
@@ -112,7 +112,7 @@ extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, int64_t 
   dim3 grid((unsigned)a_tiles, (unsigned)splits);
   assign_simt_kernel<<<grid, SA, 0, st>>>((const __nv_bfloat16*)a_planes, pa, a_rows, a_plane_rows,
                                           (const __nv_bfloat16*)b_planes, pb, b_rows, b_plane_rows, Dp, b_half_sqnorm,
-                                          b_index_offset, keys);
+                                          side_mode, b_index_offset, keys);
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

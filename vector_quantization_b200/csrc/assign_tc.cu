@@ -185,18 +185,24 @@ __device__ __forceinline__ void stash_chunk(uint32_t pred, uint32_t saddr, const
 // Branch-free running arg-max over a 32-column chunk held in registers: the thread keeps only
 // (best score, first column of the chunk that produced it) and stashes that chunk's 32 scores; the
 // position inside the chunk is resolved once per row tile at flush time (resolve_index).
-// USE_SIDE: score = acc - side[col] (L2);  MASK: columns >= n_valid (zero-padded rows of the last code
+// SIDE 1: score = acc - side[col] (L2), SIDE 2: score = acc * side[col];  MASK: columns >= n_valid (zero-padded rows of the last code
 // tile) are excluded.
-template <bool USE_SIDE, bool MASK>
+template <int SIDE, bool MASK>
 __device__ __forceinline__ void chunk_scores(const uint32_t (&r)[32], uint32_t side_saddr, int n_valid, float (&s)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    if constexpr (USE_SIDE) {
+    if constexpr (SIDE == 1) {        // L2: score = <a,b> - 0.5|b|^2
       const float4 h = lds128(side_saddr + j * 4);  // warp-wide broadcast
       s[j] = __uint_as_float(r[j]) - h.x;
       s[j + 1] = __uint_as_float(r[j + 1]) - h.y;
       s[j + 2] = __uint_as_float(r[j + 2]) - h.z;
       s[j + 3] = __uint_as_float(r[j + 3]) - h.w;
+    } else if constexpr (SIDE == 2) { // per-column scale: score = <a,b> * (1/|b|)  (un-normalised B rows)
+      const float4 h = lds128(side_saddr + j * 4);
+      s[j] = __uint_as_float(r[j]) * h.x;
+      s[j + 1] = __uint_as_float(r[j + 1]) * h.y;
+      s[j + 2] = __uint_as_float(r[j + 2]) * h.z;
+      s[j + 3] = __uint_as_float(r[j + 3]) * h.w;
     } else {
       s[j] = __uint_as_float(r[j]);
       s[j + 1] = __uint_as_float(r[j + 1]);
@@ -226,21 +232,21 @@ __device__ __forceinline__ void chunk_commit(float mx, const float (&s)[32], uin
   // warp-uniform skip: after the first few code tiles most chunks improve no row of the warp
   if (__any_sync(0xffffffffu, better)) stash_chunk((uint32_t)better, stash_saddr, s);
 }
-template <bool USE_SIDE, bool MASK>
+template <int SIDE, bool MASK>
 __device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t side_saddr, uint32_t col_base,
                                              int n_valid, uint32_t stash_saddr, float& best, uint32_t& best_col) {
   float s[32];
-  chunk_scores<USE_SIDE, MASK>(r, side_saddr, n_valid, s);
+  chunk_scores<SIDE, MASK>(r, side_saddr, n_valid, s);
   chunk_commit(chunk_max(s), s, col_base, stash_saddr, best, best_col);
 }
 // two adjacent chunks at once: the two max trees are independent, which doubles the ILP of the reduction
-template <bool USE_SIDE, bool MASK>
+template <int SIDE, bool MASK>
 __device__ __forceinline__ void pair_argmax(const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t side_saddr,
                                             uint32_t col_base, int nv0, int nv1, uint32_t stash_saddr, float& best,
                                             uint32_t& best_col) {
   float s0[32], s1[32];
-  chunk_scores<USE_SIDE, MASK>(r0, side_saddr, nv0, s0);
-  chunk_scores<USE_SIDE, MASK>(r1, side_saddr + 128, nv1, s1);
+  chunk_scores<SIDE, MASK>(r0, side_saddr, nv0, s0);
+  chunk_scores<SIDE, MASK>(r1, side_saddr + 128, nv1, s1);
   const float mx0 = chunk_max(s0), mx1 = chunk_max(s1);
   chunk_commit(mx0, s0, col_base, stash_saddr, best, best_col);
   chunk_commit(mx1, s1, col_base + 32, stash_saddr, best, best_col);
@@ -263,7 +269,7 @@ __device__ __forceinline__ uint32_t resolve_index(uint32_t stash_saddr, float be
 // One warp's 4 x 32 columns of a 128 x 256 accumulator; TMEM loads are double-buffered so that the load of
 // chunk c+1 is in flight while chunk c is reduced.  The accumulator is released to the MMA warp as soon
 // as the last load has landed in registers.
-template <bool USE_SIDE, bool MASK>
+template <int SIDE, bool MASK>
 __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr, uint32_t gcol0, int b_rows,
                                             uint64_t* tmem_empty_bar, int lane, uint32_t stash_saddr, float& best,
                                             uint32_t& best_col) {
@@ -276,18 +282,18 @@ __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr,
   tmem_ld32(taddr, ra);
   tmem_ld_wait(ra);
   tmem_ld32(taddr + 32, rb);
-  chunk_argmax<USE_SIDE, MASK>(ra, side_saddr, gcol0, nv(0), stash_saddr, best, best_col);
+  chunk_argmax<SIDE, MASK>(ra, side_saddr, gcol0, nv(0), stash_saddr, best, best_col);
   tmem_ld_wait(rb);
   tmem_ld32(taddr + 64, ra);
-  chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), stash_saddr, best, best_col);
+  chunk_argmax<SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), stash_saddr, best, best_col);
   tmem_ld_wait(ra);
   tmem_ld32(taddr + 96, rb);
-  chunk_argmax<USE_SIDE, MASK>(ra, side_saddr + 256, gcol0 + 64, nv(2), stash_saddr, best, best_col);
+  chunk_argmax<SIDE, MASK>(ra, side_saddr + 256, gcol0 + 64, nv(2), stash_saddr, best, best_col);
   tmem_ld_wait(rb);
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(tmem_empty_bar);  // every load of this warp is in registers: buffer is free
-  chunk_argmax<USE_SIDE, MASK>(rb, side_saddr + 384, gcol0 + 96, nv(3), stash_saddr, best, best_col);
+  chunk_argmax<SIDE, MASK>(rb, side_saddr + 384, gcol0 + 96, nv(3), stash_saddr, best, best_col);
 }
 
 // Epilogue role.  NEW = 8: one group of 8 warps drains every tile.  NEW = 16: TWO groups of 8 warps, group g
@@ -296,7 +302,7 @@ __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr,
 // serialise with the reduction.  Inside a group, warp%4 selects the TMEM lane quarter (hardware rule) and
 // (warp_in_group / 4) the 128-column half.  Each group keeps its own running best per row and publishes it
 // with the 64-bit atomicMin (the combine is associative: same result as a single group).
-template <bool USE_SIDE, int NEW>
+template <int SIDE, int NEW>
 __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_base, uint8_t* stash_smem,
                                               float* side_smem, uint64_t* tmem_full, uint64_t* tmem_empty, int t0,
                                               int t1, int b_tiles, int a_rows, int b_rows,
@@ -320,7 +326,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
   for (int t = t0; t < t1; ++t) {
     const uint32_t buf = (uint32_t)(t - t0) & 1u;
     if (GROUPS == 1 || buf == (uint32_t)group) {
-      if constexpr (USE_SIDE) {
+      if constexpr (SIDE != 0) {
         // the group's 256 threads stage the 256 side terms of this code tile (vector padded with +inf);
         // the barrier also orders "everyone in the group finished the tile that used this buffer before"
         side_smem[buf * BN + gtid] = __ldg(b_half_sqnorm + bt * BN + gtid);
@@ -332,9 +338,9 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
       const uint32_t side_saddr = side_base + buf * (BN * 4);
       const uint32_t gcol0 = (uint32_t)(bt * BN) + col0;
       if (last_partial && bt == b_tiles - 1)
-        tile_argmax<USE_SIDE, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+        tile_argmax<SIDE, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
       else
-        tile_argmax<USE_SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+        tile_argmax<SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
       if (buf) par1 ^= 1; else par0 ^= 1;
     }
     if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish
@@ -362,7 +368,7 @@ __global__ void __launch_bounds__(64 + NEW * 32, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ TermTable terms, int pa, int pb, int kblocks, int nstages, int64_t a_rows,
                  int64_t a_rows_pad, int64_t b_rows, int64_t b_rows_pad, const float* __restrict__ b_half_sqnorm,
-                 int64_t b_index_offset, unsigned long long* __restrict__ keys) {
+                 int side_mode, int64_t b_index_offset, unsigned long long* __restrict__ keys) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
   // WHOLE: a stage holds every B plane of one code tile; the row tile's A planes are RESIDENT in one of two
@@ -539,12 +545,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue: fused arg-max =====================
-    if (b_half_sqnorm != nullptr)
-      epilogue_loop<true, NEW>(warp, lane, tmem_base, stash_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,
-                               (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys);
-    else
-      epilogue_loop<false, NEW>(warp, lane, tmem_base, stash_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,
-                                (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys);
+#define VQB_EPI(SIDE_)                                                                                              \
+  epilogue_loop<SIDE_, NEW>(warp, lane, tmem_base, stash_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,  \
+                            (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys)
+    if (b_half_sqnorm == nullptr || side_mode == 0) VQB_EPI(0);
+    else if (side_mode == 1) VQB_EPI(1);
+    else VQB_EPI(2);
+#undef VQB_EPI
   }
 
   tc_fence_before();
@@ -617,8 +624,8 @@ static TermTable make_terms(int pa, int pb) {
 
 template <int BK, bool WHOLE, int NEW>
 static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, const void* b_planes, int pb,
-                  int64_t b_rows, int64_t b_pad, int Dp, const float* h, int64_t off, unsigned long long* keys,
-                  cudaStream_t st) {
+                  int64_t b_rows, int64_t b_pad, int Dp, const float* h, int side_mode, int64_t off,
+                  unsigned long long* keys, cudaStream_t st) {
   CUtensorMap ma, mb;
   if (int e = make_operand_map(&ma, a_planes, pa * a_pad, Dp, BK, BM)) return e;
   if (int e = make_operand_map(&mb, b_planes, pb * b_pad, Dp, BK, BN)) return e;
@@ -639,14 +646,14 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
   int grid = sm_count();
   if (total < grid) grid = (int)total;
   assign_tc_kernel<BK, WHOLE, NEW><<<grid, 64 + NEW * 32, smem_bytes, st>>>(ma, mb, terms, pa, pb, Dp / BK, nstages, a_rows, a_pad,
-                                                                  b_rows, b_pad, h, off, keys);
+                                                                  b_rows, b_pad, h, side_mode, off, keys);
   VQB_LAUNCH_OK();
   return VQB_OK;
 }
 
 int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, const void* b_planes, int pb,
-                     int64_t b_rows, int64_t b_pad, int D, const float* h, int64_t off, unsigned long long* keys,
-                     cudaStream_t st) {
+                     int64_t b_rows, int64_t b_pad, int D, const float* h, int side_mode, int64_t off,
+                     unsigned long long* keys, cudaStream_t st) {
   const int Dp = (int)vqb_operand_dp(D);
   // One epilogue group (8 warps) is the default: the two-group variant (16 warps, one group per TMEM
   // accumulator) measured SLOWER on B200 for D = 32 (0.103 vs 0.092 ms at cfg 2) because 576 threads cap the
@@ -664,8 +671,8 @@ int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad
   const bool whole = Dp <= 64 && (size_t)(2 * pa * BM + 2 * pb * BN) * Dp * 2 <= 196608 - stash;
 #define VQB_LAUNCH(BK_, W_)                                                                                         \
   do {                                                                                                              \
-    if (nwarps == 16) return launch<BK_, W_, 16>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, off, keys, st); \
-    return launch<BK_, W_, 8>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, off, keys, st);                   \
+    if (nwarps == 16) return launch<BK_, W_, 16>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, side_mode, off, keys, st); \
+    return launch<BK_, W_, 8>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, side_mode, off, keys, st);                   \
   } while (0)
   if (Dp == 16) { if (whole) VQB_LAUNCH(16, true); VQB_LAUNCH(16, false); }
   if (Dp == 32) { if (whole) VQB_LAUNCH(32, true); VQB_LAUNCH(32, false); }

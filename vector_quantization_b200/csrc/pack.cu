@@ -211,6 +211,25 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const TG* __restrict__ 
   }
 }
 
+// out[r] = 1 / max(||x_r||, eps) for r < rows, 0 in the padding up to rows_pad (per-column scale of vqb_assign)
+template <typename T, int G>
+__global__ void __launch_bounds__(256) row_inv_norm_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_pad, int D,
+                                                           float* __restrict__ out) {
+  const int lane = threadIdx.x % G;
+  const int64_t rows_per_block = blockDim.x / G;
+  for (int64_t r = blockIdx.x * rows_per_block + threadIdx.x / G; r < rows_pad;
+       r += (int64_t)gridDim.x * rows_per_block) {
+    float ss = 0.f;
+    if (r < rows)
+      for (int d = lane; d < D; d += G) {
+        const float v = to_f32<T>(x[r * D + d]);
+        ss = fmaf(v, v, ss);
+      }
+    ss = group_sum<G>(ss);
+    if (lane == 0) out[r] = r < rows ? __fdiv_rn(1.f, fmaxf(sqrtf(ss), kNormEps)) : 0.f;
+  }
+}
+
 template <int G, typename F>
 static inline void launch_rows(int64_t rows, F&& f) {
   const int rows_per_block = 256 / G;
@@ -306,6 +325,22 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
       pack_rows_kernel<__nv_bfloat16, G><<<blocks, 256, 0, st>>>(
           (const __nv_bfloat16*)src, rows, rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes,
           half_sqnorm, writeback, keys, keys ? n_keys : 0);
+  }));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, float* out, void* stream) {
+  VQB_REQUIRE(x && out, "vqb_row_inv_norm: null pointer");
+  VQB_REQUIRE(rows >= 1 && D >= 1, "vqb_row_inv_norm: bad shape");
+  const int64_t rows_pad = vqb_operand_rows_pad(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = lanes_per_row(D);
+  VQB_DISPATCH_G(g, launch_rows<G>(rows_pad, [&](int blocks) {
+    if (x_dtype == VQB_F32)
+      row_inv_norm_kernel<float, G><<<blocks, 256, 0, st>>>((const float*)x, rows, rows_pad, D, out);
+    else
+      row_inv_norm_kernel<__nv_bfloat16, G><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, rows_pad, D, out);
   }));
   VQB_LAUNCH_OK();
   return VQB_OK;

@@ -84,8 +84,15 @@ def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, preci
     operands swapped.  Cosine needs normalised token planes here (the token norm now varies along the
     reduced axis); L2 needs the tokens' 0.5|x|^2."""
     cos = metric == 'Cosine'
-    toks = ops.pack_rows(x, normalize=cos, planes=_planes_for(x, cos, precision), want_half_sqnorm=not cos)
     keys = ops.new_keys(codebook.rows, x.device)
+    if cos:
+        raw = ops.as_operand(x)
+        if raw is not None:
+            # bf16 tokens: ONE exact raw plane + a per-column 1/|x_n| scale in the epilogue instead of three planes
+            # of the normalised tokens (halves the MMA work of this pass)
+            raw.inv_norm = ops.row_inv_norm(x)
+            return ops.assign(codebook, raw, keys, l2=False, scale_columns=True, index_offset=index_offset)
+    toks = ops.pack_rows(x, normalize=cos, planes=_planes_for(x, cos, precision), want_half_sqnorm=not cos)
     return ops.assign(codebook, toks, keys, l2=not cos, index_offset=index_offset)
 
 

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, VQB_BF16, VQB_F32, FSQParams, check
 
 __all__ = [
-    'Operand', 'as_operand', 'pack_rows', 'assign', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
+    'Operand', 'as_operand', 'pack_rows', 'assign', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
     'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
     'fsq_decode', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
@@ -76,6 +76,7 @@ class Operand:
     nplanes: int
     half_sqnorm: torch.Tensor | None = None
     plane_rows: int = 0  # row stride between planes; 0 = padded default, rows = zero-copy view of a bf16 tensor
+    inv_norm: torch.Tensor | None = None  # fp32 [rows_pad] 1/|row| (per-column scale for raw-token column arg-min)
 
 
 def operand_shape(rows: int, D: int) -> tuple[int, int]:
@@ -110,18 +111,31 @@ def new_keys(n: int, device) -> torch.Tensor:
 
 
 def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset: int = 0,
-           backend: int = BACKEND_TCGEN05) -> torch.Tensor:
-    """keys[i] = min(keys[i], key(argmax_j <a_i,b_j> - (l2 ? 0.5||b_j||^2 : 0)))."""
+           backend: int = BACKEND_TCGEN05, scale_columns: bool = False) -> torch.Tensor:
+    """keys[i] = min(keys[i], key(argmax_j score)), score = <a_i,b_j> - 0.5|b_j|^2 (l2), <a_i,b_j> * (1/|b_j|)
+    (scale_columns: b holds RAW rows + `inv_norm`), or <a_i,b_j>."""
     lib = _lib.load()
     _cuda(a.planes, b.planes, keys)
     assert a.dim == b.dim and keys.dtype == torch.int64 and keys.numel() >= a.rows
-    h = None
+    side, mode = None, 0
     if l2:
         assert b.half_sqnorm is not None, 'L2 assignment needs the packed operand to carry half_sqnorm'
-        h = b.half_sqnorm
+        side, mode = b.half_sqnorm, 1
+    elif scale_columns:
+        assert b.inv_norm is not None
+        side, mode = b.inv_norm, 2
     _call('vqb_assign', lib.vqb_assign, _p(a.planes), a.nplanes, a.rows, a.plane_rows, _p(b.planes), b.nplanes, b.rows,
-          b.plane_rows, a.dim, _p(h), index_offset, _p(keys), backend, _stream())
+          b.plane_rows, a.dim, _p(side), mode, index_offset, _p(keys), backend, _stream())
     return keys
+
+
+def row_inv_norm(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _cuda(x)
+    rows, D = x.shape
+    out = torch.empty((operand_shape(rows, D)[0],), dtype=torch.float32, device=x.device)
+    _call('vqb_row_inv_norm', lib.vqb_row_inv_norm, _p(x), _dt(x), rows, D, _p(out), _stream())
+    return out
 
 
 def unpack_keys(keys: torch.Tensor, index_offset: int = 0, want_score: bool = False):
