@@ -435,9 +435,10 @@ def main():
         print(json.dumps(dict(
             metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
-            dtype='bf16 (bf16 tokens/operands, fp32 accumulate; fp32 codebook as exact bf16x3 planes)',
-            data='synthetic',
-            config=dict(base_cfg, l2_policy=f'rotating {n_sets} input sets, {n_sets * (N * D * 6) >> 20} MB > L2',
+            dtype='bf16', data='synthetic',
+            config=dict(base_cfg, arithmetic='bf16 tokens and bf16 tensor-core operands, fp32 accumulation; the fp32 '
+                        'codebook enters as 3 exact bf16 planes; z/loss fp32, token gradient bf16',
+                        l2_policy=f'rotating {n_sets} input sets, {n_sets * (N * D * 6) >> 20} MB > L2',
                         launch='CUDA graph replay' if graphs else 'eager', kernels_per_step=launches_per_step),
             clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline,
             e2e=dict(value=N * world / (e2e_ms * 1e-3), unit=unit, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,

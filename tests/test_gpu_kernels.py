@@ -64,13 +64,14 @@ def test_pack_rows(dev, rows, D, normalize, planes, dtype):
 @pytest.mark.parametrize('backend', [ops.BACKEND_SIMT, ops.BACKEND_TCGEN05], ids=['simt', 'tcgen05'])
 @pytest.mark.parametrize('metric', ['L2', 'Cosine'])
 @pytest.mark.parametrize('N,K,D', [(1000, 700, 32), (2048, 1024, 8), (384, 512, 256), (300, 333, 64), (257, 4100, 20),
-                                   (128, 256, 768)])
+                                   (128, 256, 768), (1, 1, 1), (3, 2, 5), (130, 7, 16), (5, 300, 2)])
 def test_assign_fp32_parity(dev, backend, metric, N, K, D):
     x, E = O.synthetic_latents(N, K, D, seed=3407 + N + D)
     q_ref, d = O.encode(metric, x, E)
     q, score = _assign(x, E, metric, dev, backend)
     n_diff = _check_indices(d, q_ref, q.cpu(), what=f'{metric} {N}x{K}x{D}')
     assert n_diff <= max(2, N // 200)
+    assert int(q.min()) >= 0 and int(q.max()) < K
     # the kernel's score is <x, e> - 0.5|e|^2 (L2) or <x, e/|e|> (cosine)
     Ef = F.normalize(E) if metric == 'Cosine' else E
     s_ref = (x * Ef[q.cpu()]).sum(1) - (0.5 * (Ef[q.cpu()] ** 2).sum(1) if metric == 'L2' else 0)

@@ -239,19 +239,6 @@ __device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t s
   chunk_scores<SIDE, MASK>(r, side_saddr, n_valid, s);
   chunk_commit(chunk_max(s), s, col_base, stash_saddr, best, best_col);
 }
-// two adjacent chunks at once: the two max trees are independent, which doubles the ILP of the reduction
-template <int SIDE, bool MASK>
-__device__ __forceinline__ void pair_argmax(const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t side_saddr,
-                                            uint32_t col_base, int nv0, int nv1, uint32_t stash_saddr, float& best,
-                                            uint32_t& best_col) {
-  float s0[32], s1[32];
-  chunk_scores<SIDE, MASK>(r0, side_saddr, nv0, s0);
-  chunk_scores<SIDE, MASK>(r1, side_saddr + 128, nv1, s1);
-  const float mx0 = chunk_max(s0), mx1 = chunk_max(s1);
-  chunk_commit(mx0, s0, col_base, stash_saddr, best, best_col);
-  chunk_commit(mx1, s1, col_base + 32, stash_saddr, best, best_col);
-}
-
 // first position of `best` inside the stashed winning chunk (lowest index wins ties, like torch.argmin)
 __device__ __forceinline__ uint32_t resolve_index(uint32_t stash_saddr, float best) {
   int j = 31;
