@@ -391,7 +391,8 @@ def synthetic_latents(N: int, K: int, D: int, seed: int = 3407, sigma: float = 0
         E = F.normalize(E)
     if clustered:
         pi = torch.randint(0, K, (N,), generator=g)
-        x = E[pi] + sigma * E.std() * torch.randn(N, D, generator=g)
+        std = E.std() if E.numel() > 1 else torch.tensor(1.0)   # std of a single element is NaN
+        x = E[pi] + sigma * std * torch.randn(N, D, generator=g)
     else:
         x = torch.randn(N, D, generator=g)
     return x, E

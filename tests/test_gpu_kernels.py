@@ -79,6 +79,24 @@ def test_assign_fp32_parity(dev, backend, metric, N, K, D):
 
 
 @pytest.mark.parametrize('backend', [ops.BACKEND_SIMT, ops.BACKEND_TCGEN05], ids=['simt', 'tcgen05'])
+def test_assign_nan_token_rows_return_index_zero(dev, backend):
+    """A token with a NaN component has NaN distance to every code: torch.argmin returns 0 for such a row
+    (what the reference's `distance.argmin(-1)` yields); the other rows are unaffected and nothing reads out
+    of bounds downstream."""
+    N, K, D = 300, 77, 32
+    x, E = O.synthetic_latents(N, K, D, seed=5)
+    x[17, 3] = float('nan')
+    x[255] = float('nan')
+    q_ref, d = O.encode('L2', x, E)
+    assert q_ref[17] == 0 and q_ref[255] == 0
+    q, _ = _assign(x, E, 'L2', dev, backend)
+    assert q[17] == 0 and q[255] == 0
+    keep = torch.ones(N, dtype=torch.bool)
+    keep[[17, 255]] = False
+    _check_indices(d[keep], q_ref[keep], q.cpu()[keep], what='rows next to NaN rows')
+
+
+@pytest.mark.parametrize('backend', [ops.BACKEND_SIMT, ops.BACKEND_TCGEN05], ids=['simt', 'tcgen05'])
 def test_assign_bf16_tokens_exact_operands(dev, backend):
     """bf16 tokens are ONE exact plane; the fp32 codebook is three: products are exact, so the only
     difference from the fp32 oracle on the up-cast inputs is fp32 accumulation order."""

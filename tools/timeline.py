@@ -22,4 +22,4 @@ t0 = int(ts[ts > 0].min())
 rel = (ts - t0).clamp_min(-1)
 print('tile | producer: wait_start got_empty tma_issued | mma: start got_tmem_empty got_full committed | epi: wait_start got_full released')
 for t in range(0, 40):
-    print(t, rel[0, t, :3].tolist(), rel[1, t].tolist(), rel[2, t, :3].tolist())
+    print(t, rel[0, t, :3].tolist(), rel[1, t].tolist(), rel[2, t].tolist())

@@ -239,6 +239,20 @@ __device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t s
   chunk_scores<SIDE, MASK>(r, side_saddr, n_valid, s);
   chunk_commit(chunk_max(s), s, col_base, stash_saddr, best, best_col);
 }
+// Two adjacent chunks at once: their max trees are independent, so the scheduler can interleave the two
+// dependent FMNMX3 chains (the reduction is latency-bound with 2 epilogue warps per SM sub-partition).
+template <int SIDE, bool MASK>
+__device__ __forceinline__ void pair_argmax(const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t side_saddr,
+                                            uint32_t col_base, int nv0, int nv1, uint32_t stash_saddr, float& best,
+                                            uint32_t& best_col) {
+  float s0[32], s1[32];
+  chunk_scores<SIDE, MASK>(r0, side_saddr, nv0, s0);
+  chunk_scores<SIDE, MASK>(r1, side_saddr + 128, nv1, s1);
+  const float mx0 = chunk_max(s0), mx1 = chunk_max(s1);
+  chunk_commit(mx0, s0, col_base, stash_saddr, best, best_col);
+  chunk_commit(mx1, s1, col_base + 32, stash_saddr, best, best_col);
+}
+
 // first position of `best` inside the stashed winning chunk (lowest index wins ties, like torch.argmin)
 __device__ __forceinline__ uint32_t resolve_index(uint32_t stash_saddr, float best) {
   int j = 31;
@@ -259,28 +273,30 @@ __device__ __forceinline__ uint32_t resolve_index(uint32_t stash_saddr, float be
 template <int SIDE, bool MASK>
 __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr, uint32_t gcol0, int b_rows,
                                             uint64_t* tmem_empty_bar, int lane, uint32_t stash_saddr, float& best,
-                                            uint32_t& best_col) {
+                                            uint32_t& best_col, int tsi = 1 << 20) {
   uint32_t ra[32], rb[32];
   auto nv = [&](int c) -> int {
     if constexpr (!MASK) return 32;
     const int left = b_rows - (int)(gcol0 + 32 * c);
     return left >= 32 ? 32 : (left < 0 ? 0 : left);
   };
+  uint32_t rc[32], rd[32];
   tmem_ld32(taddr, ra);
-  tmem_ld_wait(ra);
   tmem_ld32(taddr + 32, rb);
-  chunk_argmax<SIDE, MASK>(ra, side_saddr, gcol0, nv(0), stash_saddr, best, best_col);
-  tmem_ld_wait(rb);
-  tmem_ld32(taddr + 64, ra);
-  chunk_argmax<SIDE, MASK>(rb, side_saddr + 128, gcol0 + 32, nv(1), stash_saddr, best, best_col);
   tmem_ld_wait(ra);
-  tmem_ld32(taddr + 96, rb);
-  chunk_argmax<SIDE, MASK>(ra, side_saddr + 256, gcol0 + 64, nv(2), stash_saddr, best, best_col);
   tmem_ld_wait(rb);
+  if (lane == 0) TS(2, tsi, 1);
+  tmem_ld32(taddr + 64, rc);
+  tmem_ld32(taddr + 96, rd);
+  pair_argmax<SIDE, MASK>(ra, rb, side_saddr, gcol0, nv(0), nv(1), stash_saddr, best, best_col);
+  if (lane == 0) TS(2, tsi, 2);
+  tmem_ld_wait(rc);
+  tmem_ld_wait(rd);
+  if (lane == 0) TS(2, tsi, 3);
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(tmem_empty_bar);  // every load of this warp is in registers: buffer is free
-  chunk_argmax<SIDE, MASK>(rb, side_saddr + 384, gcol0 + 96, nv(3), stash_saddr, best, best_col);
+  pair_argmax<SIDE, MASK>(rc, rd, side_saddr + 256, gcol0 + 64, nv(2), nv(3), stash_saddr, best, best_col);
 }
 
 // Epilogue role.  NEW = 8: one group of 8 warps drains every tile.  NEW = 16: TWO groups of 8 warps, group g
@@ -320,6 +336,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
         named_bar_sync(1 + group, 256);
       }
       mbar_wait(tmem_full + buf, buf ? par1 : par0);
+      if (warp == 2 && lane == 0) TS(2, t - t0, 0);
       tc_fence_after();
       const uint32_t taddr = taddr0 + buf * BN;
       const uint32_t side_saddr = side_base + buf * (BN * 4);
@@ -327,7 +344,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
       if (last_partial && bt == b_tiles - 1)
         tile_argmax<SIDE, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
       else
-        tile_argmax<SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+        tile_argmax<SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col, warp == 2 ? t - t0 : 1 << 20);
       if (buf) par1 ^= 1; else par0 ^= 1;
     }
     if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish

@@ -71,6 +71,8 @@ __host__ __device__ __forceinline__ float from_orderable(uint32_t o) {
 __host__ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t index) {
   return (static_cast<unsigned long long>(~orderable(score)) << 32) | index;
 }
+// Initial value of a key slot ("no candidate yet").  A row whose scores are all NaN keeps it.
+constexpr unsigned long long kNoKey = ~0ull;
 __host__ __device__ __forceinline__ uint32_t key_index(unsigned long long k) { return static_cast<uint32_t>(k); }
 __host__ __device__ __forceinline__ float key_score(unsigned long long k) {
   return from_orderable(~static_cast<uint32_t>(k >> 32));

@@ -73,7 +73,13 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* sh /* >= 2
 __device__ __forceinline__ int64_t row_index(const int64_t* __restrict__ quant,
                                              const unsigned long long* __restrict__ keys, int64_t n,
                                              int64_t key_offset, int64_t K) {
-  int64_t q = quant ? quant[n] : (int64_t)key_index(keys[n]) - key_offset;
+  int64_t q;
+  if (quant) {
+    q = quant[n];
+  } else {
+    const unsigned long long k = keys[n];
+    q = k == kNoKey ? 0 : (int64_t)key_index(k) - key_offset;   // no finite score (NaN token): 0, like torch.argmin
+  }
   return q < 0 ? 0 : (q >= K ? K - 1 : q);  // never read out of bounds on a corrupt index
 }
 
@@ -307,7 +313,7 @@ __global__ void unpack_keys_kernel(const unsigned long long* __restrict__ keys, 
                                    int64_t* __restrict__ idx, float* __restrict__ score) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const unsigned long long k = keys[i];
-    if (idx) idx[i] = (int64_t)key_index(k) - offset;
+    if (idx) idx[i] = k == kNoKey ? 0 : (int64_t)key_index(k) - offset;   // NaN row: index 0, like torch.argmin
     if (score) score[i] = key_score(k);
   }
 }
