@@ -170,7 +170,7 @@ def run_cfg5(args, rank, world, local_rank):
     g = torch.Generator(device='cpu').manual_seed(SEED)
     x = torch.randn(N, D, generator=g).to(torch.bfloat16).to(dev)
     W = torch.randn(hi - lo, D, generator=torch.Generator(device='cpu').manual_seed(SEED + 1 + rank)).to(dev)
-    precision = os.environ.get('VQB_PRECISION', 'exact')
+    precision = os.environ.get('VQB_PRECISION', 'fp32')
 
     def step():
         return parallel.sharded_nearest_code(x, W, 'Cosine', shard_lo=lo, precision=precision)[0]
@@ -197,12 +197,13 @@ def run_cfg5(args, rank, world, local_rank):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
-    terms = {'exact': 3, 'high': 2, 'fast': 1}[precision]
+    terms = {'fp32': 2, 'exact': 3, 'high': 2, 'fast': 1}[precision]
+    fmt = 'the fp16 (hi, lo*2^11) plane pair (22 bits)' if precision == 'fp32' else f'{terms} bf16 plane(s)'
     if rank == 0:
         print(json.dumps(dict(
             metric='quantized tokens/sec', value=N / (ms * 1e-3), unit='tokens/s', n_gpus=world, steps=steps,
             warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True, scaling='strong', vs_baseline=None,
-            dtype=f'bf16 tokens, fp32 codebook as {terms} exact bf16 plane(s)', data='synthetic',
+            dtype=f'bf16 tokens, fp32 codebook as {fmt}', data='synthetic',
             config=dict(workload='cfg5: 262144x768 codebook sharded over the ranks, 65536 tokens replicated, '
                                  'min-loc all-reduce', parallelism=f'codebook-sharded x{world}', precision=precision,
                         l2_policy='operands (shard planes >= 150 MB) exceed L2'),
@@ -343,13 +344,17 @@ def main():
     value = N * world / (ms * 1e-3)
 
     # ---- dominant kernel (tcgen05 assignment) timed live with CUDA events on the launching stream ----
-    # Same operands as inside the step (raw bf16 tokens: 1 exact plane; normalised fp32 codebook: 3 planes).
+    # Same operands as inside the step (raw bf16 tokens: 1 exact plane; normalised fp32 codebook: the fp16
+    # (hi, lo*2^11) pair for the default precision, 3 bf16 planes for precision='exact').
     # A 1 GiB memset before every launch flushes L2 and keeps the GPU busy while the host enqueues, so the
     # event pair brackets the kernel only (no host launch latency inside).
     from vector_quantization_b200 import functional as Fq
     flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
-    book = Fq.pack_codebook(q.embedding.weight.data, wl['metric'], precision=q.precision, writeback_normalized=True)
-    toks = ops.pack_rows(sets[0][0].detach(), planes=1)
+    x_first = sets[0][0].detach()
+    book = Fq.pack_codebook(q.embedding.weight.data, wl['metric'], precision=q.precision, writeback_normalized=True,
+                            tokens=x_first)
+    toks = ops.pack_rows(x_first, planes=1)
+    n_terms = 2 if book.pair else book.nplanes
     keys = ops.new_keys(N, dev)
     ops.PROFILE = []
     for i in range(min(args.steps, 30) + 3):
@@ -387,9 +392,11 @@ def main():
                     peak_source='MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (B200_PROFILING.md)',
                     kernel_ms=assign_avg, kernel_share_of_step=assign_avg / ms,
                     epilogue_gelem_per_s=N * K / (assign_avg * 1e-3) / 1e9, traffic=traffic,
-                    algorithmic_bytes=N * D * 2 + K * D * 2 * 3 + N * 8, ncu=ncu_note,
-                    note='algorithmic flops 2*N*K*D (one plane); the exact mode issues 3 plane MMAs per tile, '
-                         'so the tensor pipe itself is ~3x busier than `frac` (see ncu.tensor_pipe_active_pct)')
+                    algorithmic_bytes=N * D * 2 + K * D * 2 * book.nplanes + N * 8, ncu=ncu_note,
+                    mma_terms=n_terms, mma_issued_tflops=achieved * n_terms * (book.planes.shape[-1] / D),
+                    note=f'algorithmic flops 2*N*K*D (one plane); the fp32 codebook is fed as {book.nplanes} 16-bit '
+                         f'planes = {n_terms} MMA terms per tile, so the tensor pipe is ~{n_terms}x busier than '
+                         '`frac` (mma_issued_tflops; see ncu.tensor_pipe_active_pct)')
 
     # ---- end-to-end: pinned host inputs -> device -> step -> results back to pinned host ----
     xh = x0.pin_memory()

@@ -50,14 +50,31 @@ int vqb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *                                               vq/algorithms/vq/distances.py:41-42
  * Dp       = vqb_operand_dp(D)        (16, 32 or a multiple of 64)
  * rows_pad = vqb_operand_rows_pad(rows) (multiple of 256)
+ *
+ * Plane formats (the `planes` / `*_nplanes` arguments):
+ *   1..3              bf16 planes hi, mid, lo:  v == hi + mid + lo exactly for 3 planes of an fp32 value.
+ *   VQB_PLANES_F16    one IEEE fp16 plane of a bf16 source (`normalize` = 0): exact for 2^-17 <= |v| < 2^15
+ *                     (abs. error <= 2^-25 below; a row with a component >= 2^15 is scaled by a power of two,
+ *                     which leaves its arg-max unchanged).  The tensor core cannot mix fp16 and bf16 operands,
+ *                     so this is how one-plane bf16 tokens meet a VQB_PLANES_F16X2 codebook.
+ *   VQB_PLANES_F16X2  two IEEE fp16 planes (hi, lo'):  hi = fp16(v), lo' = fp16((v - hi) * 2^11), so that
+ *                     v = hi + lo' * 2^-11 to 22 significant bits (abs. error <= max(2^-22 |v|, 2^-36)).
+ *                     Only for l2-normalised rows (|v| <= 1, `normalize` = 1).  `vqb_assign` accumulates the
+ *                     lo' term first and folds the 2^-11 into the accumulator with the tensor core's
+ *                     scale-input-d, so an fp32 codebook costs TWO MMA terms against one-plane tokens
+ *                     instead of three.  The other operand must be VQB_PLANES_F16 or VQB_PLANES_F16X2
+ *                     (both operands of one vqb_assign call are bf16 planes, or both are fp16 planes).
  */
+#define VQB_PLANES_F16 0x11
+#define VQB_PLANES_F16X2 0x12
+#define VQB_PLANE_COUNT(p) ((p) & 0xf)
 int64_t vqb_operand_dp(int D);
 int64_t vqb_operand_rows_pad(int64_t rows);
 size_t vqb_operand_bytes(int64_t rows, int D, int planes);
 int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D,
                   int normalize,            /* 1: pack F.normalize(row) instead of row */
-                  int planes,               /* 1..3 bf16 planes */
-                  void* dst_planes,         /* bf16 [planes][rows_pad][Dp], fully written (padding zeroed) */
+                  int planes,               /* 1..3 bf16 planes, VQB_PLANES_F16 (bf16 source, normalize = 0) or VQB_PLANES_F16X2 (normalize = 1) */
+                  void* dst_planes,         /* 16-bit [VQB_PLANE_COUNT(planes)][rows_pad][Dp], fully written (padding zeroed) */
                   float* half_sqnorm,       /* optional [rows_pad]: 0.5*||packed row||^2 (fp32); +inf in padding */
                   float* writeback_f32,     /* optional [rows, D]: the (normalised) fp32 row; may alias src when src is fp32 */
                   unsigned long long* keys_to_reset, int64_t n_keys, /* optional: fill with 0xFF.. (fused memset for vqb_assign) */

@@ -108,6 +108,95 @@ def test_assign_bf16_tokens_exact_operands(dev, backend):
     _check_indices(d, q_ref, q.cpu(), what='bf16 tokens')
 
 
+def test_pack_rows_fp16_pair_format(dev):
+    """VQB_PLANES_F16X2: hi = fp16(v), lo' = fp16((v - hi) * 2^11) of the NORMALISED row;
+    hi + lo' * 2^-11 reproduces v to 22 bits (abs error <= max(2^-22 |v|, 2^-36))."""
+    g = torch.Generator().manual_seed(7)
+    for rows, D, dtype in ((1000, 32, torch.float32), (300, 256, torch.float32), (77, 20, torch.float32),
+                           (513, 768, torch.bfloat16)):
+        src = (torch.randn(rows, D, generator=g) * 3).to(dtype)
+        wb = torch.empty(rows, D, dtype=torch.float32, device=dev)
+        op = ops.pack_rows(src.to(dev), normalize=True, fmt='f16x2', writeback=wb)
+        assert op.pair and op.nplanes == 2 and op.abi_planes == 0x12
+        planes = op.planes.view(torch.float16).float().cpu()
+        v = wb.cpu()                                # the kernel's own fp32 F.normalize(row)
+        torch.testing.assert_close(v, F.normalize(src.float()), rtol=3e-7, atol=1e-9)
+        rec = (planes[0, :rows, :D].double() + planes[1, :rows, :D].double() / 2048)
+        err = (rec - v.double()).abs()
+        assert (err <= (v.abs().double() * 2.0 ** -22).clamp_min(2.0 ** -36) + 1e-12).all(), float(err.max())
+        assert not planes[:, rows:].any() and not planes[:, :, D:].any()                    # padding zeroed
+    with pytest.raises(ValueError):
+        ops.pack_rows(src.to(dev), normalize=False, fmt='f16x2')
+
+
+@pytest.mark.parametrize('backend', [ops.BACKEND_SIMT, ops.BACKEND_TCGEN05], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('N,K,D', [(4096, 2048, 32), (1000, 700, 64), (384, 1100, 256), (257, 4100, 20), (300, 333, 768),
+                                   (2048, 512, 8)])
+def test_assign_fp16_pair_codebook(dev, backend, N, K, D):
+    """bf16 tokens (one plane) x fp16-pair codebook: two MMA terms, the lo' term first and the accumulator scaled
+    by 2^-11 (scale-input-d) when the hi term is added.  Indices equal the fp32 oracle except near-ties; the
+    score is <x, e/|e|> to fp32 rounding."""
+    x, E = O.synthetic_latents(N, K, D, seed=11 + D)
+    xb = x.to(torch.bfloat16)
+    q_ref, d = O.encode('Cosine', xb.float(), E)
+    book = ops.pack_rows(E.to(dev), normalize=True, fmt='f16x2')
+    toks = ops.pack_rows(xb.to(dev), fmt='f16')
+    keys = ops.new_keys(N, dev)
+    ops.assign(toks, book, keys, l2=False, backend=backend)
+    q, score = ops.unpack_keys(keys, want_score=True)
+    _check_indices(d, q_ref, q.cpu(), what=f'fp16 pair {N}x{K}x{D}')
+    s_ref = (xb.double() * F.normalize(E).double()[q.cpu()]).sum(1)
+    scale = xb.float().norm(dim=1).double()
+    # 2^-22 operand representation + fp32 accumulation over D products
+    tol = (2.0 ** -22 + 2.0 ** -23 * D ** 0.5) * scale + 1e-9
+    assert ((score.cpu().double() - s_ref).abs() <= tol).all()
+
+
+def test_assign_fp16_pair_both_operands_column_argmin(dev):
+    """pair x pair (three terms: a_lo'.b_hi, a_hi.b_lo', then the scaled a_hi.b_hi): the column arg-min of
+    NearestAnchor with normalised tokens that are not a zero-copy operand (D = 20 needs padding)."""
+    N, K, D = 1500, 300, 20
+    x, E = O.synthetic_latents(N, K, D, seed=5)
+    xb = x.to(torch.bfloat16)
+    d = 1 - F.normalize(xb.float()) @ F.normalize(E).t()
+    book = ops.pack_rows(E.to(dev), normalize=True, fmt='f16x2')
+    toks = ops.pack_rows(xb.to(dev), normalize=True, fmt='f16x2')
+    for backend in (ops.BACKEND_SIMT, ops.BACKEND_TCGEN05):
+        keys = ops.new_keys(K, dev)
+        ops.assign(book, toks, keys, l2=False, backend=backend)
+        _check_indices(d.t().contiguous(), d.argmin(0), ops.unpack_keys(keys).cpu(), what='pair x pair')
+
+
+def test_assign_rejects_mixed_fp16_bf16_operands(dev):
+    """kind::f16 MMAs take fp16 x fp16 or bf16 x bf16 (a mixed pair is an illegal instruction on B200)."""
+    from vector_quantization_b200._lib import VQBError
+    x, E = O.synthetic_latents(300, 64, 32)
+    book = ops.pack_rows(E.to(dev), normalize=True, fmt='f16x2')
+    for toks in (ops.pack_rows(x.to(dev), planes=3), ops.pack_rows(x.to(torch.bfloat16).to(dev), planes=1)):
+        with pytest.raises(VQBError):
+            ops.assign(toks, book, ops.new_keys(300, dev), l2=False)
+
+
+def test_pack_rows_fp16_single_plane(dev):
+    """VQB_PLANES_F16: bf16 tokens are exact in one fp16 plane; a row with a huge component is scaled by a power
+    of two (its arg-max is unchanged)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(515, 24, generator=g).to(torch.bfloat16)
+    x[7] *= 1e6                                   # beyond the fp16 range
+    x[9, 0] = 3e-6                                # below the exact range: abs error <= 2^-25
+    op = ops.pack_rows(x.to(dev), fmt='f16')
+    assert op.fmt == 'f16' and op.abi_planes == 0x11 and op.nplanes == 1
+    got = op.planes.view(torch.float16)[0, :515, :24].float().cpu()
+    keep = torch.ones(515, dtype=torch.bool); keep[[7, 9]] = False
+    assert torch.equal(got[keep], x.float()[keep])
+    ratio = (got[7] / x.float()[7])
+    assert torch.isfinite(got[7]).all() and got[7].abs().max() < 2 ** 15
+    assert (ratio == ratio[0]).all() and float(torch.log2(ratio[0])) == round(float(torch.log2(ratio[0])))
+    assert (got[9] - x.float()[9]).abs().max() <= 2.0 ** -25
+    with pytest.raises(ValueError):
+        ops.pack_rows(x.float().to(dev), fmt='f16')
+
+
 def test_assign_tie_break_lowest_index(dev):
     """Exact ties resolve to the lowest index, like torch.argmin (duplicate codebook rows)."""
     N, D = 512, 32

@@ -23,11 +23,13 @@ def timeit(fn, iters=20, warm=3):
 
 cases = [  # name, N, K, D, metric, x dtype, planes_x, planes_e
     ('cfg2 cos bf16x/3p', 65536, 8192, 32, 'cos', torch.bfloat16, 1, 3),
+    ('cfg2 cos bf16x/pair', 65536, 8192, 32, 'cos', torch.bfloat16, 1, 'pair'),
     ('cfg2 cos bf16x/2p', 65536, 8192, 32, 'cos', torch.bfloat16, 1, 2),
     ('cfg2 cos bf16x/1p', 65536, 8192, 32, 'cos', torch.bfloat16, 1, 1),
     ('cfg3 l2 D8 3x3', 65536, 16384, 8, 'l2', torch.float32, 3, 3),
     ('cfg3 l2 D8 1x1', 65536, 16384, 8, 'l2', torch.bfloat16, 1, 1),
     ('cfg4 cos D256 1x3', 16384, 8192, 256, 'cos', torch.bfloat16, 1, 3),
+    ('cfg4 cos D256 1xpair', 16384, 8192, 256, 'cos', torch.bfloat16, 1, 'pair'),
     ('cfg4 cos D256 1x1', 16384, 8192, 256, 'cos', torch.bfloat16, 1, 1),
     ('cfg1 l2 D256 3x3', 16384, 8192, 256, 'l2', torch.float32, 3, 3),
     ('cfg5/8 cos D768 1x1', 65536, 32768, 768, 'cos', torch.bfloat16, 1, 1),
@@ -40,16 +42,17 @@ for name, N, K, D, metric, dt, px, pe in cases:
     x = torch.randn(N, D, device=dev).to(dt)
     E = torch.randn(K, D, device=dev)
     cos = metric == 'cos'
-    a = ops.pack_rows(x, planes=px)
-    b = ops.pack_rows(E, normalize=cos, planes=pe, want_half_sqnorm=not cos)
+    a = ops.pack_rows(x, planes=px) if pe != 'pair' else ops.pack_rows(x, fmt='f16')
+    pair = pe == 'pair'
+    b = ops.pack_rows(E, normalize=cos, planes=None if pair else pe, want_half_sqnorm=not cos, fmt='f16x2' if pair else 'bf16')
     keys = ops.new_keys(N, dev)
     med, best = timeit(lambda: ops.assign(a, b, keys, l2=not cos))
-    terms = {(1, 1): 1, (1, 2): 2, (1, 3): 3, (3, 3): 6, (2, 2): 3}[(px, pe)]
+    terms = {(1, 1): 1, (1, 2): 2, (1, 3): 3, (3, 3): 6, (2, 2): 3, (1, 'pair'): 2}[(px, pe)]
     flops = 2.0 * N * K * D
     rec = dict(case=name, ms_median=round(med, 4), ms_best=round(best, 4), terms=terms,
                algo_tflops=round(flops / med / 1e9, 1), mma_tflops=round(flops * terms * (ops.operand_shape(1, D)[1] / D) / med / 1e9, 1),
                gelem_per_s=round(N * K / med / 1e6, 1), mtok_per_s=round(N / med / 1e3, 1))
-    pk = timeit(lambda: ops.pack_rows(E, normalize=cos, planes=pe, want_half_sqnorm=not cos), iters=5)[0]
+    pk = timeit(lambda: ops.pack_rows(E, normalize=cos, planes=None if pair else pe, want_half_sqnorm=not cos, fmt='f16x2' if pair else 'bf16'), iters=5)[0]
     rec['pack_codebook_ms'] = round(pk, 4)
     print(json.dumps(rec), flush=True)
     out.append(rec)

@@ -19,6 +19,8 @@ CSRC = _HERE / 'csrc'
 
 VQB_F32, VQB_BF16 = 0, 1
 BACKEND_TCGEN05, BACKEND_SIMT = 0, 1
+PLANES_F16 = 0x11     # VQB_PLANES_F16: one fp16 plane of a bf16 source
+PLANES_F16X2 = 0x12   # VQB_PLANES_F16X2: the fp16 (hi, lo * 2^11) plane pair
 
 
 class VQBError(RuntimeError):

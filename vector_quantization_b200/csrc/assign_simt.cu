@@ -17,6 +17,12 @@ constexpr int SD = 32;   // depth chunk
 
 __device__ __forceinline__ float load_planes(const __nv_bfloat16* __restrict__ base, int planes,
                                              int64_t plane_stride, int64_t off) {
+  if (planes == VQB_PLANES_F16) return __half2float(__ushort_as_half(__bfloat16_as_ushort(base[off])));
+  if (is_f16x2(planes)) {  // fp16 pair: v = hi + lo' * 2^-11
+    const __half hi = __ushort_as_half(__bfloat16_as_ushort(base[off]));
+    const __half lo = __ushort_as_half(__bfloat16_as_ushort(base[plane_stride + off]));
+    return __half2float(hi) + __half2float(lo) * (1.f / (float)(1 << kPairShift));
+  }
   float v = 0.f;
   // lo -> hi so that the exact sum is reproduced bit for bit (|lo| << |mid| << |hi|)
   for (int p = planes - 1; p >= 0; --p) v += __bfloat162float(base[p * plane_stride + off]);
@@ -90,7 +96,9 @@ extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, int64_t 
   VQB_REQUIRE(a_planes && b_planes && keys, "vqb_assign: null pointer");
   VQB_REQUIRE(a_rows >= 1 && b_rows >= 1 && D >= 1, "vqb_assign: bad shape a_rows=%lld b_rows=%lld D=%d",
               (long long)a_rows, (long long)b_rows, D);
-  VQB_REQUIRE(pa >= 1 && pa <= 3 && pb >= 1 && pb <= 3, "vqb_assign: planes must be 1..3");
+  VQB_REQUIRE(planes_valid(pa) && planes_valid(pb), "vqb_assign: planes must be 1..3, VQB_PLANES_F16 or VQB_PLANES_F16X2");
+  VQB_REQUIRE(is_f16(pa) == is_f16(pb),
+              "vqb_assign: the tensor core cannot mix fp16 and bf16 operands (a_nplanes=0x%x b_nplanes=0x%x)", pa, pb);
   VQB_REQUIRE(b_rows + b_index_offset < 0xffffffffll && b_index_offset >= 0,
               "vqb_assign: column index does not fit 32 bits");
   cudaStream_t st = (cudaStream_t)stream;

@@ -25,11 +25,15 @@ constexpr int BN = 256;           // codes per tile (UMMA N)
 constexpr int UMMA_K = 16;        // bf16
 constexpr int kMaxTerms = 6;
 constexpr uint32_t kTmemCols = 512;  // two 256-column accumulators
+constexpr int kEpilogueWarps = 8;
+constexpr int kThreads = 64 + kEpilogueWarps * 32;
+constexpr uint32_t kStashBytes = kEpilogueWarps * 4096;  // winning-chunk stash: [warp][8 float4][32 lanes]
 
 struct TermTable {
   int n;
   int a[kMaxTerms];
   int b[kMaxTerms];
+  int scale[kMaxTerms];  // 1: the accumulator is multiplied by 2^-kPairShift before this term is added
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -91,6 +95,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D = D * 2^-11 + A.B  (scale-input-d): folds the 2^11 pre-scale of an fp16 pair's low plane back
+__device__ __forceinline__ void umma_f16_scaled(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  static_assert(kPairShift == 11, "immediate below");
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
 // mbarrier arrives once all tcgen05.mma issued so far by this thread have completed
@@ -273,7 +286,7 @@ __device__ __forceinline__ uint32_t resolve_index(uint32_t stash_saddr, float be
 template <int SIDE, bool MASK>
 __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr, uint32_t gcol0, int b_rows,
                                             uint64_t* tmem_empty_bar, int lane, uint32_t stash_saddr, float& best,
-                                            uint32_t& best_col, int tsi = 1 << 20) {
+                                            uint32_t& best_col) {
   uint32_t ra[32], rb[32];
   auto nv = [&](int c) -> int {
     if constexpr (!MASK) return 32;
@@ -285,38 +298,29 @@ __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr,
   tmem_ld32(taddr + 32, rb);
   tmem_ld_wait(ra);
   tmem_ld_wait(rb);
-  if (lane == 0) TS(2, tsi, 1);
   tmem_ld32(taddr + 64, rc);
   tmem_ld32(taddr + 96, rd);
   pair_argmax<SIDE, MASK>(ra, rb, side_saddr, gcol0, nv(0), nv(1), stash_saddr, best, best_col);
-  if (lane == 0) TS(2, tsi, 2);
   tmem_ld_wait(rc);
   tmem_ld_wait(rd);
-  if (lane == 0) TS(2, tsi, 3);
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(tmem_empty_bar);  // every load of this warp is in registers: buffer is free
   pair_argmax<SIDE, MASK>(rc, rd, side_saddr + 256, gcol0 + 64, nv(2), nv(3), stash_saddr, best, best_col);
 }
 
-// Epilogue role.  NEW = 8: one group of 8 warps drains every tile.  NEW = 16: TWO groups of 8 warps, group g
-// owns TMEM accumulator g, i.e. every other tile — while one group reduces tile i from registers the other
-// is already loading tile i+1, which hides the barrier hand-off and TMEM-load latencies that otherwise
-// serialise with the reduction.  Inside a group, warp%4 selects the TMEM lane quarter (hardware rule) and
-// (warp_in_group / 4) the 128-column half.  Each group keeps its own running best per row and publishes it
-// with the 64-bit atomicMin (the combine is associative: same result as a single group).
-template <int SIDE, int NEW>
+// Epilogue role: 8 warps drain every tile; warp%4 selects the TMEM lane quarter (hardware rule) and
+// (warp-2)/4 the 128-column half of the accumulator.
+template <int SIDE>
 __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_base, uint8_t* stash_smem,
                                               float* side_smem, uint64_t* tmem_full, uint64_t* tmem_empty, int t0,
                                               int t1, int b_tiles, int a_rows, int b_rows,
                                               const float* __restrict__ b_half_sqnorm, uint32_t b_index_offset,
                                               unsigned long long* __restrict__ keys) {
-  constexpr int GROUPS = NEW / 8;
   const int ew = warp - 2;
-  const int group = ew >> 3, ewg = ew & 7;
   const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32): the only ones this warp may read
-  const uint32_t col0 = (uint32_t)(ewg >> 2) * 128;
-  const int gtid = (threadIdx.x - 64) & 255;   // thread index inside the group
+  const uint32_t col0 = (uint32_t)(ew >> 2) * 128;
+  const int gtid = (int)threadIdx.x - 64;       // 0..255 among the epilogue threads
   const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
   const uint32_t side_base = smem_u32(side_smem) + col0 * 4;
   const uint32_t stash_saddr = smem_u32(stash_smem) + (uint32_t)ew * 4096 + (uint32_t)lane * 16;
@@ -326,14 +330,21 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
   uint32_t best_col = 0xffffffffu;
   int at = t0 / b_tiles, bt = t0 - at * b_tiles;
   uint32_t par0 = 0, par1 = 0;                 // per-accumulator phase parity
+  // side term of this thread's column for the tile about to be staged, fetched one tile ahead so that its
+  // L2 latency is not exposed in front of the barrier
+  float side_val = 0.f;
+  if constexpr (SIDE != 0) {
+    if (t0 < t1) side_val = __ldg(b_half_sqnorm + bt * BN + gtid);
+  }
   for (int t = t0; t < t1; ++t) {
     const uint32_t buf = (uint32_t)(t - t0) & 1u;
-    if (GROUPS == 1 || buf == (uint32_t)group) {
+    {
       if constexpr (SIDE != 0) {
-        // the group's 256 threads stage the 256 side terms of this code tile (vector padded with +inf);
-        // the barrier also orders "everyone in the group finished the tile that used this buffer before"
-        side_smem[buf * BN + gtid] = __ldg(b_half_sqnorm + bt * BN + gtid);
-        named_bar_sync(1 + group, 256);
+        // the 256 epilogue threads stage the 256 side terms of this code tile (vector padded with +inf); the
+        // barrier also orders "everyone finished the tile that used this buffer before"
+        side_smem[buf * BN + gtid] = side_val;
+        if (t + 1 < t1) side_val = __ldg(b_half_sqnorm + (bt + 1 == b_tiles ? 0 : bt + 1) * BN + gtid);
+        named_bar_sync(1, 256);
       }
       mbar_wait(tmem_full + buf, buf ? par1 : par0);
       if (warp == 2 && lane == 0) TS(2, t - t0, 0);
@@ -344,7 +355,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
       if (last_partial && bt == b_tiles - 1)
         tile_argmax<SIDE, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
       else
-        tile_argmax<SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col, warp == 2 ? t - t0 : 1 << 20);
+        tile_argmax<SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
       if (buf) par1 ^= 1; else par0 ^= 1;
     }
     if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish
@@ -367,10 +378,11 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
 // WHOLE = true : one pipeline stage holds every operand plane of one (row tile, code tile) work item
 //                (Dp == BK <= 64): one barrier wait, all term MMAs back to back, two commits per tile.
 // WHOLE = false: classic k-blocked ring, one stage = one BK-wide slab of one plane pair (large D).
-template <int BK, bool WHOLE, int NEW>
-__global__ void __launch_bounds__(64 + NEW * 32, 1)
+template <int BK, bool WHOLE>
+__global__ void __launch_bounds__(kThreads, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ TermTable terms, int pa, int pb, int kblocks, int nstages, int64_t a_rows,
+                 const __grid_constant__ TermTable terms, uint32_t idesc, int pa, int pb, int kblocks, int nstages,
+                 int64_t a_rows,
                  int64_t a_rows_pad, int64_t b_rows, int64_t b_rows_pad, const float* __restrict__ b_half_sqnorm,
                  int side_mode, int64_t b_index_offset, unsigned long long* __restrict__ keys) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -379,8 +391,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // slots (loaded once per row tile, not once per work item).  k-blocked: a stage is one [A slab | B slab] pair.
   const uint32_t stage_bytes = WHOLE ? (uint32_t)pb * kBBytes : kABytes + kBBytes;
   const uint32_t a_slot_bytes = WHOLE ? (uint32_t)pa * kABytes : 0u;
-  // carve: [A slots] | [stages] | stash[NEW warps][4 KB] | side[2][256] | barriers | tmem ptr   (1024 B aligned)
-  constexpr uint32_t kStashBytes = NEW * 4096;  // winning-chunk stash: [warp][8 float4][32 lanes]
+  // carve: [A slots] | [stages] | stash[8 warps][4 KB] | side[2][256] | barriers | tmem ptr   (1024 B aligned)
   uint8_t* smem_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem = smem_a + 2 * (size_t)a_slot_bytes;
   uint8_t* stash_smem = smem + (size_t)nstages * stage_bytes;
@@ -407,7 +418,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 8);  // the 8 warps of the group that drains this accumulator
+      mbar_init(tmem_empty + i, kEpilogueWarps);
       mbar_init(a_full + i, 1);
       mbar_init(a_empty + i, 1);
     }
@@ -478,8 +489,6 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-converged, one elected lane issues) =====================
     {
-      // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N=256, M=128
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
@@ -514,8 +523,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint64_t adesc = make_smem_desc<BK>(sa + (uint32_t)terms.a[term] * kABytes);
                 const uint64_t bdesc = make_smem_desc<BK>(sb + (uint32_t)terms.b[term] * kBBytes);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                  umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (term | k) != 0);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  if (k == 0 && terms.scale[term]) umma_f16_scaled(d_tmem, adesc, bdesc, idesc);
+                  else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (term | k) != 0);
+                }
               }
             }
             umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
@@ -527,20 +538,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         } else {
           const int nv = terms.n * kblocks;
+          int term = 0, kb = 0;
 #pragma unroll 1
           for (int v = 0; v < nv; ++v) {
+            const bool rescale = kb == 0 && terms.scale[term] != 0;  // first MMA of a term that follows the 2^11-scaled ones
             mbar_wait(full_bar + stage, phase);
             tc_fence_after();
             const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
             if (elect_one()) {
               const uint64_t adesc = make_smem_desc<BK>(sa), bdesc = make_smem_desc<BK>(sa + kABytes);
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (v | k) != 0);
+              for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+                if (k == 0 && rescale) umma_f16_scaled(d_tmem, adesc, bdesc, idesc);
+                else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (v | k) != 0);
+              }
               umma_commit(empty_bar + stage);
               if (v == nv - 1) umma_commit(tmem_full + buf);  // accumulator complete -> epilogue
             }
             __syncwarp();
+            if (++kb == kblocks) { kb = 0; ++term; }
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
@@ -550,8 +566,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================== epilogue: fused arg-max =====================
 #define VQB_EPI(SIDE_)                                                                                              \
-  epilogue_loop<SIDE_, NEW>(warp, lane, tmem_base, stash_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,  \
-                            (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys)
+  epilogue_loop<SIDE_>(warp, lane, tmem_base, stash_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,       \
+                       (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys)
     if (b_half_sqnorm == nullptr || side_mode == 0) VQB_EPI(0);
     else if (side_mode == 1) VQB_EPI(1);
     else VQB_EPI(2);
@@ -608,32 +624,49 @@ static int make_operand_map(CUtensorMap* map, const void* base, int64_t total_ro
   return VQB_OK;
 }
 
-// plane-pair terms kept: i + j <= max(pa, pb) - 1 (every dropped term is below 2^-24 relative for 3 planes);
-// smallest terms first so that they are not absorbed by the large ones.
+// plane-pair terms kept for bf16 planes: i + j <= max(pa, pb) - 1 (every dropped term is below 2^-24 relative
+// for 3 planes); smallest terms first so that they are not absorbed by the large ones.
+// fp16 pairs (hi, lo' = lo * 2^11): the lo' terms go first, then the accumulator is scaled by 2^-11 in the
+// same instruction that adds the first hi term (lo'.lo' would be 2^-22 relative: dropped).
 static TermTable make_terms(int pa, int pb) {
   TermTable t{};
+  auto push = [&](int i, int j, int scale) {
+    if (t.n < kMaxTerms) {
+      t.a[t.n] = i;
+      t.b[t.n] = j;
+      t.scale[t.n] = scale;
+      ++t.n;
+    }
+  };
+  if (is_f16(pa)) {                    // fp16 family (both operands: checked by vqb_assign)
+    if (is_f16x2(pa)) push(1, 0, 0);   // a_lo' . b_hi
+    if (is_f16x2(pb)) push(0, 1, 0);   // a_hi  . b_lo'
+    push(0, 0, t.n > 0 ? 1 : 0);       // D = D * 2^-11 + a_hi . b_hi
+    return t;
+  }
   const int order = (pa > pb ? pa : pb) - 1;
   for (int s = order; s >= 0; --s)
     for (int i = 0; i < pa; ++i) {
       const int j = s - i;
       if (j < 0 || j >= pb) continue;
-      if (t.n < kMaxTerms) {
-        t.a[t.n] = i;
-        t.b[t.n] = j;
-        ++t.n;
-      }
+      push(i, j, 0);
     }
   return t;
 }
 
-template <int BK, bool WHOLE, int NEW>
+template <int BK, bool WHOLE>
 static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, const void* b_planes, int pb,
                   int64_t b_rows, int64_t b_pad, int Dp, const float* h, int side_mode, int64_t off,
                   unsigned long long* keys, cudaStream_t st) {
-  CUtensorMap ma, mb;
+  const TermTable terms = make_terms(pa, pb);
+  // kind::f16 instruction descriptor: D = f32, A / B = bf16 (1) or f16 (0), K-major both, N = 256, M = 128
+  const uint32_t idesc = (1u << 4) | ((is_f16(pa) ? 0u : 1u) << 7) | ((is_f16(pb) ? 0u : 1u) << 10) |
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  pa = plane_count(pa);
+  pb = plane_count(pb);
+  CUtensorMap ma, mb;  // TMA moves 16-bit elements: the bf16 data type also carries the fp16 planes
   if (int e = make_operand_map(&ma, a_planes, pa * a_pad, Dp, BK, BM)) return e;
   if (int e = make_operand_map(&mb, b_planes, pb * b_pad, Dp, BK, BN)) return e;
-  constexpr uint32_t kStashBytes = NEW * 4096;
   const uint32_t stage_bytes = WHOLE ? (uint32_t)(pb * BN) * BK * 2 : (uint32_t)(BM + BN) * BK * 2;
   const uint32_t a_resident = WHOLE ? 2u * (uint32_t)pa * BM * BK * 2 : 0u;
   int nstages = (int)((196608 - kStashBytes - a_resident) / stage_bytes);
@@ -642,14 +675,13 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
                             (2 * nstages + 8) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    VQB_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<BK, WHOLE, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    VQB_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<BK, WHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  const TermTable terms = make_terms(pa, pb);
   const int64_t total = ((a_rows + BM - 1) / BM) * ((b_rows + BN - 1) / BN);
   int grid = sm_count();
   if (total < grid) grid = (int)total;
-  assign_tc_kernel<BK, WHOLE, NEW><<<grid, 64 + NEW * 32, smem_bytes, st>>>(ma, mb, terms, pa, pb, Dp / BK, nstages, a_rows, a_pad,
+  assign_tc_kernel<BK, WHOLE><<<grid, kThreads, smem_bytes, st>>>(ma, mb, terms, idesc, pa, pb, Dp / BK, nstages, a_rows, a_pad,
                                                                   b_rows, b_pad, h, side_mode, off, keys);
   VQB_LAUNCH_OK();
   return VQB_OK;
@@ -659,25 +691,11 @@ int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad
                      int64_t b_rows, int64_t b_pad, int D, const float* h, int side_mode, int64_t off,
                      unsigned long long* keys, cudaStream_t st) {
   const int Dp = (int)vqb_operand_dp(D);
-  // One epilogue group (8 warps) is the default: the two-group variant (16 warps, one group per TMEM
-  // accumulator) measured SLOWER on B200 for D = 32 (0.103 vs 0.092 ms at cfg 2) because 576 threads cap the
-  // kernel at 96 registers (spills) and the second 32 KB stash costs a pipeline stage; it only wins for
-  // D = 8.  VQB_EPILOGUE_WARPS=16 keeps it reachable for experiments.
-  static int new_override = -1;
-  if (new_override < 0) {
-    const char* e = getenv("VQB_EPILOGUE_WARPS");
-    new_override = e ? atoi(e) : 0;
-  }
-  const int nwarps = new_override == 16 ? 16 : 8;
-  const size_t stash = (size_t)nwarps * 4096;
-  // whole-tile stages need at least a double buffer of all planes of one work item in shared memory
   // resident-A mode: two A slots plus at least two whole-B-tile stages must fit in shared memory
-  const bool whole = Dp <= 64 && (size_t)(2 * pa * BM + 2 * pb * BN) * Dp * 2 <= 196608 - stash;
-#define VQB_LAUNCH(BK_, W_)                                                                                         \
-  do {                                                                                                              \
-    if (nwarps == 16) return launch<BK_, W_, 16>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, side_mode, off, keys, st); \
-    return launch<BK_, W_, 8>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, side_mode, off, keys, st);                   \
-  } while (0)
+  const bool whole =
+      Dp <= 64 && (size_t)(2 * plane_count(pa) * BM + 2 * plane_count(pb) * BN) * Dp * 2 <= 196608 - kStashBytes;
+#define VQB_LAUNCH(BK_, W_) \
+  return launch<BK_, W_>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, side_mode, off, keys, st)
   if (Dp == 16) { if (whole) VQB_LAUNCH(16, true); VQB_LAUNCH(16, false); }
   if (Dp == 32) { if (whole) VQB_LAUNCH(32, true); VQB_LAUNCH(32, false); }
   if (whole) VQB_LAUNCH(64, true);

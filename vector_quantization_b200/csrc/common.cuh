@@ -1,6 +1,7 @@
 // Shared helpers for the vqb200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -31,6 +32,15 @@ void set_error(const char* fmt, ...);
 #define VQB_LAUNCH_OK() VQB_CUDA_OK(cudaGetLastError())
 
 constexpr float kNormEps = 1e-12f;  // F.normalize default eps
+
+// plane formats (include/vqb200.h): 1..3 bf16 planes, one fp16 plane, or the fp16 (hi, lo * 2^11) pair
+constexpr int kPairShift = 11;       // lo' = (v - hi) * 2^11; vqb_assign folds 2^-11 back with scale-input-d
+__host__ __device__ inline bool is_f16(int planes) { return (planes & 0x10) != 0; }       // fp16 family
+__host__ __device__ inline bool is_f16x2(int planes) { return planes == VQB_PLANES_F16X2; }
+__host__ __device__ inline int plane_count(int planes) { return VQB_PLANE_COUNT(planes); }
+__host__ __device__ inline bool planes_valid(int planes) {
+  return (planes >= 1 && planes <= 3) || planes == VQB_PLANES_F16 || planes == VQB_PLANES_F16X2;
+}
 
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
@@ -89,6 +99,20 @@ __device__ __forceinline__ float group_sum(float v) {  // sum over aligned group
 #pragma unroll
   for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+template <int W>
+__device__ __forceinline__ float group_max(float v) {  // max over aligned groups of W lanes
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// One-plane fp16 rows keep |v| < 2^15: a row whose largest component is >= 2^15 is scaled by an exact power of two
+// (the row arg-max of <row, b_j> does not change; such rows do not occur in latent spaces)
+__device__ __forceinline__ float f16_row_scale(float row_absmax) {
+  int e;
+  frexpf(row_absmax, &e);  // row_absmax = m * 2^e, 0.5 <= m < 1
+  return (e > 15 && row_absmax < INFINITY) ? ldexpf(1.f, 15 - e) : 1.f;
 }
 
 inline int sm_count() {

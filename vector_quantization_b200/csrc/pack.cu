@@ -37,14 +37,16 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
   for (int64_t r = blockIdx.x * rows_per_block + threadIdx.x / G; r < rows_pad;
        r += (int64_t)gridDim.x * rows_per_block) {
     const bool real = r < rows;
-    float ss = 0.f;
+    float ss = 0.f, amax = 0.f;
     if (real)
       for (int d = lane; d < D; d += G) {
         float v = to_f32<T>(src[r * D + d]);
         ss = fmaf(v, v, ss);
+        amax = fmaxf(amax, fabsf(v));
       }
     ss = group_sum<G>(ss);
     const float denom = normalize ? fmaxf(sqrtf(ss), kNormEps) : 1.f;
+    const float f16_scale = planes == VQB_PLANES_F16 ? f16_row_scale(group_max<G>(amax)) : 1.f;
     float ss2 = 0.f;
     for (int d = lane; d < Dp; d += G) {
       float v = 0.f;
@@ -54,14 +56,24 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
         if (writeback) writeback[r * D + d] = v;
       }
       ss2 = fmaf(v, v, ss2);
-      // exact 3-way split: v == hi + mid + lo
-      float rem = v;
+      if (planes == VQB_PLANES_F16) {
+        dst[r * Dp + d] = __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(v * f16_scale)));
+      } else if (is_f16x2(planes)) {
+        // fp16 pair: hi = fp16(v), lo' = fp16((v - hi) * 2^11); the subtraction is exact
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn((v - __half2float(hi)) * (float)(1 << kPairShift));
+        dst[r * Dp + d] = __ushort_as_bfloat16(__half_as_ushort(hi));
+        dst[(rows_pad + r) * Dp + d] = __ushort_as_bfloat16(__half_as_ushort(lo));
+      } else {
+        // exact 3-way split: v == hi + mid + lo
+        float rem = v;
 #pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        if (p < planes) {
-          __nv_bfloat16 h = __float2bfloat16_rn(rem);
-          dst[((int64_t)p * rows_pad + r) * Dp + d] = h;
-          rem = rem - __bfloat162float(h);
+        for (int p = 0; p < 3; ++p) {
+          if (p < planes) {
+            __nv_bfloat16 h = __float2bfloat16_rn(rem);
+            dst[((int64_t)p * rows_pad + r) * Dp + d] = h;
+            rem = rem - __bfloat162float(h);
+          }
         }
       }
     }
@@ -116,6 +128,15 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
     }
     ss = group_sum<G>(ss);
     const float denom = normalize ? fmaxf(sqrtf(ss), kNormEps) : 1.f;
+    float f16_scale = 1.f;
+    if (planes == VQB_PLANES_F16) {
+      float amax = 0.f;
+#pragma unroll
+      for (int it = 0; it < NV; ++it)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[it][i]));
+      f16_scale = f16_row_scale(group_max<G>(amax));
+    }
     float ss2 = 0.f;
 #pragma unroll
     for (int it = 0; it < NV; ++it) {
@@ -134,6 +155,29 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
         float rem[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rem[i] = v[it][i];
+        if (planes == VQB_PLANES_F16) {
+          uint4 raw;
+          __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(rem[2 * i] * f16_scale, rem[2 * i + 1] * f16_scale);
+          *reinterpret_cast<uint4*>(dst + r * Dp + d0) = raw;
+          continue;
+        }
+        if (is_f16x2(planes)) {
+          uint4 raw_hi, raw_lo;
+          __half2* hh = reinterpret_cast<__half2*>(&raw_hi);
+          __half2* hl = reinterpret_cast<__half2*>(&raw_lo);
+          constexpr float kUp = (float)(1 << kPairShift);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hh[i] = __floats2half2_rn(rem[2 * i], rem[2 * i + 1]);
+            const float2 back = __half22float2(hh[i]);
+            hl[i] = __floats2half2_rn((rem[2 * i] - back.x) * kUp, (rem[2 * i + 1] - back.y) * kUp);
+          }
+          *reinterpret_cast<uint4*>(dst + r * Dp + d0) = raw_hi;
+          *reinterpret_cast<uint4*>(dst + (rows_pad + r) * Dp + d0) = raw_lo;
+          continue;
+        }
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
           if (p < planes) {
@@ -275,7 +319,7 @@ int64_t vqb_operand_dp(int D) {
 }
 int64_t vqb_operand_rows_pad(int64_t rows) { return round_up(rows < 1 ? 1 : rows, 256); }
 size_t vqb_operand_bytes(int64_t rows, int D, int planes) {
-  return (size_t)planes * (size_t)vqb_operand_rows_pad(rows) * (size_t)vqb_operand_dp(D) * 2;
+  return (size_t)plane_count(planes) * (size_t)vqb_operand_rows_pad(rows) * (size_t)vqb_operand_dp(D) * 2;
 }
 
 int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes,
@@ -283,7 +327,10 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
                   int64_t n_keys, void* stream) {
   VQB_REQUIRE(src && dst_planes, "vqb_pack_rows: null pointer");
   VQB_REQUIRE(rows >= 0 && D >= 1 && D <= 8192, "vqb_pack_rows: bad shape rows=%lld D=%d", (long long)rows, D);
-  VQB_REQUIRE(planes >= 1 && planes <= 3, "vqb_pack_rows: planes must be 1..3 (got %d)", planes);
+  VQB_REQUIRE(planes_valid(planes), "vqb_pack_rows: planes must be 1..3, VQB_PLANES_F16 or VQB_PLANES_F16X2 (got %d)", planes);
+  VQB_REQUIRE(!is_f16x2(planes) || normalize, "vqb_pack_rows: VQB_PLANES_F16X2 needs normalize = 1 (|v| <= 1)");
+  VQB_REQUIRE(planes != VQB_PLANES_F16 || (!normalize && src_dtype == VQB_BF16),
+              "vqb_pack_rows: VQB_PLANES_F16 takes un-normalised bf16 rows (8 significant bits are exact in fp16)");
   VQB_REQUIRE(src_dtype == VQB_F32 || src_dtype == VQB_BF16, "vqb_pack_rows: bad dtype %d", src_dtype);
   const int64_t rows_pad = vqb_operand_rows_pad(rows);
   const int Dp = (int)vqb_operand_dp(D);

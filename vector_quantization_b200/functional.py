@@ -14,7 +14,13 @@ import torch
 
 from . import ops
 
-PRECISION_PLANES = {'exact': 3, 'high': 2, 'fast': 1}
+# How an fp32 operand is fed to the bf16/fp16 tensor cores:
+#   'fp32'  (default) representation error below fp32 rounding noise: the fp16 (hi, lo * 2^11) pair (22 bits, two
+#           MMA terms) for a normalised codebook against one-plane bf16 tokens, three exact bf16 planes otherwise
+#   'exact' always three bf16 planes (v == hi + mid + lo bit for bit; every kept product is exact)
+#   'high'  two bf16 planes (16 bits), 'fast' one bf16 plane (8 bits)
+PRECISION_PLANES = {'fp32': 3, 'exact': 3, 'high': 2, 'fast': 1}
+DEFAULT_PRECISION = 'fp32'
 
 
 class _L2Normalize(torch.autograd.Function):
@@ -41,20 +47,30 @@ def _planes_for(t: torch.Tensor, normalized: bool, precision: str) -> int:
     return PRECISION_PLANES[precision]
 
 
+def _pair_ok(W: torch.Tensor, normalize: bool, precision: str, tokens: torch.Tensor | None) -> bool:
+    """fp16-pair codebook planes: normalised fp32 rows, and the tokens are bf16 (used RAW under the cosine metric,
+    the arg-min does not depend on the token norm; their 8 significant bits are exact in one fp16 plane)."""
+    return (precision == 'fp32' and normalize and W.dtype == torch.float32 and tokens is not None
+            and tokens.dtype == torch.bfloat16)
+
+
 @torch.no_grad()
-def pack_codebook(W: torch.Tensor, metric: str, *, precision: str = 'exact', writeback_normalized: bool = False,
-                  reset_keys: torch.Tensor | None = None) -> ops.Operand:
+def pack_codebook(W: torch.Tensor, metric: str, *, precision: str = DEFAULT_PRECISION,
+                  writeback_normalized: bool = False, reset_keys: torch.Tensor | None = None,
+                  tokens: torch.Tensor | None = None) -> ops.Operand:
     """Codebook operand: cosine -> planes of F.normalize(W) (optionally written back to W in place, which is
-    NormalizeCallback's `weight.data = normalize(weight)`, normalize.py:26-28); L2 -> planes of W and 0.5|e|^2."""
+    NormalizeCallback's `weight.data = normalize(weight)`, normalize.py:26-28); L2 -> planes of W and 0.5|e|^2.
+    `tokens`: the token tensor this codebook will be matched against (selects the plane format)."""
     cos = metric == 'Cosine'
     normalize = cos or writeback_normalized
-    return ops.pack_rows(W, normalize=normalize, planes=_planes_for(W, normalize, precision),
+    pair = cos and _pair_ok(W, normalize, precision, tokens)
+    return ops.pack_rows(W, normalize=normalize, planes=None if pair else _planes_for(W, normalize, precision),
                          want_half_sqnorm=not cos, writeback=W if writeback_normalized else None,
-                         reset_keys=reset_keys)
+                         reset_keys=reset_keys, fmt='f16x2' if pair else 'bf16')
 
 
 @torch.no_grad()
-def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precision: str = 'exact',
+def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precision: str = DEFAULT_PRECISION,
                  keys: torch.Tensor | None = None, index_offset: int = 0, normalize_tokens: bool = False,
                  tokens: ops.Operand | None = None, keys_are_reset: bool = False) -> torch.Tensor:
     """Packed (score,index) keys [N] of the nearest code of every token (row arg-min of the distance).
@@ -66,25 +82,38 @@ def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precisi
         keys = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
         keys_are_reset = False
     if tokens is None:
-        norm = normalize_tokens and not cos
-        tokens = None if norm else ops.as_operand(x)
-        if tokens is None:
-            tokens = ops.pack_rows(x, normalize=norm, planes=_planes_for(x, norm, precision),
-                                   reset_keys=None if keys_are_reset else keys)
+        if codebook.fmt != 'bf16':
+            # fp16-pair codebook (cosine, bf16 tokens): the raw tokens as one fp16 plane (no bf16/fp16 mixing on
+            # the tensor core); two MMA terms instead of the three of an exact bf16-plane codebook
+            if not (cos and x.dtype == torch.bfloat16):
+                raise ValueError('a fp16-pair codebook needs bf16 tokens and the cosine metric: '
+                                 'pack the codebook with pack_codebook(..., tokens=x)')
+            tokens = ops.pack_rows(x, fmt='f16', reset_keys=None if keys_are_reset else keys)
             keys_are_reset = True
+        else:
+            norm = normalize_tokens and not cos
+            tokens = None if norm else ops.as_operand(x)
+            if tokens is None:
+                tokens = ops.pack_rows(x, normalize=norm, planes=_planes_for(x, norm, precision),
+                                       reset_keys=None if keys_are_reset else keys)
+                keys_are_reset = True
     if not keys_are_reset:
         keys.fill_(-1)
     return ops.assign(tokens, codebook, keys, l2=not cos, index_offset=index_offset)
 
 
 @torch.no_grad()
-def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precision: str = 'exact',
+def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precision: str = DEFAULT_PRECISION,
                    index_offset: int = 0) -> torch.Tensor:
     """Packed keys [K]: for every code, the nearest token (column arg-min) — the same kernel with the
     operands swapped.  Cosine needs normalised token planes here (the token norm now varies along the
     reduced axis); L2 needs the tokens' 0.5|x|^2."""
     cos = metric == 'Cosine'
     keys = ops.new_keys(codebook.rows, x.device)
+    if codebook.fmt != 'bf16':
+        # fp16 codebook planes need fp16 token planes: the normalised tokens as a pair (three MMA terms)
+        toks = ops.pack_rows(x, normalize=True, fmt='f16x2')
+        return ops.assign(codebook, toks, keys, l2=False, index_offset=index_offset)
     if cos:
         raw = ops.as_operand(x)
         if raw is not None:
@@ -110,6 +139,7 @@ class _QuantizeSTELoss(torch.autograd.Function):
             quant = index
         ctx.save_for_backward(x, W, quant)
         ctx.cfg = (normalize_x, want_norm)
+        ctx.set_materialize_grads(False)   # unused outputs arrive as None instead of freshly zero-filled tensors
         if xn is None:
             xn = x.detach()
         ctx.mark_non_differentiable(quant, xn)
@@ -146,12 +176,15 @@ class _FSQ(torch.autograd.Function):
         zq, idx = ops.fsq_forward(x, params)
         ctx.save_for_backward(x)
         ctx.params = params
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(idx)
         return zq, idx
 
     @staticmethod
     def backward(ctx, gz, _gidx):
         (x,) = ctx.saved_tensors
+        if gz is None:
+            return None, None
         return ops.fsq_backward(gz.contiguous(), x, ctx.params), None
 
 

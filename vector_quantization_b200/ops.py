@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, VQB_BF16, VQB_F32, FSQParams, check
+from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, PLANES_F16, PLANES_F16X2, VQB_BF16, VQB_F32, FSQParams, check
 
 __all__ = [
     'Operand', 'as_operand', 'pack_rows', 'assign', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
@@ -77,6 +77,15 @@ class Operand:
     half_sqnorm: torch.Tensor | None = None
     plane_rows: int = 0  # row stride between planes; 0 = padded default, rows = zero-copy view of a bf16 tensor
     inv_norm: torch.Tensor | None = None  # fp32 [rows_pad] 1/|row| (per-column scale for raw-token column arg-min)
+    fmt: str = 'bf16'    # 'bf16': 1..3 bf16 planes | 'f16': one fp16 plane | 'f16x2': the fp16 (hi, lo * 2^11) pair
+
+    @property
+    def pair(self) -> bool:
+        return self.fmt == 'f16x2'
+
+    @property
+    def abi_planes(self) -> int:
+        return {'bf16': self.nplanes, 'f16': PLANES_F16, 'f16x2': PLANES_F16X2}[self.fmt]
 
 
 def operand_shape(rows: int, D: int) -> tuple[int, int]:
@@ -86,23 +95,38 @@ def operand_shape(rows: int, D: int) -> tuple[int, int]:
 
 def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None = None,
               want_half_sqnorm: bool = False, writeback: torch.Tensor | None = None,
-              reset_keys: torch.Tensor | None = None) -> Operand:
-    """fp32/bf16 rows -> exact bf16 planes (see vqb_pack_rows).  `planes=None` picks the exact
-    representation: 1 plane for un-normalised bf16 input, 3 planes otherwise."""
+              reset_keys: torch.Tensor | None = None, fmt: str = 'bf16') -> Operand:
+    """fp32/bf16 rows -> operand planes (see vqb_pack_rows).
+    fmt='bf16': exact bf16 planes; `planes=None` picks the exact representation (1 plane for un-normalised bf16
+                input, 3 planes otherwise).
+    fmt='f16x2': the two-plane fp16 (hi, lo * 2^11) pair of NORMALISED rows: 22 significant bits, two MMA terms.
+    fmt='f16':  one fp16 plane of un-normalised bf16 rows (the partner of an 'f16x2' operand)."""
     lib = _lib.load()
     _cuda(src, writeback, reset_keys)
     assert src.dim() == 2
     rows, D = src.shape
-    if planes is None:
-        planes = 1 if (src.dtype == torch.bfloat16 and not normalize) else 3
+    if fmt == 'f16x2':
+        if not normalize:
+            raise ValueError("the fp16-pair plane format needs normalised rows (|v| <= 1)")
+        planes, code = 2, PLANES_F16X2
+    elif fmt == 'f16':
+        if normalize or src.dtype != torch.bfloat16:
+            raise ValueError("the one-plane fp16 format takes un-normalised bf16 rows")
+        planes, code = 1, PLANES_F16
+    elif fmt == 'bf16':
+        if planes is None:
+            planes = 1 if (src.dtype == torch.bfloat16 and not normalize) else 3
+        code = planes
+    else:
+        raise ValueError(f'unknown plane format {fmt!r}')
     rows_pad, Dp = operand_shape(rows, D)
-    dst = torch.empty((planes, rows_pad, Dp), dtype=torch.bfloat16, device=src.device)
+    dst = torch.empty((planes, rows_pad, Dp), dtype=torch.bfloat16, device=src.device)   # 16-bit storage
     h = torch.empty((rows_pad,), dtype=torch.float32, device=src.device) if want_half_sqnorm else None
     if writeback is not None:
         assert writeback.dtype == torch.float32 and writeback.shape == src.shape
-    _call('vqb_pack_rows', lib.vqb_pack_rows, _p(src), _dt(src), rows, D, int(normalize), planes, _p(dst), _p(h), _p(writeback),
-                            _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _stream())
-    return Operand(dst, rows, D, planes, h)
+    _call('vqb_pack_rows', lib.vqb_pack_rows, _p(src), _dt(src), rows, D, int(normalize), code, _p(dst), _p(h),
+          _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _stream())
+    return Operand(dst, rows, D, planes, h, fmt=fmt)
 
 
 def new_keys(n: int, device) -> torch.Tensor:
@@ -124,7 +148,7 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
     elif scale_columns:
         assert b.inv_norm is not None
         side, mode = b.inv_norm, 2
-    _call('vqb_assign', lib.vqb_assign, _p(a.planes), a.nplanes, a.rows, a.plane_rows, _p(b.planes), b.nplanes, b.rows,
+    _call('vqb_assign', lib.vqb_assign, _p(a.planes), a.abi_planes, a.rows, a.plane_rows, _p(b.planes), b.abi_planes, b.rows,
           b.plane_rows, a.dim, _p(side), mode, index_offset, _p(keys), backend, _stream())
     return keys
 

@@ -91,7 +91,7 @@ def unpack_keys_host(keys: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
 
 # ---- codebook-sharded assignment (new functionality; BASELINE.json configs[4]) -------------
 def sharded_nearest_code(x: torch.Tensor, W_shard: torch.Tensor, metric: str, *, shard_lo: int | None = None,
-                         total_codes: int | None = None, precision: str = 'exact'):
+                         total_codes: int | None = None, precision: str = 'fp32'):
     """Tokens replicated, codebook rows split in contiguous blocks over the ranks.  Every rank runs the fused
     tcgen05 arg-min against ITS rows with `b_index_offset = shard_lo` (keys carry GLOBAL code indices), then ONE
     packed (distance, index) min-loc all-reduce over [N] picks the global nearest code — lowest global index on
@@ -102,7 +102,7 @@ def sharded_nearest_code(x: torch.Tensor, W_shard: torch.Tensor, metric: str, *,
         assert total_codes is not None
         shard_lo = shard_range(total_codes)[0]
     keys = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
-    book = Fq.pack_codebook(W_shard, metric, precision=precision, reset_keys=keys)
+    book = Fq.pack_codebook(W_shard, metric, precision=precision, reset_keys=keys, tokens=x)
     Fq.nearest_code(x, book, metric, precision=precision, keys=keys, keys_are_reset=True, index_offset=shard_lo)
     all_reduce_min_keys_(keys)
     return ops.unpack_keys(keys), keys

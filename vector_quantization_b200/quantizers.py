@@ -122,7 +122,7 @@ class VectorQuantizer(BaseQuantizer):
     """distance -> arg-min -> (codebook update callbacks) -> gather -> losses -> straight-through, as three
     kernel launches: pack+assign (tcgen05, no N x K matrix), [stats/update], fused gather+STE+loss."""
 
-    def __init__(self, *args, embedding: nn.Embedding, distance: BaseDistance, precision: str = 'exact',
+    def __init__(self, *args, embedding: nn.Embedding, distance: BaseDistance, precision: str = Fq.DEFAULT_PRECISION,
                  **kwargs) -> None:
         super().__init__(*args, **kwargs)
         if precision not in Fq.PRECISION_PLANES:
@@ -179,7 +179,7 @@ class VectorQuantizer(BaseQuantizer):
         metric = self._distance.metric
         keys = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
         book = Fq.pack_codebook(W, metric, precision=self.precision,
-                                writeback_normalized=memo.pop('_normalize_codebook', False), reset_keys=keys)
+                                writeback_normalized=memo.pop('_normalize_codebook', False), reset_keys=keys, tokens=x)
         normalize_tokens = memo.pop('_normalize_x', False)
         Fq.nearest_code(x, book, metric, precision=self.precision, keys=keys, keys_are_reset=True,
                         normalize_tokens=normalize_tokens)
