@@ -353,7 +353,7 @@ def main():
     x_first = sets[0][0].detach()
     book = Fq.pack_codebook(q.embedding.weight.data, wl['metric'], precision=q.precision, writeback_normalized=True,
                             tokens=x_first)
-    toks = ops.pack_rows(x_first, planes=1)
+    toks = ops.pack_rows(x_first, fmt='f16') if book.pair else ops.pack_rows(x_first, planes=1)
     n_terms = 2 if book.pair else book.nplanes
     keys = ops.new_keys(N, dev)
     ops.PROFILE = []
@@ -443,8 +443,11 @@ def main():
             metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
             dtype='bf16', data='synthetic',
-            config=dict(base_cfg, arithmetic='bf16 tokens and bf16 tensor-core operands, fp32 accumulation; the fp32 '
-                        'codebook enters as 3 exact bf16 planes; z/loss fp32, token gradient bf16',
+            config=dict(base_cfg, arithmetic='16-bit tensor-core operands, fp32 accumulation: ' + (
+                            'bf16 tokens as one exact fp16 plane, the fp32 codebook as the fp16 (hi, lo*2^11) plane '
+                            'pair (22 significant bits, 2 MMA terms)' if book.pair else
+                            f'tokens and the fp32 codebook as exact bf16 planes ({n_terms} MMA terms)') +
+                        '; z/loss fp32, token gradient in the token dtype', precision=q.precision,
                         l2_policy=f'rotating {n_sets} input sets, {n_sets * (N * D * 6) >> 20} MB > L2',
                         launch='CUDA graph replay' if graphs else 'eager', kernels_per_step=launches_per_step),
             clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline,
