@@ -113,6 +113,16 @@ int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, float* out
 /* keys -> int64 indices (and optional fp32 scores); `index_offset` is subtracted. */
 int vqb_unpack_keys(const unsigned long long* keys, int64_t n, int64_t index_offset,
                     int64_t* index_out, float* score_out, void* stream);
+/* Tokenise-only output: keys -> compact token ids for the token dumps of
+ * vq/tasks/image_tokenization/runners/callbacks.py:40-53 and tools/tokenize_llamagen.py:93-103.
+ * out_bytes 2: uint16 (codebooks of at most 65 536 codes), 4: int32. */
+int vqb_compact_tokens(const unsigned long long* keys, int64_t n, int64_t index_offset, void* out, int out_bytes,
+                       void* stream);
+/* Batched transpose of the last two dims, src [batch][rows][cols] -> dst [batch][cols][rows], elem_bytes 2|4|8:
+ * the caller's `b c h w -> (b h w) c` (rows = c, cols = h*w) and `(b h w) c -> b c h w` (rows = h*w, cols = c)
+ * rearranges around the quantizer, vq/tasks/image_tokenization/models/base.py:124,126-127. */
+int vqb_transpose_last2(const void* src, int elem_bytes, int64_t batch, int64_t rows, int64_t cols, void* dst,
+                        void* stream);
 /* Flip bit 63 so signed-int64 MIN (NCCL/gloo ReduceOp.MIN on torch.int64) orders like unsigned. */
 int vqb_keys_flip_sign(unsigned long long* keys, int64_t n, void* stream);
 

@@ -30,6 +30,7 @@ import math
 from dataclasses import dataclass, field
 from typing import Sequence
 
+import einops
 import torch
 import torch.nn.functional as F
 
@@ -353,6 +354,24 @@ class FSQ:
 # --------------------------------------------------------------------------- #
 # usage metrics (vq/tasks/image_tokenization/runners/metrics.py:25-73)
 # --------------------------------------------------------------------------- #
+
+
+def model_quantize(spec: 'QuantizerSpec', x_nchw: torch.Tensor, weight: torch.Tensor, **kwargs):
+    """`BaseModel.quantize` (vq/tasks/image_tokenization/models/base.py:116-129): rearrange
+    'b c h w -> (b h w) c', quantizer forward, rearrange '(b h w) c -> b c h w' + contiguous."""
+    b, c, h, w = x_nchw.shape
+    rows = einops.rearrange(x_nchw, 'b c h w -> (b h w) c')
+    out = quantizer_forward(spec, [rows], weight, **kwargs)
+    z = einops.rearrange(out['z_ste'][0], '(b h w) c -> b c h w', b=b, c=c, h=h, w=w).contiguous()
+    return z, out['loss'][0], dict(out, x_shape=(b, c, h, w))
+
+
+def model_encode_to_quant(kind: str, x_nchw: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """`BaseModel.encode_to_quant` after the encoder (base.py:131-146), without callbacks:
+    tokens [b, h, w] int64."""
+    b, _, h, w = x_nchw.shape
+    quant, _ = encode(kind, einops.rearrange(x_nchw, 'b c h w -> (b h w) c'), weight)
+    return einops.rearrange(quant, '(b h w) -> b h w', b=b, h=h, w=w)
 
 
 def codebook_usage(counts: torch.Tensor) -> float:

@@ -130,3 +130,34 @@ def test_shard_range_covers_everything_once():
         spans = [parallel.shard_range(total, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == total
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_token_dump_formats(tmp_path):
+    """`.pth` Tokens dict of TokenizeCallback (runners/callbacks.py:40-53) and the LlamaGen `.npy` codes of shape
+    (1, 10, -1) (tools/tokenize_llamagen.py:93-103); compact uint16 / int32 ids are widened to int64 on disk."""
+    import numpy as np
+    from vector_quantization_b200 import tokenizer
+    quant = torch.randint(0, 60000, (2 * 4 * 4,)).to(torch.uint16)
+    tokenizer.save_tokens(tmp_path / 't.pth', ['x', 'y'], torch.tensor([1, 2]), quant, (2, 8, 4, 4))
+    d = tokenizer.load_tokens(tmp_path / 't.pth')
+    assert d['tokens'].shape == (2, 4, 4) and d['tokens'].dtype == torch.int64
+    assert torch.equal(d['tokens'].view(-1), quant.to(torch.int32).to(torch.int64)) and int(d['tokens'].max()) > 32767
+    q10 = torch.randint(0, 16384, (10, 16, 16), dtype=torch.int32)
+    tokenizer.save_llamagen_codes(tmp_path / 'c.npy', tmp_path / 'l.npy', q10, torch.tensor([7]))
+    codes, labels = np.load(tmp_path / 'c.npy'), np.load(tmp_path / 'l.npy')
+    assert codes.shape == (1, 10, 256) and codes.dtype == np.int64 and (codes[0] == q10.view(10, -1).numpy()).all()
+    assert labels.tolist() == [7]
+
+
+def test_oracle_caller_restatement_matches_reference_rearranges():
+    """oracle.model_quantize follows BaseModel.quantize: token n = (b, h, w) row-major, channels last."""
+    from oracle import oracle as O
+    b, c, h, w, K = 2, 8, 3, 5, 16
+    rows, E = O.synthetic_latents(b * h * w, K, c, seed=2)
+    x = rows.view(b, h, w, c).permute(0, 3, 1, 2).contiguous()
+    spec = O.QuantizerSpec(distance='L2', losses={'l': dict(type='VQGANLoss')})
+    z, loss, out = O.model_quantize(spec, x, E)
+    ref = O.quantizer_forward(spec, [rows], E)
+    assert torch.equal(out['quant'][0], ref['quant'][0]) and torch.equal(loss, ref['loss'][0])
+    assert torch.equal(z, ref['z_ste'][0].view(b, h, w, c).permute(0, 3, 1, 2)) and z.is_contiguous()
+    assert torch.equal(O.model_encode_to_quant('L2', x, E), ref['quant'][0].view(b, h, w))

@@ -56,6 +56,28 @@ for N, K, D, dt in ((1 << 20, 8192, 32, torch.bfloat16), (1 << 20, 8192, 32, tor
     report(f'pack_rows 3 planes {tag}', ms, N * (D * sx + 3 * ops.operand_shape(1, D)[1] * 2 + 4))
     del x, W, q, gz, stats
 
+# caller-side layout kernels: NCHW <-> token-major transposes, fp16 token plane, compact token ids
+for B, C, HW, dt in ((4096, 32, 256, torch.bfloat16), (4096, 32, 256, torch.float32), (1024, 256, 256, torch.bfloat16),
+                     (16384, 8, 256, torch.float32)):
+    sx = 2 if dt == torch.bfloat16 else 4
+    x = torch.randn(B, C, HW, device=dev).to(dt)
+    ms = timeit(lambda: ops.transpose_last2(x))
+    report(f'transpose nchw->rows B={B} C={C} HW={HW} {"bf16" if sx == 2 else "fp32"}', ms, 2 * x.numel() * sx)
+    rows = ops.transpose_last2(x)
+    ms = timeit(lambda: ops.transpose_last2(rows))
+    report(f'transpose rows->nchw B={B} C={C} HW={HW} {"bf16" if sx == 2 else "fp32"}', ms, 2 * x.numel() * sx)
+    del x, rows
+xb = torch.randn(1 << 20, 32, device=dev).to(torch.bfloat16)
+ms = timeit(lambda: ops.pack_rows(xb, fmt='f16'))
+report('pack_rows one fp16 plane N=1048576 D=32 bf16', ms, xb.numel() * 4)
+Wn = torch.randn(1 << 18, 32, device=dev)
+ms = timeit(lambda: ops.pack_rows(Wn, normalize=True, fmt='f16x2'))
+report('pack_rows fp16 pair N=262144 D=32 fp32', ms, Wn.numel() * (4 + 4))
+keys = torch.randint(0, 8192, (1 << 22,), device=dev)
+ms = timeit(lambda: ops.compact_tokens(keys, 8192))
+report('compact_tokens N=4194304 uint16', ms, keys.numel() * 10)
+del xb, Wn, keys
+
 for levels in ([8, 8, 5, 5, 5], [8, 8, 8, 5, 5, 5]):
     N = 1 << 22
     D = len(levels)

@@ -2,7 +2,7 @@
 registry names / config keys / forward contract of magic-research/vector_quantization
 (`vq/algorithms`).  See DESIGN.md and INTEGRATION.md."""
 from . import _lib, ops  # noqa: F401
-from . import functional, parallel, registry  # noqa: F401
+from . import functional, parallel, registry, tokenizer  # noqa: F401
 from .anchors import *  # noqa: F401,F403
 from .callbacks import *  # noqa: F401,F403
 from .distances import *  # noqa: F401,F403

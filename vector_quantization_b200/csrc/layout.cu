@@ -1,0 +1,88 @@
+// Data formats either side of the quantizer:
+//   * the tokenizer model's `b c h w -> (b h w) c` / `(b h w) c -> b c h w` rearranges
+//     (vq/tasks/image_tokenization/models/base.py:124,126-127) as one tiled, coalesced batched transpose;
+//   * the tokenise-only output: packed assignment keys -> compact token ids (uint16 for K <= 65536, else
+//     int32) for the token dumps (runners/callbacks.py:40-53, tools/tokenize_llamagen.py:93-103).
+// Both are HBM-bound single passes.
+#include "common.cuh"
+
+namespace vqb {
+
+constexpr int kTile = 32;
+
+// src [batch][rows][cols] -> dst [batch][cols][rows]; 32 x 32 tile through padded shared memory, both the
+// global read (along cols) and the global write (along rows) are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(kTile * 8) transpose_last2_kernel(const T* __restrict__ src, int64_t rows,
+                                                                    int64_t cols, T* __restrict__ dst) {
+  __shared__ T tile[kTile][kTile + 1];
+  const int64_t b = blockIdx.z;
+  const T* __restrict__ s = src + b * rows * cols;
+  T* __restrict__ d = dst + b * rows * cols;
+  const int64_t c0 = (int64_t)blockIdx.x * kTile, r0 = (int64_t)blockIdx.y * kTile;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int i = ty; i < kTile; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    if (r < rows && c < cols) tile[i][tx] = s[r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < kTile; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) d[c * rows + r] = tile[tx][i];
+  }
+}
+
+template <typename TO>
+__global__ void compact_tokens_kernel(const unsigned long long* __restrict__ keys, int64_t n, int64_t offset,
+                                      TO* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    out[i] = (TO)(k == kNoKey ? 0 : (int64_t)key_index(k) - offset);
+  }
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" {
+
+int vqb_transpose_last2(const void* src, int elem_bytes, int64_t batch, int64_t rows, int64_t cols, void* dst,
+                        void* stream) {
+  VQB_REQUIRE(src && dst, "vqb_transpose_last2: null pointer");
+  VQB_REQUIRE(src != dst, "vqb_transpose_last2: in-place transpose is not supported");
+  VQB_REQUIRE(elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8, "vqb_transpose_last2: elem_bytes must be 2, 4 or 8");
+  VQB_REQUIRE(batch >= 0 && rows >= 0 && cols >= 0, "vqb_transpose_last2: bad shape");
+  if (batch == 0 || rows == 0 || cols == 0) return VQB_OK;
+  VQB_REQUIRE(batch <= 65535 && (rows + kTile - 1) / kTile <= 65535, "vqb_transpose_last2: grid limit (batch, rows/32 <= 65535)");
+  const dim3 grid((unsigned)((cols + kTile - 1) / kTile), (unsigned)((rows + kTile - 1) / kTile), (unsigned)batch);
+  const dim3 block(kTile, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (elem_bytes == 2)
+    transpose_last2_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)src, rows, cols, (uint16_t*)dst);
+  else if (elem_bytes == 4)
+    transpose_last2_kernel<uint32_t><<<grid, block, 0, st>>>((const uint32_t*)src, rows, cols, (uint32_t*)dst);
+  else
+    transpose_last2_kernel<unsigned long long><<<grid, block, 0, st>>>((const unsigned long long*)src, rows, cols,
+                                                                        (unsigned long long*)dst);
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_compact_tokens(const unsigned long long* keys, int64_t n, int64_t index_offset, void* out, int out_bytes,
+                       void* stream) {
+  VQB_REQUIRE(keys && out, "vqb_compact_tokens: null pointer");
+  VQB_REQUIRE(out_bytes == 2 || out_bytes == 4, "vqb_compact_tokens: out_bytes must be 2 (uint16) or 4 (int32)");
+  if (n <= 0) return VQB_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_bytes == 2) compact_tokens_kernel<uint16_t><<<blocks, 256, 0, st>>>(keys, n, index_offset, (uint16_t*)out);
+  else compact_tokens_kernel<int32_t><<<blocks, 256, 0, st>>>(keys, n, index_offset, (int32_t*)out);
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+}  // extern "C"

@@ -125,6 +125,29 @@ def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, preci
     return ops.assign(codebook, toks, keys, l2=not cos, index_offset=index_offset)
 
 
+class _TransposeLast2(torch.autograd.Function):
+    """[B, R, C] -> [B, C, R]; the backward is the same kernel on the gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.transpose_last2(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.transpose_last2(g.contiguous())
+
+
+def nchw_to_rows(x: torch.Tensor) -> torch.Tensor:
+    """einops 'b c h w -> (b h w) c' (vq/tasks/image_tokenization/models/base.py:124) as one transpose kernel."""
+    b, c, h, w = x.shape
+    return _TransposeLast2.apply(x.contiguous().view(b, c, h * w)).view(b * h * w, c)
+
+
+def rows_to_nchw(z: torch.Tensor, b: int, c: int, h: int, w: int) -> torch.Tensor:
+    """einops '(b h w) c -> b c h w' + .contiguous() (base.py:126-127) as one transpose kernel."""
+    return _TransposeLast2.apply(z.contiguous().view(b, h * w, c)).view(b, c, h, w)
+
+
 class _QuantizeSTELoss(torch.autograd.Function):
     """Outputs the four MSE terms as SEPARATE 0-dim tensors so that autograd hands their upstream gradients
     back as four device scalars (no select_backward / stack kernels between the loss and our backward)."""

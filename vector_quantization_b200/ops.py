@@ -19,7 +19,7 @@ __all__ = [
     'Operand', 'as_operand', 'pack_rows', 'assign', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
     'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
-    'fsq_decode', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
+    'fsq_decode', 'transpose_last2', 'compact_tokens', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
 ]
 
 
@@ -127,6 +127,29 @@ def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None 
     _call('vqb_pack_rows', lib.vqb_pack_rows, _p(src), _dt(src), rows, D, int(normalize), code, _p(dst), _p(h),
           _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _stream())
     return Operand(dst, rows, D, planes, h, fmt=fmt)
+
+
+def transpose_last2(src: torch.Tensor) -> torch.Tensor:
+    """[B, R, C] -> [B, C, R] contiguous (vqb_transpose_last2): the caller's NCHW <-> token-major rearranges."""
+    lib = _lib.load()
+    _cuda(src)
+    assert src.dim() == 3 and src.element_size() in (2, 4, 8)
+    B, R, C = src.shape
+    dst = torch.empty((B, C, R), dtype=src.dtype, device=src.device)
+    _call('vqb_transpose_last2', lib.vqb_transpose_last2, _p(src), src.element_size(), B, R, C, _p(dst), _stream())
+    return dst
+
+
+def compact_tokens(keys: torch.Tensor, codebook_size: int, index_offset: int = 0) -> torch.Tensor:
+    """Packed keys -> compact token ids: uint16 for codebooks of at most 65 536 codes, int32 otherwise."""
+    lib = _lib.load()
+    _cuda(keys)
+    assert keys.dtype == torch.int64
+    small = codebook_size <= 65536
+    out = torch.empty(keys.shape, dtype=torch.uint16 if small else torch.int32, device=keys.device)
+    _call('vqb_compact_tokens', lib.vqb_compact_tokens, _p(keys), keys.numel(), index_offset, _p(out), 2 if small else 4,
+          _stream())
+    return out
 
 
 def new_keys(n: int, device) -> torch.Tensor:
