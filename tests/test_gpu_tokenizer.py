@@ -28,7 +28,8 @@ def _golden_quantizer(name, dev):
 
 @pytest.mark.parametrize('shape,dtype', [((3, 32, 16, 16), torch.float32), ((2, 8, 5, 7), torch.bfloat16),
                                          ((1, 256, 16, 16), torch.bfloat16), ((5, 33, 3, 11), torch.float32),
-                                         ((2, 4, 1, 1), torch.int64)])
+                                         ((2, 4, 1, 1), torch.int64), ((2, 8, 16, 16), torch.bfloat16),
+                                         ((3, 6, 4, 4), torch.int64), ((2, 100, 16, 24), torch.float32)])
 def test_transpose_kernel_matches_permute(dev, shape, dtype):
     b, c, h, w = shape
     g = torch.Generator().manual_seed(sum(shape))

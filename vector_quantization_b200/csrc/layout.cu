@@ -34,6 +34,44 @@ __global__ void __launch_bounds__(kTile * 8) transpose_last2_kernel(const T* __r
   }
 }
 
+// Vectorised variant (cols and rows multiples of the 16-byte vector): a TR (rows) x TC (cols) tile is read
+// with 128-bit loads along cols, transposed through shared memory, and written with 128-bit stores along rows.
+template <typename T, int TR, int TC>
+__global__ void __launch_bounds__(256) transpose_last2_vec_kernel(const T* __restrict__ src, int64_t rows, int64_t cols,
+                                                                  T* __restrict__ dst) {
+  constexpr int VE = 16 / sizeof(T);          // elements per 128-bit vector
+  constexpr int PITCH = TC + 4 / sizeof(T) + (sizeof(T) == 8 ? 1 : 0);   // +1 bank word: conflict-free column reads
+  __shared__ T tile[TR][PITCH];
+  const int64_t b = blockIdx.z;
+  const T* __restrict__ s = src + b * rows * cols;
+  T* __restrict__ d = dst + b * rows * cols;
+  const int64_t c0 = (int64_t)blockIdx.x * TC, r0 = (int64_t)blockIdx.y * TR;
+  // load: (TC / VE) vectors per row
+  constexpr int VPR = TC / VE;
+  for (int v = threadIdx.x; v < TR * VPR; v += 256) {
+    const int r = v / VPR, cv = (v % VPR) * VE;
+    if (r0 + r < rows && c0 + cv < cols) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(s + (r0 + r) * cols + c0 + cv);
+      const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int i = 0; i < VE; ++i) tile[r][cv + i] = e[i];
+    }
+  }
+  __syncthreads();
+  // store: output row = source column c, TR contiguous elements along r -> TR / VE vectors per output row
+  constexpr int VPC = TR / VE;
+  for (int v = threadIdx.x; v < TC * VPC; v += 256) {
+    const int c = v % TC, rv = (v / TC) * VE;   // consecutive lanes -> consecutive c: conflict-free shared reads
+    if (c0 + c < cols && r0 + rv < rows) {
+      uint4 raw;
+      T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+      for (int i = 0; i < VE; ++i) e[i] = tile[rv + i][c];
+      *reinterpret_cast<uint4*>(d + (c0 + c) * rows + r0 + rv) = raw;
+    }
+  }
+}
+
 template <typename TO>
 __global__ void compact_tokens_kernel(const unsigned long long* __restrict__ keys, int64_t n, int64_t offset,
                                       TO* __restrict__ out) {
@@ -56,10 +94,32 @@ int vqb_transpose_last2(const void* src, int elem_bytes, int64_t batch, int64_t 
   VQB_REQUIRE(elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8, "vqb_transpose_last2: elem_bytes must be 2, 4 or 8");
   VQB_REQUIRE(batch >= 0 && rows >= 0 && cols >= 0, "vqb_transpose_last2: bad shape");
   if (batch == 0 || rows == 0 || cols == 0) return VQB_OK;
-  VQB_REQUIRE(batch <= 65535 && (rows + kTile - 1) / kTile <= 65535, "vqb_transpose_last2: grid limit (batch, rows/32 <= 65535)");
+  VQB_REQUIRE(batch <= 65535 && (rows + 15) / 16 <= 65535, "vqb_transpose_last2: grid limit (batch, rows/16 <= 65535)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ve = 16 / elem_bytes;
+  if (rows % ve == 0 && cols % ve == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0) {
+    // tile shape follows the matrix: a narrow side (channels = 8 or 16) gets a narrow tile
+#define VQB_TR_CASE(T_, TR_, TC_)                                                                              \
+    do {                                                                                                       \
+      const dim3 vgrid((unsigned)((cols + TC_ - 1) / TC_), (unsigned)((rows + TR_ - 1) / TR_), (unsigned)batch); \
+      transpose_last2_vec_kernel<T_, TR_, TC_><<<vgrid, 256, 0, st>>>((const T_*)src, rows, cols, (T_*)dst);   \
+    } while (0)
+#define VQB_TR_SHAPE(T_)                                      \
+    do {                                                      \
+      if (cols <= 16) VQB_TR_CASE(T_, 128, 16);               \
+      else if (rows <= 16) VQB_TR_CASE(T_, 16, 128);          \
+      else VQB_TR_CASE(T_, 32, 64);                           \
+    } while (0)
+    if (elem_bytes == 2) VQB_TR_SHAPE(uint16_t);
+    else if (elem_bytes == 4) VQB_TR_SHAPE(uint32_t);
+    else VQB_TR_SHAPE(unsigned long long);
+#undef VQB_TR_SHAPE
+#undef VQB_TR_CASE
+    VQB_LAUNCH_OK();
+    return VQB_OK;
+  }
   const dim3 grid((unsigned)((cols + kTile - 1) / kTile), (unsigned)((rows + kTile - 1) / kTile), (unsigned)batch);
   const dim3 block(kTile, 8);
-  cudaStream_t st = (cudaStream_t)stream;
   if (elem_bytes == 2)
     transpose_last2_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)src, rows, cols, (uint16_t*)dst);
   else if (elem_bytes == 4)
