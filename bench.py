@@ -227,6 +227,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS) + ['cfg5'])
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--breakdown', action='store_true',
+                    help='also time CUDA graphs of step prefixes (encode only / + gather+loss / + backward)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -342,6 +344,40 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     value = N * world / (ms * 1e-3)
+
+    breakdown = None
+    if args.breakdown and graphs is not None and world == 1:
+        # in-graph share of each stage: graphs of step PREFIXES over the same rotating input sets
+        def prefix(stage):
+            def fn(i):
+                xi, gzi = sets[i % n_sets]
+                if stage == 0:
+                    with torch.no_grad():
+                        q.encode(xi.detach(), dict(_lazy_unpack=True, _lazy_normalize=True))  # as in forward()
+                    return
+                z, loss, memo = q(xi, dict())
+                if stage == 2:
+                    torch.autograd.grad((z, loss), (xi,), (gzi, one))
+            return fn
+        breakdown = {}
+        for stage, name in enumerate(('encode (packs + assign)', '+ gather/STE/loss', '+ backward')):
+            fn = prefix(stage)
+            gs = []
+            for i in range(n_sets):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    fn(i)
+                gs.append(g)
+            for i in range(10):
+                gs[i % n_sets].replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                gs[i % n_sets].replay()
+            e1.record()
+            torch.cuda.synchronize()
+            breakdown[name] = e0.elapsed_time(e1) / args.steps
+            del gs
 
     # ---- dominant kernel (tcgen05 assignment) timed live with CUDA events on the launching stream ----
     # Same operands as inside the step (raw bf16 tokens: 1 exact plane; normalised fp32 codebook: the fp16
@@ -474,7 +510,7 @@ def main():
                         '; z/loss fp32, token gradient in the token dtype', precision=q.precision,
                         l2_policy=f'rotating {n_sets} input sets, {n_sets * (N * D * 6) >> 20} MB > L2',
                         launch='CUDA graph replay' if graphs else 'eager', kernels_per_step=launches_per_step),
-            clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline,
+            clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline, breakdown_ms=breakdown,
             e2e=dict(value=N * world / (e2e_ms * 1e-3), unit=unit, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h),
             gpu_launches=launches_per_step * args.steps)))

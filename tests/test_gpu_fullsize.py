@@ -122,3 +122,40 @@ def test_cfg5_shape_shard_combine_is_associative(dev):
     idx = ops.unpack_keys(whole)[:256].cpu()
     ref = (F.normalize(x[:256].float()) @ F.normalize(E).to(torch.bfloat16).float().t()).argmax(1).cpu()
     assert (idx == ref).float().mean() > 0.98
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('D', [32, 64, 16])
+def test_gather_and_backward_geometry_independent_of_row_count(dev, dtype, D):
+    """Above ~57k rows the gather / backward kernels switch to half the lanes per row (one wave instead of 1.15):
+    the per-row results must be bit-identical to the small-N geometry (run on two halves), the loss equal to
+    reduction-order rounding."""
+    N, K = 70000, 1024
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(N, D, generator=g).to(dtype).to(dev)
+    W = F.normalize(torch.randn(K, D, generator=g)).to(dev)
+    q = torch.randint(0, K, (N,), generator=g).to(dev)
+    gz = torch.randn(N, D, generator=g).to(dev)
+    g4 = torch.tensor([0.3, 0.7, 1.0, 0.25], device=dev)
+    z, mse4, _, xn = ops.gather_ste_loss(x, W, quant=q, normalize_x=True, want_norm=True, want_xnorm=True)
+    gx, gW = ops.quantize_backward(gz, x, W, q, g4, normalize_x=True, want_norm=True, need_gW=True)
+    h = N // 2
+    zs, xns, gxs, m4 = [], [], [], []
+    gW2 = torch.zeros_like(W)
+    for lo, hi in ((0, h), (h, N)):
+        z_, m_, _, xn_ = ops.gather_ste_loss(x[lo:hi].contiguous(), W, quant=q[lo:hi].contiguous(), normalize_x=True,
+                                             want_norm=True, want_xnorm=True)
+        # the loss scale 2/(N D) of a half is twice the whole's: halve the upstream loss gradients
+        gx_, gW_ = ops.quantize_backward(gz[lo:hi].contiguous(), x[lo:hi].contiguous(), W, q[lo:hi].contiguous(),
+                                         g4 * ((hi - lo) / N), normalize_x=True, want_norm=True, need_gW=True)
+        zs.append(z_); xns.append(xn_); gxs.append(gx_); m4.append(m_ * ((hi - lo) / N)); gW2 += gW_
+    # the row norm is summed over a different lane split: equal to fp32 rounding, not bit for bit
+    torch.testing.assert_close(z, torch.cat(zs), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(xn, torch.cat(xns), rtol=1e-6, atol=1e-7)
+    z_raw = ops.gather_ste_loss(x, W, quant=q, normalize_x=False, want_norm=False)[0]
+    z_raw2 = torch.cat([ops.gather_ste_loss(x[lo:hi].contiguous(), W, quant=q[lo:hi].contiguous(), normalize_x=False,
+                                            want_norm=False)[0] for lo, hi in ((0, h), (h, N))])
+    assert torch.equal(z_raw, z_raw2)                      # no reduction on the value path: bit-exact
+    torch.testing.assert_close(mse4, m4[0] + m4[1], rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(gx.float(), torch.cat(gxs).float(), rtol=1e-5 if dtype == torch.float32 else 1e-2, atol=1e-7)
+    torch.testing.assert_close(gW, gW2, rtol=1e-4, atol=1e-6)

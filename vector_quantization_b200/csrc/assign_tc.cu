@@ -404,6 +404,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* a_empty = a_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 2);
 
+  // PDL: barrier init / TMEM allocation below overlap the tail of the preceding launch (the operand packs);
+  // global memory is first touched after pdl_wait().
+  pdl_launch_dependents();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t a_tiles = (a_rows + BM - 1) / BM, b_tiles = (b_rows + BN - 1) / BN;
   const int64_t total = a_tiles * b_tiles;
@@ -429,6 +432,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (warp-converged, one elected lane issues) =====================
@@ -681,8 +685,8 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
   const int64_t total = ((a_rows + BM - 1) / BM) * ((b_rows + BN - 1) / BN);
   int grid = sm_count();
   if (total < grid) grid = (int)total;
-  assign_tc_kernel<BK, WHOLE><<<grid, kThreads, smem_bytes, st>>>(ma, mb, terms, idesc, pa, pb, Dp / BK, nstages, a_rows, a_pad,
-                                                                  b_rows, b_pad, h, side_mode, off, keys);
+  VQB_CUDA_OK(launch_pdl(assign_tc_kernel<BK, WHOLE>, grid, kThreads, smem_bytes, st, ma, mb, terms, idesc, pa, pb, Dp / BK,
+                         nstages, a_rows, a_pad, b_rows, b_pad, h, side_mode, off, keys));
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

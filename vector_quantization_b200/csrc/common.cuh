@@ -115,6 +115,30 @@ __device__ __forceinline__ float f16_row_scale(float row_absmax) {
   return (e > 15 && row_absmax < INFINITY) ? ldexpf(1.f, 15 - e) : 1.f;
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// The hot step is a chain of short kernels (pack, pack, assign, gather, backward); with PDL the next grid is
+// scheduled while the previous one drains, so the ~2 us launch + ramp of each link overlaps its predecessor.
+// Every PDL-launched kernel calls pdl_wait() before touching global memory (it returns once the preceding
+// grid has completed and its writes are visible; a no-op for a normal launch).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

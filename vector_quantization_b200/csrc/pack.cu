@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
     const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
     __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
     unsigned long long* __restrict__ keys, int64_t n_keys) {
+  pdl_wait();               // the source rows / the key buffer may still be in use by the preceding launch
+  pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_keys; i += (int64_t)gridDim.x * blockDim.x)
     keys[i] = ~0ull;
   const int lane = threadIdx.x % G;
@@ -349,10 +351,10 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
 #define VQB_PACK_CASE(G_, NV_)                                                                                       \
     if (gv == G_ && nv == NV_) {                                                                                     \
       if (src_dtype == VQB_F32)                                                                                      \
-        pack_rows_vec_kernel<float, G_, NV_><<<blocks, 256, 0, st>>>((const float*)src, rows, rows_pad, D, Dp,        \
+        launch_pdl(pack_rows_vec_kernel<float, G_, NV_>, blocks, 256, 0, st, (const float*)src, rows, rows_pad, D, Dp, \
             normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys, keys ? n_keys : 0);        \
       else                                                                                                           \
-        pack_rows_vec_kernel<__nv_bfloat16, G_, NV_><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, rows,         \
+        launch_pdl(pack_rows_vec_kernel<__nv_bfloat16, G_, NV_>, blocks, 256, 0, st, (const __nv_bfloat16*)src, rows, \
             rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys,            \
             keys ? n_keys : 0);                                                                                      \
       VQB_LAUNCH_OK();                                                                                               \

@@ -7,6 +7,7 @@
 // 128-bit loads for bf16, 2 x 128-bit for fp32) and keeps its slice of the row in registers, so every
 // element is read from memory exactly once although the math needs two passes (norms, then outputs).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
     int64_t* __restrict__ quant_out, float* __restrict__ xn_out, float* __restrict__ z_out, int want_norm,
     float* __restrict__ mse4, float* __restrict__ partials, unsigned int* __restrict__ ticket) {
   __shared__ float sh[16];
-  __shared__ bool is_last;
+  pdl_wait();               // keys / codebook come from the preceding launches of the step
+  pdl_launch_dependents();
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
   float sse = 0.f, sse_n = 0.f;
@@ -162,23 +164,26 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
     if (quant_out && valid && lane == 0) quant_out[n] = q;
   }
   block_sum2(sse, sse_n, sh);
+  // Only warp 0 stays for the ticket: the other warps retire without waiting for the fence, and the last
+  // block's warp 0 alone folds the per-block partials (fixed assignment and tree order -> deterministic).
+  if (threadIdx.x >= 32) return;
+  unsigned int t = 0;
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = sse;
     partials[kMaxPartials + blockIdx.x] = sse_n;
     __threadfence();
-    const unsigned int t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+    t = atomicAdd(ticket, 1u);
   }
-  __syncthreads();
-  if (is_last) {  // whole block, fixed assignment and tree order -> run-to-run deterministic
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t == gridDim.x - 1) {
     __threadfence();
     float a = 0.f, b = 0.f;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) {
       a += __ldcg(partials + i);
       b += __ldcg(partials + kMaxPartials + i);
     }
-    __syncthreads();  // sh is reused
-    block_sum2(a, b, sh);
+    a = warp_sum(a);
+    b = warp_sum(b);
     if (threadIdx.x == 0) {
       const float inv = 1.f / ((float)N * (float)D);
       mse4[0] = a * inv;
@@ -196,11 +201,13 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
 //   g_z = c_cb (z - y) + J_n(z)^T [c_cbn (v - u)]                   -> atomically added to gW[q]
 //   g_x_in = J_n(x_in)^T g_y  when normalize_x, else g_y            J_n(a)^T g = (g - (g.n(a)) n(a)) / |a|
 template <typename TX, int G, int V, int NV>
-__global__ void __launch_bounds__(256) quantize_backward_kernel(
+__global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
     const float* __restrict__ gz, const TX* __restrict__ x, int normalize_x, const float* __restrict__ W, int64_t K,
     const int64_t* __restrict__ quant, int64_t N, int D, const float* __restrict__ g_cb,
     const float* __restrict__ g_cm, const float* __restrict__ g_cbn, const float* __restrict__ g_cmn, int want_norm,
     TX* __restrict__ gx, float* __restrict__ gW) {
+  pdl_wait();               // upstream gradients / indices come from the preceding launches
+  pdl_launch_dependents();
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
   const float scale = 2.f / ((float)N * (float)D);
@@ -347,7 +354,7 @@ static inline int grid_for(int64_t rows, int rows_per_block) {
 struct RowGeom {
   int V, G, NV;
 };
-static inline bool row_geom(int D, RowGeom* g) {
+static inline bool row_geom(int D, int64_t N, RowGeom* g) {
   g->V = (D % 8 == 0) ? 8 : 1;
   const int slices = (D + g->V - 1) / g->V;
   g->G = 1;
@@ -355,6 +362,14 @@ static inline bool row_geom(int D, RowGeom* g) {
   int nv = 1;
   while (nv * g->G < slices) nv <<= 1;
   g->NV = nv;
+  // These kernels are one dependent-latency chain per thread: a launch that needs slightly more threads than
+  // the GPU holds at once (cfg 2: 65 536 rows x 4 lanes = 1.15 waves) pays the chain twice.  Halving the lanes
+  // per row (each lane then owns two slices: more loads in flight per thread) brings it back to one wave.
+  const int64_t resident_threads = (int64_t)sm_count() * 1536;
+  if (g->V == 8 && g->NV == 1 && g->G >= 2 && g->G <= 16 && N * g->G > resident_threads) {
+    g->G >>= 1;
+    g->NV = 2;
+  }
   return g->NV <= 8;
 }
 
@@ -373,6 +388,8 @@ using namespace vqb;
   VQB_GEOM_CASE(8, 1, 1, __VA_ARGS__) VQB_GEOM_CASE(8, 2, 1, __VA_ARGS__) VQB_GEOM_CASE(8, 4, 1, __VA_ARGS__)     \
   VQB_GEOM_CASE(8, 8, 1, __VA_ARGS__) VQB_GEOM_CASE(8, 16, 1, __VA_ARGS__) VQB_GEOM_CASE(8, 32, 1, __VA_ARGS__)   \
   VQB_GEOM_CASE(8, 32, 2, __VA_ARGS__) VQB_GEOM_CASE(8, 32, 4, __VA_ARGS__) VQB_GEOM_CASE(8, 32, 8, __VA_ARGS__)  \
+  VQB_GEOM_CASE(8, 1, 2, __VA_ARGS__) VQB_GEOM_CASE(8, 2, 2, __VA_ARGS__) VQB_GEOM_CASE(8, 4, 2, __VA_ARGS__)     \
+  VQB_GEOM_CASE(8, 8, 2, __VA_ARGS__)                                                                             \
   VQB_GEOM_CASE(1, 1, 1, __VA_ARGS__) VQB_GEOM_CASE(1, 2, 1, __VA_ARGS__) VQB_GEOM_CASE(1, 4, 1, __VA_ARGS__)     \
   VQB_GEOM_CASE(1, 8, 1, __VA_ARGS__) VQB_GEOM_CASE(1, 16, 1, __VA_ARGS__) VQB_GEOM_CASE(1, 32, 1, __VA_ARGS__)   \
   VQB_GEOM_CASE(1, 32, 2, __VA_ARGS__) VQB_GEOM_CASE(1, 32, 4, __VA_ARGS__) VQB_GEOM_CASE(1, 32, 8, __VA_ARGS__)
@@ -390,17 +407,17 @@ int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D, int normal
   VQB_REQUIRE(N >= 1 && D >= 1 && K >= 1, "vqb_gather_ste_loss: bad shape N=%lld D=%d K=%lld", (long long)N, D,
               (long long)K);
   RowGeom geom;
-  VQB_REQUIRE(row_geom(D, &geom), "vqb_gather_ste_loss: D=%d unsupported (multiple of 8 up to 2048, or any D <= 256)", D);
+  VQB_REQUIRE(row_geom(D, N, &geom), "vqb_gather_ste_loss: D=%d unsupported (multiple of 8 up to 2048, or any D <= 256)", D);
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = grid_for(N, 256 / geom.G);
   VQB_REQUIRE(blocks <= kMaxPartials, "vqb_gather_ste_loss: grid too large");
   bool launched = false;
   if (x_dtype == VQB_F32) {
-    VQB_DISPATCH_GEOM((quantize_forward_kernel<float, G, V, NV><<<blocks, 256, 0, st>>>(
+    VQB_DISPATCH_GEOM((launch_pdl(quantize_forward_kernel<float, G, V, NV>, blocks, 256, 0, st,
         (const float*)x, N, D, normalize_x, W, K, quant, keys, key_index_offset, quant_out, x_norm_out, z_out,
         want_norm, mse4, partials, ticket)))
   } else if (x_dtype == VQB_BF16) {
-    VQB_DISPATCH_GEOM((quantize_forward_kernel<__nv_bfloat16, G, V, NV><<<blocks, 256, 0, st>>>(
+    VQB_DISPATCH_GEOM((launch_pdl(quantize_forward_kernel<__nv_bfloat16, G, V, NV>, blocks, 256, 0, st,
         (const __nv_bfloat16*)x, N, D, normalize_x, W, K, quant, keys, key_index_offset, quant_out, x_norm_out, z_out,
         want_norm, mse4, partials, ticket)))
   }
@@ -415,15 +432,15 @@ int vqb_quantize_backward(const float* gz, const void* x, int x_dtype, int norma
   VQB_REQUIRE(gz && x && W && quant && gx, "vqb_quantize_backward: null pointer");
   VQB_REQUIRE(N >= 1 && D >= 1 && K >= 1, "vqb_quantize_backward: bad shape");
   RowGeom geom;
-  VQB_REQUIRE(row_geom(D, &geom), "vqb_quantize_backward: D=%d unsupported", D);
+  VQB_REQUIRE(row_geom(D, N, &geom), "vqb_quantize_backward: D=%d unsupported", D);
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = grid_for(N, 256 / geom.G);
   bool launched = false;
   if (x_dtype == VQB_F32) {
-    VQB_DISPATCH_GEOM((quantize_backward_kernel<float, G, V, NV><<<blocks, 256, 0, st>>>(
+    VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<float, G, V, NV>, blocks, 256, 0, st,
         gz, (const float*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm, (float*)gx, gW)))
   } else if (x_dtype == VQB_BF16) {
-    VQB_DISPATCH_GEOM((quantize_backward_kernel<__nv_bfloat16, G, V, NV><<<blocks, 256, 0, st>>>(
+    VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<__nv_bfloat16, G, V, NV>, blocks, 256, 0, st,
         gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm,
         (__nv_bfloat16*)gx, gW)))
   }
