@@ -389,7 +389,7 @@ def main():
     x_first = sets[0][0].detach()
     book = Fq.pack_codebook(q.embedding.weight.data, wl['metric'], precision=q.precision, writeback_normalized=True,
                             tokens=x_first)
-    toks = ops.pack_rows(x_first, fmt='f16') if book.pair else ops.pack_rows(x_first, planes=1)
+    toks = ops.as_operand(x_first) or ops.pack_rows(x_first, fmt='f16' if book.pair else 'bf16', planes=None if book.pair else 1)
     n_terms = 2 if book.pair else book.nplanes
     keys = ops.new_keys(N, dev)
     ops.PROFILE = []
@@ -504,7 +504,7 @@ def main():
             ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
             dtype='bf16', data='synthetic',
             config=dict(base_cfg, arithmetic='16-bit tensor-core operands, fp32 accumulation: ' + (
-                            'bf16 tokens as one exact fp16 plane, the fp32 codebook as the fp16 (hi, lo*2^11) plane '
+                            'bf16 tokens zero-copy (converted to fp16 in shared memory), the fp32 codebook as the fp16 (hi, lo*2^11) plane '
                             'pair (22 significant bits, 2 MMA terms)' if book.pair else
                             f'tokens and the fp32 codebook as exact bf16 planes ({n_terms} MMA terms)') +
                         '; z/loss fp32, token gradient in the token dtype', precision=q.precision,

@@ -168,13 +168,36 @@ def test_assign_fp16_pair_both_operands_column_argmin(dev):
 
 
 def test_assign_rejects_mixed_fp16_bf16_operands(dev):
-    """kind::f16 MMAs take fp16 x fp16 or bf16 x bf16 (a mixed pair is an illegal instruction on B200)."""
+    """kind::f16 MMAs take fp16 x fp16 or bf16 x bf16 (a mixed pair is an illegal instruction on B200).  The one
+    supported mix is a ONE-plane bf16 A operand with D <= 64, converted in shared memory by the kernel."""
     from vector_quantization_b200._lib import VQBError
     x, E = O.synthetic_latents(300, 64, 32)
     book = ops.pack_rows(E.to(dev), normalize=True, fmt='f16x2')
-    for toks in (ops.pack_rows(x.to(dev), planes=3), ops.pack_rows(x.to(torch.bfloat16).to(dev), planes=1)):
-        with pytest.raises(VQBError):
-            ops.assign(toks, book, ops.new_keys(300, dev), l2=False)
+    with pytest.raises(VQBError):
+        ops.assign(ops.pack_rows(x.to(dev), planes=3), book, ops.new_keys(300, dev), l2=False)
+    x2, E2 = O.synthetic_latents(300, 64, 128)
+    with pytest.raises(VQBError):   # D > 64: k-blocked ring, no resident token tile to convert
+        ops.assign(ops.pack_rows(x2.to(torch.bfloat16).to(dev), planes=1),
+                   ops.pack_rows(E2.to(dev), normalize=True, fmt='f16x2'), ops.new_keys(300, dev), l2=False)
+
+
+@pytest.mark.parametrize('backend', [ops.BACKEND_SIMT, ops.BACKEND_TCGEN05], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('N,K,D', [(4096, 2048, 32), (1000, 700, 64), (333, 5000, 16), (65536, 1024, 32)])
+def test_assign_zero_copy_bf16_tokens_against_fp16_pair(dev, backend, N, K, D):
+    """Raw bf16 tokens handed over zero-copy against a fp16-pair codebook: the kernel converts the resident token
+    tile to fp16 in shared memory.  Same keys as with a packed fp16 token plane, and parity with the oracle."""
+    x, E = O.synthetic_latents(N, K, D, seed=3 + D)
+    xb = x.to(torch.bfloat16).to(dev)
+    book = ops.pack_rows(E.to(dev), normalize=True, fmt='f16x2')
+    raw = ops.as_operand(xb)
+    assert raw is not None and raw.fmt == 'bf16' and raw.planes.data_ptr() == xb.data_ptr()
+    k_raw, k_packed = ops.new_keys(N, dev), ops.new_keys(N, dev)
+    ops.assign(raw, book, k_raw, l2=False, backend=backend)
+    ops.assign(ops.pack_rows(xb, fmt='f16'), book, k_packed, l2=False, backend=backend)
+    if backend == ops.BACKEND_TCGEN05:
+        assert torch.equal(k_raw, k_packed)
+    q_ref, d = O.encode('Cosine', xb.float().cpu(), E)
+    _check_indices(d, q_ref, ops.unpack_keys(k_raw).cpu(), what=f'zero-copy bf16 x pair {N}x{K}x{D}')
 
 
 def test_pack_rows_fp16_single_plane(dev):

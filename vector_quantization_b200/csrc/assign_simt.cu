@@ -97,7 +97,9 @@ extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, int64_t 
   VQB_REQUIRE(a_rows >= 1 && b_rows >= 1 && D >= 1, "vqb_assign: bad shape a_rows=%lld b_rows=%lld D=%d",
               (long long)a_rows, (long long)b_rows, D);
   VQB_REQUIRE(planes_valid(pa) && planes_valid(pb), "vqb_assign: planes must be 1..3, VQB_PLANES_F16 or VQB_PLANES_F16X2");
-  VQB_REQUIRE(is_f16(pa) == is_f16(pb),
+  // fp16 and bf16 operands cannot be mixed on the tensor core; the one exception is a ONE-plane bf16 A operand
+  // (zero-copy tokens) against fp16 B planes with D <= 64, converted inside the kernel
+  VQB_REQUIRE(is_f16(pa) == is_f16(pb) || (pa == 1 && is_f16(pb) && vqb_operand_dp(D) <= 64),
               "vqb_assign: the tensor core cannot mix fp16 and bf16 operands (a_nplanes=0x%x b_nplanes=0x%x)", pa, pb);
   VQB_REQUIRE(b_rows + b_index_offset < 0xffffffffll && b_index_offset >= 0,
               "vqb_assign: column index does not fit 32 bits");

@@ -145,6 +145,34 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// In-place bf16 -> fp16 conversion of a TMA-written shared-memory slot by one warp (any swizzle: element-wise),
+// followed by the generic->async proxy fence that makes the result visible to tcgen05.mma.  Saturating: a bf16
+// magnitude above 65504 becomes +-65504 (vqb_pack_rows' VQB_PLANES_F16 rescales such rows instead).
+__device__ __forceinline__ void convert_slot_bf16_to_f16(uint32_t saddr, uint32_t bytes, int lane) {
+  constexpr int U = 4;  // chunks in flight per lane: the slot is a multiple of 32 lanes x 16 B x 4 (128 rows x >= 16 columns)
+  for (uint32_t off = (uint32_t)lane * 16; off < bytes; off += U * 32 * 16) {
+    uint32_t w[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3])
+                   : "r"(saddr + off + u * 512));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float lo = __uint_as_float(w[u][i] << 16), hi = __uint_as_float(w[u][i] & 0xffff0000u);
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[u][i]) : "f"(hi), "f"(lo));
+      }
+      asm volatile("st.shared.v4.b32 [%4], {%0, %1, %2, %3};" ::"r"(w[u][0]), "r"(w[u][1]), "r"(w[u][2]), "r"(w[u][3]),
+                   "r"(saddr + off + u * 512)
+                   : "memory");
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+}
+
 // K-major, hardware-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout).
 template <int BK>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -384,7 +412,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ TermTable terms, uint32_t idesc, int pa, int pb, int kblocks, int nstages,
                  int64_t a_rows,
                  int64_t a_rows_pad, int64_t b_rows, int64_t b_rows_pad, const float* __restrict__ b_half_sqnorm,
-                 int side_mode, int64_t b_index_offset, unsigned long long* __restrict__ keys) {
+                 int side_mode, int64_t b_index_offset, unsigned long long* __restrict__ keys, int a_convert) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
   // WHOLE: a stage holds every B plane of one code tile; the row tile's A planes are RESIDENT in one of two
@@ -510,6 +538,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if constexpr (WHOLE) {
           if (bt_m == 0 || t == t0) {  // first tile of a row tile in this CTA's range: its A planes must have landed
             mbar_wait(a_full + (a_count_m & 1), (uint32_t)((a_count_m >> 1) & 1));
+            // zero-copy bf16 tokens against fp16 codebook planes: convert the resident A tile once per row tile
+            if (a_convert)
+              convert_slot_bf16_to_f16(smem_u32(smem_a) + (uint32_t)(a_count_m & 1) * a_slot_bytes, a_slot_bytes, lane);
             ++a_count_m;
           }
           const int slot = (int)((a_count_m - 1) & 1);
@@ -662,6 +693,16 @@ template <int BK, bool WHOLE>
 static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, const void* b_planes, int pb,
                   int64_t b_rows, int64_t b_pad, int Dp, const float* h, int side_mode, int64_t off,
                   unsigned long long* keys, cudaStream_t st) {
+  // one bf16 plane (e.g. zero-copy tokens) against fp16 planes: the kernel converts the resident A tile in
+  // shared memory (whole-tile mode only)
+  const int a_convert = (pa == 1 && is_f16(pb)) ? 1 : 0;
+  if (a_convert) {
+    if (!WHOLE) {
+      set_error("vqb_assign: bf16 rows against fp16 planes need D <= 64 (in-kernel conversion); pack them with VQB_PLANES_F16");
+      return VQB_ERR_ARG;
+    }
+    pa = VQB_PLANES_F16;
+  }
   const TermTable terms = make_terms(pa, pb);
   // kind::f16 instruction descriptor: D = f32, A / B = bf16 (1) or f16 (0), K-major both, N = 256, M = 128
   const uint32_t idesc = (1u << 4) | ((is_f16(pa) ? 0u : 1u) << 7) | ((is_f16(pb) ? 0u : 1u) << 10) |
@@ -686,7 +727,7 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
   int grid = sm_count();
   if (total < grid) grid = (int)total;
   VQB_CUDA_OK(launch_pdl(assign_tc_kernel<BK, WHOLE>, grid, kThreads, smem_bytes, st, ma, mb, terms, idesc, pa, pb, Dp / BK,
-                         nstages, a_rows, a_pad, b_rows, b_pad, h, side_mode, off, keys));
+                         nstages, a_rows, a_pad, b_rows, b_pad, h, side_mode, off, keys, a_convert));
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

@@ -88,8 +88,12 @@ def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precisi
             if not (cos and x.dtype == torch.bfloat16):
                 raise ValueError('a fp16-pair codebook needs bf16 tokens and the cosine metric: '
                                  'pack the codebook with pack_codebook(..., tokens=x)')
-            tokens = ops.pack_rows(x, fmt='f16', reset_keys=None if keys_are_reset else keys)
-            keys_are_reset = True
+            # D in {16, 32, 64}: zero-copy, the kernel converts the resident token tile to fp16 in shared memory;
+            # otherwise one fp16 plane is packed
+            tokens = ops.as_operand(x) if x.shape[1] <= 64 else None
+            if tokens is None:
+                tokens = ops.pack_rows(x, fmt='f16', reset_keys=None if keys_are_reset else keys)
+                keys_are_reset = True
         else:
             norm = normalize_tokens and not cos
             tokens = None if norm else ops.as_operand(x)
