@@ -389,7 +389,9 @@ def main():
     x_first = sets[0][0].detach()
     book = Fq.pack_codebook(q.embedding.weight.data, wl['metric'], precision=q.precision, writeback_normalized=True,
                             tokens=x_first)
-    toks = ops.as_operand(x_first) or ops.pack_rows(x_first, fmt='f16' if book.pair else 'bf16', planes=None if book.pair else 1)
+    toks = ops.as_operand(x_first) if (D <= 64 or not book.pair) else None      # same choice as Fq.nearest_code
+    if toks is None:
+        toks = ops.pack_rows(x_first, fmt='f16') if book.pair else ops.pack_rows(x_first, planes=1)
     n_terms = 2 if book.pair else book.nplanes
     keys = ops.new_keys(N, dev)
     ops.PROFILE = []

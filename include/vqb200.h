@@ -108,7 +108,9 @@ int vqb_assign(const void* a_planes, int a_nplanes, int64_t a_rows, int64_t a_pl
 
 /* out[r] = 1 / max(||x_r||, 1e-12), zero in the padding up to vqb_operand_rows_pad(rows): the side_mode-2 column
  * scale that lets the column arg-min of NearestAnchor use RAW (un-normalised, one exact bf16 plane) tokens. */
-int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, float* out, void* stream);
+int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D,
+                     int f16_rows /* 1: the rows are fed as a VQB_PLANES_F16 plane; its power-of-two row scale is folded in */,
+                     float* out, void* stream);
 
 /* keys -> int64 indices (and optional fp32 scores); `index_offset` is subtracted. */
 int vqb_unpack_keys(const unsigned long long* keys, int64_t n, int64_t index_offset,

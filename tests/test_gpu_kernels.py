@@ -167,6 +167,32 @@ def test_assign_fp16_pair_both_operands_column_argmin(dev):
         _check_indices(d.t().contiguous(), d.argmin(0), ops.unpack_keys(keys).cpu(), what='pair x pair')
 
 
+def test_column_argmin_fp16_token_plane_with_scaled_rows(dev):
+    """NearestAnchor column arg-min against a fp16-pair codebook with bf16 tokens: tokens as ONE fp16 plane +
+    1/|x_n| column scale (two MMA terms).  A token with huge components is stored scaled by a power of two; the
+    same factor is folded into its inverse norm, so it competes with its true cosine."""
+    from vector_quantization_b200 import functional as Fq
+    N, K, D = 3000, 257, 32
+    x, E = O.synthetic_latents(N, K, D, seed=9)
+    x[5] = E[100] * 1e6                 # exactly aligned with code 100, far outside the fp16 range
+    x[7] = E[200] * 3e-4
+    xb = x.to(torch.bfloat16)
+    d = 1 - F.normalize(xb.float()) @ F.normalize(E).t()
+    book = Fq.pack_codebook(E.to(dev), 'Cosine', tokens=xb.to(dev))
+    assert book.pair
+    for backend in (ops.BACKEND_SIMT, ops.BACKEND_TCGEN05):
+        raw = ops.pack_rows(xb.to(dev), fmt='f16')
+        raw.inv_norm = ops.row_inv_norm(xb.to(dev), f16_rows=True)
+        keys = ops.new_keys(K, dev)
+        ops.assign(book, raw, keys, l2=False, scale_columns=True, backend=backend)
+        idx, score = ops.unpack_keys(keys, want_score=True)
+        _check_indices(d.t().contiguous(), d.argmin(0), idx.cpu(), what='fp16 token plane column arg-min')
+        assert idx[100] == 5 and idx[200] == 7
+        torch.testing.assert_close(score.cpu(), (1 - d).max(0).values, rtol=1e-5, atol=2e-6)
+    keys2 = Fq.column_nearest(xb.to(dev), book, 'Cosine')
+    assert torch.equal(ops.unpack_keys(keys2), idx)
+
+
 def test_assign_rejects_mixed_fp16_bf16_operands(dev):
     """kind::f16 MMAs take fp16 x fp16 or bf16 x bf16 (a mixed pair is an illegal instruction on B200).  The one
     supported mix is a ONE-plane bf16 A operand with D <= 64, converted in shared memory by the kernel."""

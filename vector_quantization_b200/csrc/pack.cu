@@ -257,22 +257,25 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const TG* __restrict__ 
   }
 }
 
-// out[r] = 1 / max(||x_r||, eps) for r < rows, 0 in the padding up to rows_pad (per-column scale of vqb_assign)
+// out[r] = 1 / max(||x_r||, eps) for r < rows, 0 in the padding up to rows_pad (per-column scale of vqb_assign).
+// f16_rows: the rows are fed as a VQB_PLANES_F16 plane, i.e. possibly scaled by f16_row_scale -> fold it in.
 template <typename T, int G>
 __global__ void __launch_bounds__(256) row_inv_norm_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_pad, int D,
-                                                           float* __restrict__ out) {
+                                                           int f16_rows, float* __restrict__ out) {
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
   for (int64_t r = blockIdx.x * rows_per_block + threadIdx.x / G; r < rows_pad;
        r += (int64_t)gridDim.x * rows_per_block) {
-    float ss = 0.f;
+    float ss = 0.f, amax = 0.f;
     if (r < rows)
       for (int d = lane; d < D; d += G) {
         const float v = to_f32<T>(x[r * D + d]);
         ss = fmaf(v, v, ss);
+        amax = fmaxf(amax, fabsf(v));
       }
     ss = group_sum<G>(ss);
-    if (lane == 0) out[r] = r < rows ? __fdiv_rn(1.f, fmaxf(sqrtf(ss), kNormEps)) : 0.f;
+    const float scale = f16_rows ? f16_row_scale(group_max<G>(amax)) : 1.f;
+    if (lane == 0) out[r] = r < rows ? __fdiv_rn(1.f, fmaxf(sqrtf(ss), kNormEps) * scale) : 0.f;
   }
 }
 
@@ -379,7 +382,7 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
   return VQB_OK;
 }
 
-int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, float* out, void* stream) {
+int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, int f16_rows, float* out, void* stream) {
   VQB_REQUIRE(x && out, "vqb_row_inv_norm: null pointer");
   VQB_REQUIRE(rows >= 1 && D >= 1, "vqb_row_inv_norm: bad shape");
   const int64_t rows_pad = vqb_operand_rows_pad(rows);
@@ -387,9 +390,9 @@ int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, float* out
   const int g = lanes_per_row(D);
   VQB_DISPATCH_G(g, launch_rows<G>(rows_pad, [&](int blocks) {
     if (x_dtype == VQB_F32)
-      row_inv_norm_kernel<float, G><<<blocks, 256, 0, st>>>((const float*)x, rows, rows_pad, D, out);
+      row_inv_norm_kernel<float, G><<<blocks, 256, 0, st>>>((const float*)x, rows, rows_pad, D, f16_rows, out);
     else
-      row_inv_norm_kernel<__nv_bfloat16, G><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, rows_pad, D, out);
+      row_inv_norm_kernel<__nv_bfloat16, G><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, rows_pad, D, f16_rows, out);
   }));
   VQB_LAUNCH_OK();
   return VQB_OK;

@@ -108,15 +108,20 @@ def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precisi
 
 @torch.no_grad()
 def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precision: str = DEFAULT_PRECISION,
-                   index_offset: int = 0) -> torch.Tensor:
+                   index_offset: int = 0, tokens: ops.Operand | None = None) -> torch.Tensor:
     """Packed keys [K]: for every code, the nearest token (column arg-min) — the same kernel with the
-    operands swapped.  Cosine needs normalised token planes here (the token norm now varies along the
+    operands swapped.  `tokens`: an already packed fmt='f16' token plane to share with `nearest_code`.  Cosine needs normalised token planes here (the token norm now varies along the
     reduced axis); L2 needs the tokens' 0.5|x|^2."""
     cos = metric == 'Cosine'
     keys = ops.new_keys(codebook.rows, x.device)
     if codebook.fmt != 'bf16':
-        # fp16 codebook planes need fp16 token planes: the normalised tokens as a pair (three MMA terms)
-        toks = ops.pack_rows(x, normalize=True, fmt='f16x2')
+        # fp16 codebook planes need fp16 token planes
+        if x.dtype == torch.bfloat16:
+            # raw bf16 tokens as ONE fp16 plane + the per-column 1/|x_n| scale in the epilogue: two MMA terms
+            raw = tokens if (tokens is not None and tokens.fmt == 'f16') else ops.pack_rows(x, fmt='f16')
+            raw.inv_norm = ops.row_inv_norm(x, f16_rows=True)
+            return ops.assign(codebook, raw, keys, l2=False, scale_columns=True, index_offset=index_offset)
+        toks = ops.pack_rows(x, normalize=True, fmt='f16x2')      # normalised tokens as a pair: three terms
         return ops.assign(codebook, toks, keys, l2=False, index_offset=index_offset)
     if cos:
         raw = ops.as_operand(x)

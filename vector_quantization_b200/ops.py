@@ -176,12 +176,13 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
     return keys
 
 
-def row_inv_norm(x: torch.Tensor) -> torch.Tensor:
+def row_inv_norm(x: torch.Tensor, f16_rows: bool = False) -> torch.Tensor:
+    """1 / max(|x_r|, eps) per row (zero in the operand padding); f16_rows: for rows packed with fmt='f16'."""
     lib = _lib.load()
     _cuda(x)
     rows, D = x.shape
     out = torch.empty((operand_shape(rows, D)[0],), dtype=torch.float32, device=x.device)
-    _call('vqb_row_inv_norm', lib.vqb_row_inv_norm, _p(x), _dt(x), rows, D, _p(out), _stream())
+    _call('vqb_row_inv_norm', lib.vqb_row_inv_norm, _p(x), _dt(x), rows, D, int(f16_rows), _p(out), _stream())
     return out
 
 

@@ -181,12 +181,17 @@ class VectorQuantizer(BaseQuantizer):
         book = Fq.pack_codebook(W, metric, precision=self.precision,
                                 writeback_normalized=memo.pop('_normalize_codebook', False), reset_keys=keys, tokens=x)
         normalize_tokens = memo.pop('_normalize_x', False)
+        want_columns = self.training and self._callbacks.needs_column_nearest
+        tokens = None
+        if want_columns and book.fmt != 'bf16' and x.dtype == torch.bfloat16:
+            tokens = ops.pack_rows(x, fmt='f16')      # one fp16 token plane shared by the row and the column pass
         Fq.nearest_code(x, book, metric, precision=self.precision, keys=keys, keys_are_reset=True,
-                        normalize_tokens=normalize_tokens)
+                        normalize_tokens=normalize_tokens, tokens=tokens)
         memo['keys'] = keys
-        if self.training and self._callbacks.needs_column_nearest:
+        if want_columns:
             offset = parallel.rank() * x.shape[0] if self._callbacks.column_nearest_global else 0
-            memo['column_keys'] = Fq.column_nearest(x, book, metric, precision=self.precision, index_offset=offset)
+            memo['column_keys'] = Fq.column_nearest(x, book, metric, precision=self.precision, index_offset=offset,
+                                                    tokens=tokens)
         if memo.pop('_lazy_unpack', False):
             return keys, memo            # forward(): the fused gather kernel unpacks the indices
         return ops.unpack_keys(keys), memo
