@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQB200_ABI_VERSION 1
+#define VQB200_ABI_VERSION 2 /* 2: fp16 plane formats, vqb_row_inv_norm(f16_rows), vqb_transpose_last2, vqb_compact_tokens */
 
 typedef enum { VQB_OK = 0, VQB_ERR_ARG = -1, VQB_ERR_CUDA = -2, VQB_ERR_UNSUPPORTED = -3 } vqb_status;
 typedef enum { VQB_F32 = 0, VQB_BF16 = 1 } vqb_dtype;

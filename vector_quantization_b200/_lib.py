@@ -17,6 +17,7 @@ _HERE = pathlib.Path(__file__).resolve().parent
 LIB_PATH = _HERE / 'libvqb200.so'
 CSRC = _HERE / 'csrc'
 
+ABI_VERSION = 2
 VQB_F32, VQB_BF16 = 0, 1
 BACKEND_TCGEN05, BACKEND_SIMT = 0, 1
 PLANES_F16 = 0x11     # VQB_PLANES_F16: one fp16 plane of a bf16 source
@@ -102,8 +103,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.vqb_abi_version() != 1:
-        raise VQBError(f'ABI version mismatch: library reports {lib.vqb_abi_version()}, binding expects 1')
+    if lib.vqb_abi_version() != ABI_VERSION:
+        raise VQBError(f'ABI version mismatch: library reports {lib.vqb_abi_version()}, binding expects {ABI_VERSION}')
     _lib = lib
     return lib
 
