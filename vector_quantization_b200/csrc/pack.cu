@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
     const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
     __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
     unsigned long long* __restrict__ keys, int64_t n_keys) {
+  pdl_wait();               // PDL: the source rows / key buffer may still be in use by the preceding launch
+  pdl_launch_dependents();
   // fused memset of the assignment keys
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_keys;
        i += (int64_t)gridDim.x * blockDim.x)
@@ -262,6 +264,8 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const TG* __restrict__ 
 template <typename T, int G>
 __global__ void __launch_bounds__(256) row_inv_norm_kernel(const T* __restrict__ x, int64_t rows, int64_t rows_pad, int D,
                                                            int f16_rows, float* __restrict__ out) {
+  pdl_wait();               // PDL: inputs come from the preceding launches
+  pdl_launch_dependents();
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
   for (int64_t r = blockIdx.x * rows_per_block + threadIdx.x / G; r < rows_pad;
@@ -370,11 +374,11 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
   const int g = lanes_per_row(Dp);
   VQB_DISPATCH_G(g, launch_rows<G>(rows_pad, [&](int blocks) {
     if (src_dtype == VQB_F32)
-      pack_rows_kernel<float, G><<<blocks, 256, 0, st>>>((const float*)src, rows, rows_pad, D, Dp, normalize,
+      launch_pdl(pack_rows_kernel<float, G>, blocks, 256, 0, st, (const float*)src, rows, rows_pad, D, Dp, normalize,
                                                           planes, (__nv_bfloat16*)dst_planes, half_sqnorm,
                                                           writeback, keys, keys ? n_keys : 0);
     else
-      pack_rows_kernel<__nv_bfloat16, G><<<blocks, 256, 0, st>>>(
+      launch_pdl(pack_rows_kernel<__nv_bfloat16, G>, blocks, 256, 0, st, 
           (const __nv_bfloat16*)src, rows, rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes,
           half_sqnorm, writeback, keys, keys ? n_keys : 0);
   }));
@@ -390,9 +394,9 @@ int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, int f16_ro
   const int g = lanes_per_row(D);
   VQB_DISPATCH_G(g, launch_rows<G>(rows_pad, [&](int blocks) {
     if (x_dtype == VQB_F32)
-      row_inv_norm_kernel<float, G><<<blocks, 256, 0, st>>>((const float*)x, rows, rows_pad, D, f16_rows, out);
+      launch_pdl(row_inv_norm_kernel<float, G>, blocks, 256, 0, st, (const float*)x, rows, rows_pad, D, f16_rows, out);
     else
-      row_inv_norm_kernel<__nv_bfloat16, G><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, rows, rows_pad, D, f16_rows, out);
+      launch_pdl(row_inv_norm_kernel<__nv_bfloat16, G>, blocks, 256, 0, st, (const __nv_bfloat16*)x, rows, rows_pad, D, f16_rows, out);
   }));
   VQB_LAUNCH_OK();
   return VQB_OK;

@@ -318,6 +318,8 @@ __global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
 
 __global__ void unpack_keys_kernel(const unsigned long long* __restrict__ keys, int64_t n, int64_t offset,
                                    int64_t* __restrict__ idx, float* __restrict__ score) {
+  pdl_wait();               // PDL: inputs come from the preceding launches
+  pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const unsigned long long k = keys[i];
     if (idx) idx[i] = k == kNoKey ? 0 : (int64_t)key_index(k) - offset;   // NaN row: index 0, like torch.argmin
@@ -455,7 +457,7 @@ int vqb_unpack_keys(const unsigned long long* keys, int64_t n, int64_t offset, i
   if (n <= 0) return VQB_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  unpack_keys_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(keys, n, offset, idx, score);
+  launch_pdl(unpack_keys_kernel, blocks, 256, 0, (cudaStream_t)stream, keys, n, offset, idx, score);
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

@@ -14,6 +14,8 @@ template <typename TX, int G, int V>
 __global__ void __launch_bounds__(256) scatter_stats_kernel(const TX* __restrict__ x, int64_t N, int D,
                                                             int normalize_x, const int64_t* __restrict__ quant,
                                                             float* __restrict__ stats, int64_t K) {
+  pdl_wait();               // PDL: inputs come from the preceding launches
+  pdl_launch_dependents();
   const int lane_in_warp = threadIdx.x & 31;
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(256) scatter_stats_kernel(const TX* __restrict
 
 __global__ void bincount_kernel(const int64_t* __restrict__ quant, int64_t n, unsigned long long* __restrict__ counts,
                                 int64_t K, int add_total) {
+  pdl_wait();               // PDL: inputs come from the preceding launches
+  pdl_launch_dependents();
   if (add_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counts + K, (unsigned long long)n);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < round_up(n, 32);
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -100,6 +104,8 @@ __global__ void bincount_kernel(const int64_t* __restrict__ quant, int64_t n, un
 template <int G>
 __global__ void __launch_bounds__(256) kmeans_ema_kernel(const float* __restrict__ stats, float* __restrict__ W,
                                                          int64_t K, int D, float decay, float omd) {
+  pdl_wait();               // PDL: inputs come from the preceding launches
+  pdl_launch_dependents();
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
   const float* __restrict__ counts = stats + K * (int64_t)D;
@@ -139,6 +145,8 @@ template <typename TX>
 __global__ void gather_rows_by_key_kernel(const TX* __restrict__ x, int64_t N, int D,
                                           const unsigned long long* __restrict__ keys, int64_t K, int64_t offset,
                                           float* __restrict__ out) {
+  pdl_wait();               // PDL: inputs come from the preceding launches
+  pdl_launch_dependents();
   const int64_t total = K * (int64_t)D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t k = i / D;
@@ -152,6 +160,8 @@ __global__ void cvq_update_kernel(float* __restrict__ W, const float* __restrict
                                   float* __restrict__ prob, const int64_t* __restrict__ counts,
                                   const int64_t* __restrict__ total_ptr, int64_t K, int D, float decay, float omd,
                                   float eps) {
+  pdl_wait();               // PDL: inputs come from the preceding launches
+  pdl_launch_dependents();
   const float total = (float)*total_ptr;  // int64 -> fp32, then a true division like `bin_count / numel`
   // one warp per code row; lane 0 owns the probability update
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -213,10 +223,10 @@ int vqb_scatter_stats(const void* x, int x_dtype, int64_t N, int D, int normaliz
   const int blocks = grid_rows(N, 256 / g);
 #define LAUNCH(TX)                                                                                              \
   if (vec) {                                                                                                    \
-    VQB_DISPATCH_G(g, (scatter_stats_kernel<TX, G, 4><<<blocks, 256, 0, st>>>((const TX*)x, N, D, normalize_x,  \
+    VQB_DISPATCH_G(g, (launch_pdl(scatter_stats_kernel<TX, G, 4>, blocks, 256, 0, st, (const TX*)x, N, D, normalize_x,  \
                                                                                quant, stats, K)));              \
   } else {                                                                                                      \
-    VQB_DISPATCH_G(g, (scatter_stats_kernel<TX, G, 1><<<blocks, 256, 0, st>>>((const TX*)x, N, D, normalize_x,  \
+    VQB_DISPATCH_G(g, (launch_pdl(scatter_stats_kernel<TX, G, 1>, blocks, 256, 0, st, (const TX*)x, N, D, normalize_x,  \
                                                                                quant, stats, K)));              \
   }
   if (x_dtype == VQB_F32) { LAUNCH(float) }
@@ -233,7 +243,7 @@ int vqb_bincount_accumulate(const int64_t* quant, int64_t n, int64_t* counts, in
   if (n <= 0) return VQB_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  bincount_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(quant, n, (unsigned long long*)counts, K, add_total);
+  launch_pdl(bincount_kernel, blocks, 256, 0, (cudaStream_t)stream, quant, n, (unsigned long long*)counts, K, add_total);
   VQB_LAUNCH_OK();
   return VQB_OK;
 }
@@ -244,7 +254,7 @@ int vqb_kmeans_ema_update(const float* stats, float* W, int64_t K, int D, float 
   VQB_REQUIRE(K >= 1 && D >= 1, "vqb_kmeans_ema_update: bad shape");
   const int g = pow2_lanes((D + 3) / 4);
   const int blocks = grid_rows(K, 256 / g);
-  VQB_DISPATCH_G(g, (kmeans_ema_kernel<G><<<blocks, 256, 0, (cudaStream_t)stream>>>(stats, W, K, D, decay,
+  VQB_DISPATCH_G(g, (launch_pdl(kmeans_ema_kernel<G>, blocks, 256, 0, (cudaStream_t)stream, stats, W, K, D, decay,
                                                                                     one_minus_decay)));
   VQB_LAUNCH_OK();
   return VQB_OK;
@@ -258,9 +268,9 @@ int vqb_gather_rows_by_key(const void* x, int x_dtype, int64_t N, int D, const u
   int blocks = (int)((total + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   if (x_dtype == VQB_F32)
-    gather_rows_by_key_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, N, D, keys, K, offset, out);
+    launch_pdl(gather_rows_by_key_kernel<float>, blocks, 256, 0, (cudaStream_t)stream, (const float*)x, N, D, keys, K, offset, out);
   else if (x_dtype == VQB_BF16)
-    gather_rows_by_key_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, D, keys, K, offset, out);
+    launch_pdl(gather_rows_by_key_kernel<__nv_bfloat16>, blocks, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, N, D, keys, K, offset, out);
   else
     VQB_REQUIRE(false, "vqb_gather_rows_by_key: bad dtype");
   VQB_LAUNCH_OK();
@@ -274,7 +284,7 @@ int vqb_cvq_update(float* W, const float* anchors, float anchor_scale, float* pr
   VQB_REQUIRE(K >= 1 && D >= 1, "vqb_cvq_update: bad shape");
   int blocks = (int)((K * 32 + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  cvq_update_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, anchors, anchor_scale, prob, counts, total, K, D,
+  launch_pdl(cvq_update_kernel, blocks, 256, 0, (cudaStream_t)stream, W, anchors, anchor_scale, prob, counts, total, K, D,
                                                               decay, one_minus_decay, eps);
   VQB_LAUNCH_OK();
   return VQB_OK;
