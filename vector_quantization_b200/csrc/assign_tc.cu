@@ -384,6 +384,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
         tile_argmax<SIDE, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
       else
         tile_argmax<SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+      if (warp == 2 && lane == 0) TS(2, t - t0, 1);
       if (buf) par1 ^= 1; else par0 ^= 1;
     }
     if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish
@@ -396,6 +397,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
       best_col = 0xffffffffu;
       bt = 0;
       ++at;
+      if (warp == 2 && lane == 0) TS(2, t - t0, 2);
     }
   }
 }
@@ -435,6 +437,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // PDL: barrier init / TMEM allocation below overlap the tail of the preceding launch (the operand packs);
   // global memory is first touched after pdl_wait().
   pdl_launch_dependents();
+  if (threadIdx.x == 0) TS(0, 63, 3);   // kernel start (timeline builds only)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int64_t a_tiles = (a_rows + BM - 1) / BM, b_tiles = (b_rows + BN - 1) / BN;
   const int64_t total = a_tiles * b_tiles;
