@@ -12,7 +12,12 @@ pytestmark = pytest.mark.gpu
 IDX_EPS = 1e-5  # accepted near-tie: oracle distance gap of a differing index, relative to max(1, d)
 
 
-def _check_indices(d_oracle, q_oracle, q_test, eps=IDX_EPS, what=''):
+def _check_indices(d_oracle, q_oracle, q_test, eps=IDX_EPS, what='', squared=False):
+    """squared=True: near-ties are judged on d^2.  torch.cdist's mm path computes sqrt(|x|^2 - 2 x.e + |e|^2), whose
+    fp32 cancellation error is ~1e-7 (|x|^2 + |e|^2) on d^2: when the nearest codes are much closer than the vector
+    norms (e.g. D = 1 with thousands of codes) the reference's own d is only meaningful to that resolution."""
+    if squared:
+        d_oracle = d_oracle * d_oracle
     rows, gap = O.index_mismatch_report(d_oracle, q_oracle, q_test)
     if rows.numel():
         scale = d_oracle[rows, q_oracle[rows]].abs().clamp_min(1.0)
@@ -244,6 +249,41 @@ def test_pack_rows_fp16_single_plane(dev):
     assert (got[9] - x.float()[9]).abs().max() <= 2.0 ** -25
     with pytest.raises(ValueError):
         ops.pack_rows(x.float().to(dev), fmt='f16')
+
+
+def _random_shapes(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    dims = [1, 2, 3, 5, 8, 12, 16, 20, 31, 32, 33, 48, 64, 65, 96, 128, 200, 256, 320]
+    out = []
+    for _ in range(n):
+        N = int(torch.randint(1, 1500, (1,), generator=g))
+        K = int(torch.randint(1, 3000, (1,), generator=g))
+        D = dims[int(torch.randint(0, len(dims), (1,), generator=g))]
+        out.append((N, K, D))
+    return out
+
+
+@pytest.mark.parametrize('N,K,D', _random_shapes(24, seed=2024))
+def test_assign_random_shapes_all_formats(dev, N, K, D):
+    """Seeded random (ragged) shapes: every operand format of the tcgen05 kernel against the fp32 oracle —
+    fp32 tokens as three bf16 planes (L2 and cosine), bf16 tokens against the fp16-pair codebook (packed fp16
+    plane, and zero-copy with in-kernel conversion where the layout allows it)."""
+    x, E = O.synthetic_latents(N, K, D, seed=N * 7 + K)
+    for metric in ('L2', 'Cosine'):
+        q_ref, d = O.encode(metric, x, E)
+        q, _ = _assign(x, E, metric, dev, ops.BACKEND_TCGEN05)
+        _check_indices(d, q_ref, q.cpu(), what=f'{metric} bf16 planes {N}x{K}x{D}', squared=metric == 'L2')
+    xb = x.to(torch.bfloat16)
+    q_ref, d = O.encode('Cosine', xb.float(), E)
+    book = ops.pack_rows(E.to(dev), normalize=True, fmt='f16x2')
+    variants = [ops.pack_rows(xb.to(dev), fmt='f16')]
+    raw = ops.as_operand(xb.to(dev))
+    if raw is not None and D <= 64:
+        variants.append(raw)
+    for toks in variants:
+        keys = ops.new_keys(N, dev)
+        ops.assign(toks, book, keys, l2=False)
+        _check_indices(d, q_ref, ops.unpack_keys(keys).cpu(), what=f'pair codebook ({toks.fmt} tokens) {N}x{K}x{D}')
 
 
 def test_assign_tie_break_lowest_index(dev):
