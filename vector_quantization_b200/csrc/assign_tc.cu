@@ -28,6 +28,7 @@ constexpr uint32_t kTmemCols = 512;  // two 256-column accumulators
 constexpr int kEpilogueWarps = 8;
 constexpr int kThreads = 64 + kEpilogueWarps * 32;
 constexpr uint32_t kStashBytes = kEpilogueWarps * 4096;  // winning-chunk stash: [warp][8 float4][32 lanes]
+constexpr uint32_t kShareBytes = kEpilogueWarps * 32 * 16;  // per-row running best published to the other column half
 
 struct TermTable {
   int n;
@@ -341,7 +342,7 @@ __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr,
 // (warp-2)/4 the 128-column half of the accumulator.
 template <int SIDE>
 __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_base, uint8_t* stash_smem,
-                                              float* side_smem, uint64_t* tmem_full, uint64_t* tmem_empty, int t0,
+                                              uint8_t* share_smem, float* side_smem, uint64_t* tmem_full, uint64_t* tmem_empty, int t0,
                                               int t1, int b_tiles, int a_rows, int b_rows,
                                               const float* __restrict__ b_half_sqnorm, uint32_t b_index_offset,
                                               unsigned long long* __restrict__ keys) {
@@ -358,6 +359,15 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
   uint32_t best_col = 0xffffffffu;
   int at = t0 / b_tiles, bt = t0 - at * b_tiles;
   uint32_t par0 = 0, par1 = 0;                 // per-accumulator phase parity
+  // The two warps that own the two column halves of a row exchange their running best through shared memory
+  // (no synchronisation: a stale entry is still a real score of the row).  A partner value from an EARLIER code
+  // tile that beats mine makes my current candidate irrelevant and raises my threshold, which halves the number
+  // of winning-chunk stashes (the stash is 16-22 % of the kernel, profiles/r1_assign_notes.md).  Entries are
+  // tagged (row tile, code tile): only strictly earlier tiles of the same row tile are used, so on an exact
+  // tie the lower code index still wins.
+  const uint32_t my_share = smem_u32(share_smem) + ((uint32_t)ew * 32 + (uint32_t)lane) * 16;
+  const uint32_t partner_share = smem_u32(share_smem) + ((uint32_t)(ew ^ 4) * 32 + (uint32_t)lane) * 16;
+
   // side term of this thread's column for the tile about to be staged, fetched one tile ahead so that its
   // L2 latency is not exposed in front of the barrier
   float side_val = 0.f;
@@ -374,6 +384,15 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
         if (t + 1 < t1) side_val = __ldg(b_half_sqnorm + (bt + 1 == b_tiles ? 0 : bt + 1) * BN + gtid);
         named_bar_sync(1, 256);
       }
+      {
+        uint32_t pb_, pat, pbt, pad;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pb_), "=r"(pat), "=r"(pbt), "=r"(pad) : "r"(partner_share));
+        const float pbest = __uint_as_float(pb_);
+        if (pat == (uint32_t)at && pbt < (uint32_t)bt && pbest > best) {
+          best = pbest;                        // the other half already holds a better candidate (lower index on ties):
+          best_col = 0xffffffffu;              // mine is out of the race until a later chunk beats it
+        }
+      }
       mbar_wait(tmem_full + buf, buf ? par1 : par0);
       if (warp == 2 && lane == 0) TS(2, t - t0, 0);
       tc_fence_after();
@@ -385,6 +404,9 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
       else
         tile_argmax<SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
       if (warp == 2 && lane == 0) TS(2, t - t0, 1);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_share), "r"(__float_as_uint(best)), "r"((uint32_t)at),
+                   "r"((uint32_t)bt), "r"(0u)
+                   : "memory");
       if (buf) par1 ^= 1; else par0 ^= 1;
     }
     if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish
@@ -421,11 +443,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // slots (loaded once per row tile, not once per work item).  k-blocked: a stage is one [A slab | B slab] pair.
   const uint32_t stage_bytes = WHOLE ? (uint32_t)pb * kBBytes : kABytes + kBBytes;
   const uint32_t a_slot_bytes = WHOLE ? (uint32_t)pa * kABytes : 0u;
-  // carve: [A slots] | [stages] | stash[8 warps][4 KB] | side[2][256] | barriers | tmem ptr   (1024 B aligned)
+  // carve: [A slots] | [stages] | stash[8 warps][4 KB] | share[8 warps][32 x 16 B] | side[2][256] | barriers | tmem ptr
   uint8_t* smem_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem = smem_a + 2 * (size_t)a_slot_bytes;
   uint8_t* stash_smem = smem + (size_t)nstages * stage_bytes;
-  float* side_smem = reinterpret_cast<float*>(stash_smem + kStashBytes);
+  uint8_t* share_smem = stash_smem + kStashBytes;
+  float* side_smem = reinterpret_cast<float*>(share_smem + kShareBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(side_smem + 2 * BN);
   uint64_t* empty_bar = full_bar + nstages;
   uint64_t* tmem_full = empty_bar + nstages;
@@ -459,6 +482,10 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp >= 2) {  // epilogue: invalidate this thread's slot of the running-best exchange (tag = no row tile)
+    const uint32_t slot = smem_u32(share_smem) + ((uint32_t)(warp - 2) * 32 + (uint32_t)lane) * 16;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(0xff800000u), "r"(0xffffffffu), "r"(0u), "r"(0u) : "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -604,7 +631,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================== epilogue: fused arg-max =====================
 #define VQB_EPI(SIDE_)                                                                                              \
-  epilogue_loop<SIDE_>(warp, lane, tmem_base, stash_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,       \
+  epilogue_loop<SIDE_>(warp, lane, tmem_base, stash_smem, share_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,       \
                        (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys)
     if (b_half_sqnorm == nullptr || side_mode == 0) VQB_EPI(0);
     else if (side_mode == 1) VQB_EPI(1);
@@ -719,7 +746,7 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
   const uint32_t a_resident = WHOLE ? 2u * (uint32_t)pa * BM * BK * 2 : 0u;
   int nstages = (int)((196608 - kStashBytes - a_resident) / stage_bytes);
   if (nstages > 8) nstages = 8;
-  const size_t smem_bytes = 1024 + a_resident + (size_t)nstages * stage_bytes + kStashBytes + 2 * BN * sizeof(float) +
+  const size_t smem_bytes = 1024 + a_resident + (size_t)nstages * stage_bytes + kStashBytes + kShareBytes + 2 * BN * sizeof(float) +
                             (2 * nstages + 8) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
