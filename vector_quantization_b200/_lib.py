@@ -14,7 +14,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
                     c_ulonglong, c_void_p)
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / 'libvqb200.so'
+# VQB200_LIB: developer override, e.g. to A/B two builds of the library on the same GPU box
+LIB_PATH = pathlib.Path(os.environ['VQB200_LIB']) if os.environ.get('VQB200_LIB') else _HERE / 'libvqb200.so'
 CSRC = _HERE / 'csrc'
 
 ABI_VERSION = 2
