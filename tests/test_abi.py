@@ -60,3 +60,15 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG'):
         assert mnemonic in sass, f'{mnemonic} missing from the SASS of libvqb200.so'
     assert 'sm_100a' in sass
+
+
+def test_integration_sketch_matches_binding_table():
+    """The reference-side ctypes stub shown in INTEGRATION.md binds the same arity / argument kinds as _lib.SIGNATURES."""
+    import ctypes
+    text = (HEADER.parents[1] / 'INTEGRATION.md').read_text()
+    kinds = {'P': ctypes.c_void_p, 'I64': ctypes.c_int64, 'I': ctypes.c_int}
+    found = dict(re.findall(r'_lib\.(vqb_[a-z0-9_]+)\.argtypes = \[([A-Z0-9, ]+)\]', text))
+    assert {'vqb_pack_rows', 'vqb_assign', 'vqb_unpack_keys'} <= set(found)
+    for name, args in found.items():
+        sketch = [kinds[a.strip()] for a in args.split(',')]
+        assert sketch == list(_lib.SIGNATURES[name][1]), name
