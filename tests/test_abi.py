@@ -72,3 +72,16 @@ def test_integration_sketch_matches_binding_table():
     for name, args in found.items():
         sketch = [kinds[a.strip()] for a in args.split(',')]
         assert sketch == list(_lib.SIGNATURES[name][1]), name
+
+
+def test_header_is_plain_c():
+    """include/vqb200.h is the drop-in boundary: it must compile as C99 (cgo / JNI / FFI generators read it)."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        import pytest
+        pytest.skip('gcc not available')
+    for args in (['gcc', '-std=c99', '-pedantic', '-Werror', '-fsyntax-only', '-x', 'c'],
+                 ['g++', '-std=c++17', '-Werror', '-fsyntax-only', '-x', 'c++']):
+        r = subprocess.run(args + [str(HEADER)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
