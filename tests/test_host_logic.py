@@ -161,3 +161,49 @@ def test_oracle_caller_restatement_matches_reference_rearranges():
     assert torch.equal(out['quant'][0], ref['quant'][0]) and torch.equal(loss, ref['loss'][0])
     assert torch.equal(z, ref['z_ste'][0].view(b, h, w, c).permute(0, 3, 1, 2)) and z.is_contiguous()
     assert torch.equal(O.model_encode_to_quant('L2', x, E), ref['quant'][0].view(b, h, w))
+
+
+@pytest.mark.parametrize('anchor_type', ['NearestAnchor', 'CachedAnchor'])
+def test_cvqvae_callback_wiring_with_both_anchor_kinds(monkeypatch, anchor_type):
+    """Host-side wiring of CVQVAECallback.after_encode (no GPU): the C-ABI wrappers are replaced by torch
+    restatements so that the call sequence, the optional column keys and the anchor `gather` contract are exercised
+    for NearestAnchor (needs the column arg-min pass) and CachedAnchor (samples rows; no column pass)."""
+    import random
+    from oracle import oracle as O
+    from vector_quantization_b200 import ops
+    from vector_quantization_b200.anchors import cached_rows_and_indices
+    K, D, N = 16, 4, 40
+    q = vqb.build_quantizer(dict(
+        type='VQGANQuantizer', embedding=dict(type='torch_nn_modules_sparse_Embedding', num_embeddings=K, embedding_dim=D),
+        distance=dict(type='CosineDistance'), losses=dict(l=dict(type='CodebookLoss')),
+        callbacks=[dict(type='CVQVAECallback', ema=dict(decay=0.9), anchor=dict(type=anchor_type))],
+        init_weights=dict(type='vqgan')), training=True)
+    cb = [c for c in q._callbacks._callbacks if type(c).__name__ == 'CVQVAECallback'][0]
+    assert q._callbacks.needs_column_nearest == (anchor_type == 'NearestAnchor')
+
+    def bincount(quant, counts, K_=None, total_slot=False):
+        counts[:K] += torch.bincount(quant, minlength=K)
+        if total_slot:
+            counts[K] += quant.numel()
+        return counts
+    seen = {}
+    monkeypatch.setattr(ops, 'bincount_accumulate', bincount)
+    monkeypatch.setattr(ops, 'gather_rows_by_key', lambda rows, keys, off=0: rows.float()[(keys & 0xffffffff) - off])
+    monkeypatch.setattr(ops, 'cvq_update', lambda W, anchors, prob, cnt, tot, **kw: seen.update(anchors=anchors.clone(), kw=kw))
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, D, generator=g)
+    quant = torch.randint(0, K, (N,), generator=g)
+    d = O.distance('Cosine', x, q.embedding.weight.data)
+    memo = dict(encode=dict())
+    if anchor_type == 'NearestAnchor':
+        memo['encode']['column_keys'] = d.argmin(0)          # token index in the low key bits
+    torch.manual_seed(5); random.seed(5)
+    out = cb.after_encode(x, quant, memo)
+    assert out is quant and seen['kw']['anchor_scale'] == 1.0 and seen['anchors'].shape == (K, D)
+    if anchor_type == 'NearestAnchor':
+        assert torch.equal(seen['anchors'], x[d.argmin(0)])
+    else:
+        torch.manual_seed(5); random.seed(5)
+        rows, idx = cached_rows_and_indices(x, K, torch.empty(0))
+        assert torch.equal(seen['anchors'], rows[idx]) and torch.equal(cb._anchor.cache, rows[idx])
+        assert not any('_cache' in k for k in q.state_dict())   # the cache lives in a callback: not checkpointed (SURVEY §5)

@@ -39,3 +39,27 @@ def test_plugin_force_registers_into_reference_registries():
     q = ref.VQITQuantizerRegistry.build(cfg)
     assert type(q) is vqb.VQGANQuantizer and type(q.distance) is vqb.L2Distance
     assert type(q._losses['vqgan_loss']) is vqb.VQGANLoss
+
+
+@pytest.mark.parametrize('N,K', [(200, 64), (64, 64), (40, 64)])
+def test_cached_anchor_sampling_rule_equals_reference_source(N, K):
+    """CachedAnchor never reads the distance values: with equal seeds our sampling rule (rows + indices) yields the
+    reference's anchors bit for bit, over consecutive steps (cache top-up) and for N > K, N == K and N < K."""
+    import random
+    ref = ref_loader.load()
+    from vector_quantization_b200.anchors import cached_rows_and_indices
+    D = 8
+    g = torch.Generator().manual_seed(N)
+    ref_anchor = ref.cvqvae.anchors.CachedAnchor()
+    cache = torch.empty(0)
+    for step in range(3):
+        x = torch.randn(N, D, generator=g)
+        d = torch.zeros(N, K)                       # only its shape is used (anchors.py:146-159)
+        torch.manual_seed(100 + step); random.seed(100 + step)
+        want, _ = ref_anchor(x, None, d, None, torch.zeros(K))
+        torch.manual_seed(100 + step); random.seed(100 + step)
+        rows, idx = cached_rows_and_indices(x, K, cache)
+        got = rows[idx]
+        assert torch.equal(got, want), step
+        cache = got
+        assert torch.equal(ref_anchor.cache, cache)

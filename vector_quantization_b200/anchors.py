@@ -10,6 +10,9 @@ all_gather of x, d[N x K], quant and p (anchors.py:50-57) / all_reduce-mean (anc
 """
 from __future__ import annotations
 
+import random
+from typing import Mapping
+
 import torch
 from torch import nn
 
@@ -25,11 +28,14 @@ class BaseAnchor(nn.Module):
         super().__init__(*args, **kwargs)
         self._sync = sync
 
+    needs_columns = True   # gather() consumes the per-code nearest-token keys of the column arg-min pass
+
     @property
     def sync(self) -> bool:
         return self._sync
 
-    def gather(self, x: torch.Tensor, column_keys: torch.Tensor, n_local: int) -> torch.Tensor:
+    def gather(self, x: torch.Tensor, column_keys: torch.Tensor | None, n_local: int,
+               num_codes: int | None = None) -> torch.Tensor:
         raise NotImplementedError
 
 
@@ -37,7 +43,7 @@ class BaseAnchor(nn.Module):
 class NearestAnchor(BaseAnchor):
 
     @torch.no_grad()
-    def gather(self, x, column_keys, n_local):
+    def gather(self, x, column_keys, n_local, num_codes=None):
         """-> [K, D] fp32 anchors, already summed over ranks (identical on every rank)."""
         if self._sync:
             offset = parallel.rank() * n_local          # column_keys were built with this offset
@@ -53,13 +59,57 @@ class MultinomialAnchor(BaseAnchor):
     """anchors.py:88-104 samples from softmax over the materialised distance columns — registered for config
     compatibility, not implemented on the B200 path (no shipped config uses it)."""
 
-    def gather(self, x, column_keys, n_local):
+    def gather(self, x, column_keys, n_local, num_codes=None):
         raise NotImplementedError('MultinomialAnchor needs the materialised N x K distance matrix')
+
+
+def cached_rows_and_indices(x: torch.Tensor, num_codes: int, cache: torch.Tensor):
+    """The sampling rule of CachedAnchor._anchors (anchors.py:140-166), which never looks at the distance VALUES:
+    tokens (topped up with the previous anchors, then with uniform noise, when there are fewer tokens than codes)
+    and K row indices — a random permutation when rows <= K, else a sample without replacement.  Same RNG calls
+    in the same order as the reference (`torch.randperm` / `random.sample` on the host, `torch.rand` on the
+    token device), so equal seeds give equal anchors."""
+    K = int(num_codes)
+    rows = x
+    if rows.shape[0] < K and cache.numel() > 0:
+        rows = torch.cat([rows.to(cache.dtype), cache])
+    indices = torch.randperm(K) if rows.shape[0] <= K else torch.tensor(random.sample(range(rows.shape[0]), K))
+    if rows.shape[0] < K:
+        missing = torch.rand(K - rows.shape[0], rows.shape[1], device=rows.device)
+        rows = torch.cat([rows.to(missing.dtype), missing])
+    return rows, indices
 
 
 @AnchorRegistry.register_()
 class CachedAnchor(BaseAnchor):
-    """anchors.py:107-166 (random permutation + cache) — registered, not implemented yet."""
+    """anchors.py:107-166: K random token rows per step (no distances involved), remembered in the `_cache`
+    buffer to top up small batches.  sync=True gathers the tokens of every rank first (anchors.py:50-51; every
+    rank must then draw the same indices, as in the reference); sync=False averages the per-rank anchors
+    (anchors.py:64-67: all_reduce here, the 1/world in the blend kernel)."""
 
-    def gather(self, x, column_keys, n_local):
-        raise NotImplementedError('CachedAnchor is not implemented on the B200 path yet')
+    needs_columns = False
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self.register_buffer('_cache', torch.empty(0))
+
+    @property
+    def cache(self) -> torch.Tensor:
+        return self.get_buffer('_cache')
+
+    def _load_from_state_dict(self, state_dict: Mapping[str, torch.Tensor], prefix: str, *args, **kwargs) -> None:
+        cache = state_dict.get(f'{prefix}_cache')
+        if cache is not None:
+            self.cache.resize_(cache.shape)      # anchors.py:131-133
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    @torch.no_grad()
+    def gather(self, x, column_keys, n_local, num_codes=None):
+        assert num_codes is not None, 'CachedAnchor.gather needs the codebook size'
+        if self._sync and parallel.world_size() > 1:
+            x = parallel.all_gather_rows(x)
+        rows, indices = cached_rows_and_indices(x, num_codes, self.cache.to(x.device))
+        keys = indices.to(device=rows.device, dtype=torch.int64).contiguous()   # row index in the low 32 key bits
+        anchors = ops.gather_rows_by_key(rows.contiguous(), keys, 0)
+        self.register_buffer('_cache', anchors.detach().clone())
+        return anchors if self._sync else parallel.all_reduce_sum_(anchors)

@@ -286,8 +286,6 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
 class CVQVAECallback(UpdateMixin, BaseCallback):
     """Usage-probability EMA + nearest-token anchors + per-code decay blend (training only)."""
 
-    needs_column_nearest = True
-
     def __init__(self, *args, anchor, eps: float = 1e-3, **kwargs) -> None:
         super().__init__(*args, **kwargs)
         self._anchor = anchor
@@ -298,6 +296,10 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
         config = super().build_pre_hook(config, registry, item)
         config['anchor'] = AnchorRegistry.build_or_return(config['anchor'])
         return config
+
+    @property
+    def needs_column_nearest(self) -> bool:  # type: ignore[override]
+        return bool(self._anchor.needs_columns)     # NearestAnchor: yes; CachedAnchor samples rows, no distances
 
     @property
     def column_nearest_global(self) -> bool:  # type: ignore[override]
@@ -328,9 +330,9 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
         cnt = torch.zeros(K + 1, dtype=torch.int64, device=x.device)
         ops.bincount_accumulate(quant, cnt, K, total_slot=True)
         parallel.all_reduce_sum_(cnt)
-        col_keys = memo['encode']['column_keys']
+        col_keys = memo['encode'].get('column_keys')
         world = parallel.world_size()
-        anchors = self._anchor.gather(x, col_keys, N)
+        anchors = self._anchor.gather(x, col_keys, N, num_codes=K)
         scale = 1.0 if self._anchor.sync else 1.0 / world
         ops.cvq_update(W, anchors, self.probability, cnt[:K], cnt[K:], decay=self._ema.decay, eps=self._eps,
                        anchor_scale=scale)

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ['world_size', 'rank', 'all_reduce_sum_', 'all_reduce_min_keys_', 'shard_range']
+__all__ = ['world_size', 'rank', 'all_reduce_sum_', 'all_gather_rows', 'all_reduce_min_keys_', 'shard_range']
 
 _SIGN = -(1 << 63)  # 0x8000... as int64
 
@@ -39,6 +39,15 @@ def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if _on():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+def all_gather_rows(x: torch.Tensor) -> torch.Tensor:
+    """torch.cat(all_gather(x)) over the rows, rank order (cvqvae/anchors.py:51); every rank holds N rows."""
+    if not _on():
+        return x
+    parts = [torch.empty_like(x) for _ in range(world_size())]
+    dist.all_gather(parts, x.contiguous())
+    return torch.cat(parts)
 
 
 def all_reduce_min_keys_(keys: torch.Tensor) -> torch.Tensor:
