@@ -207,3 +207,29 @@ def test_cvqvae_callback_wiring_with_both_anchor_kinds(monkeypatch, anchor_type)
         rows, idx = cached_rows_and_indices(x, K, torch.empty(0))
         assert torch.equal(seen['anchors'], rows[idx]) and torch.equal(cb._anchor.cache, rows[idx])
         assert not any('_cache' in k for k in q.state_dict())   # the cache lives in a callback: not checkpointed
+
+
+def test_operand_format_selection(monkeypatch):
+    """Which plane format the host layer asks the pack kernel for (no GPU: ops.pack_rows is recorded):
+    fp16 pair only for a normalised fp32 codebook matched against bf16 tokens at the default precision;
+    exact bf16 planes for L2 / fp32 tokens / precision='exact'; fewer planes for 'high' / 'fast'."""
+    from vector_quantization_b200 import functional as Fq, ops
+    calls = []
+
+    def fake_pack(src, **kw):
+        calls.append(kw)
+        fmt = kw.get('fmt', 'bf16')
+        planes = {'f16x2': 2, 'f16': 1}.get(fmt, kw.get('planes') or (1 if src.dtype == torch.bfloat16 and not kw.get('normalize') else 3))
+        return ops.Operand(torch.empty(0), src.shape[0], src.shape[1], planes, None, fmt=fmt)
+    monkeypatch.setattr(ops, 'pack_rows', fake_pack)
+    W = torch.randn(64, 32)
+    xb, xf = torch.randn(10, 32).to(torch.bfloat16), torch.randn(10, 32)
+    assert Fq.pack_codebook(W, 'Cosine', tokens=xb).fmt == 'f16x2'
+    assert Fq.pack_codebook(W, 'Cosine', tokens=xf).fmt == 'bf16' and calls[-1]['planes'] == 3
+    assert Fq.pack_codebook(W, 'Cosine').fmt == 'bf16'                                   # tokens unknown: exact planes
+    assert Fq.pack_codebook(W, 'Cosine', tokens=xb, precision='exact').fmt == 'bf16' and calls[-1]['planes'] == 3
+    assert Fq.pack_codebook(W, 'Cosine', tokens=xb, precision='high').fmt == 'bf16' and calls[-1]['planes'] == 2
+    assert Fq.pack_codebook(W, 'Cosine', tokens=xb, precision='fast').fmt == 'bf16' and calls[-1]['planes'] == 1
+    book = Fq.pack_codebook(W, 'L2', tokens=xb)                                          # un-normalised rows: no fp16
+    assert book.fmt == 'bf16' and calls[-1]['planes'] == 3 and calls[-1]['want_half_sqnorm']
+    assert Fq.pack_codebook(W, 'L2', tokens=xb, writeback_normalized=True).fmt == 'bf16'  # LlamaGen L2 stays on bf16 planes
