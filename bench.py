@@ -2,8 +2,12 @@
 
 Workload (BASELINE.json configs[1], the config the metric is quoted on): VQ-KD cosine quantizer,
 l2-normalised 8192 x 32 codebook, batch 256 x 256 = 65 536 bf16 tokens per GPU, forward + straight-through
-backward, driven through the drop-in module (`VQKDQuantizer.forward`, reference-style config).
-A "step" is one forward+backward of the quantizer over one batch of synthetic latents.
+backward of a TRAINING step, driven through the drop-in module (`VQKDQuantizer.forward` in training mode,
+reference-style config): nearest code, per-code count/sum statistics, their exchange across the GPUs
+(vq/algorithms/vqkd/quantizers/callbacks.py:63-64, vq/utils.py:35), k-means/EMA codebook update, gather +
+straight-through + commitment loss, backward to the tokens.  At N > 1 the statistics exchange is inside
+the timed step (fused into the update kernel over NVLink peer memory; `collective` in the JSON line).
+A "step" is one such forward+backward over one batch of synthetic latents.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -32,8 +36,8 @@ SEED = 3407  # reference default (vq/train.py:21)
 
 WORKLOADS = {
     # BASELINE.json configs[1]
-    'cfg2': dict(name='cfg2: VQ-KD cosine quantizer fwd + straight-through bwd', N=65536, K=8192, D=32,
-                 metric='Cosine', training=False,
+    'cfg2': dict(name='cfg2: VQ-KD cosine quantizer training step (stats exchange + EMA update), fwd + straight-through bwd',
+                 N=65536, K=8192, D=32, metric='Cosine', training=True,
                  config=dict(type='VQKDQuantizer', distance=dict(type='CosineDistance'),
                              callbacks=[dict(type='VQKDCallback', ema=dict())],
                              losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True)))),
@@ -125,33 +129,70 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def run_reference(args, wl):
-    """The reference's CPU implementation of the path (oracle port) on the host cores, bounded sample."""
+def run_reference(args, wl, budget_s: float = 150.0):
+    """The reference's CPU implementation of the path (oracle port) on the host cores.  Runs EXACTLY args.steps timed
+    steps after args.warmup warm-ups; each step is a bounded sample of the workload: the full batch when the run fits
+    the time budget, otherwise the first rows of it (stated in `sample`)."""
     from oracle import oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     N, K, D = wl['N'], wl['K'], wl['D']
     x, E, gz = synth(N, K, D, SEED)
     spec = O.QuantizerSpec(training=wl['training'], **wl['oracle'])
-
     prob = torch.zeros(K) if wl['oracle'].get('callback') == 'CVQVAECallback' else None
 
-    def step():
-        xo = x.float().requires_grad_(True)
+    def step(n):
+        xo = x[:n].float().requires_grad_(True)
         out = O.quantizer_forward(spec, [xo], E, prob)
-        torch.autograd.backward((out['z_ste'][0], out['loss'][0]), (gz, torch.ones([])))
+        torch.autograd.backward((out['z_ste'][0], out['loss'][0]), (gz[:n], torch.ones([])))
         return out
 
-    for _ in range(min(args.warmup, 2)):
-        step()
-    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    step(N)                                    # untimed probe: sizes the per-step sample
+    probe = time.perf_counter() - t0
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    n = N
+    if probe * (steps + warmup) > budget_s:
+        n = max(1024, int(N * budget_s / (probe * (steps + warmup))) // 1024 * 1024)
+    for _ in range(warmup):
+        step(n)
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
+        step(n)
     dt = (time.perf_counter() - t0) / steps
-    value = N / dt
-    sample = f'full {wl["name"]} batch (N={N}) x {steps} steps, fp32, torch {torch.__version__} CPU'
-    return dict(value=value, ms=dt * 1e3, cores=threads, kind='port', sample=sample, steps=steps)
+    value = n / dt
+    sample = (f'{"full batch" if n == N else f"first {n} of {N} tokens"} of {wl["name"]} per step x {steps} timed steps '
+              f'after {warmup} warm-ups, fp32, torch {torch.__version__} CPU, {threads} threads')
+    return dict(value=value, ms=dt * 1e3, cores=threads, kind='port', sample=sample, steps=steps, warmup=warmup)
+
+
+def run_gpu_eager(wl, dev, x0, E, gz0, autocast: bool, steps: int = 10):
+    """Context, not the product: the reference's OWN op sequence (normalize -> einsum -> 1 - d -> argmin -> bincount /
+    scatter_add / EMA -> embedding -> mse -> backward; the oracle restatement executed with CUDA tensors, i.e. stock
+    ATen / cuBLAS kernels) on the same B200.  `autocast`: under torch.autocast(bf16) as the reference trains."""
+    from oracle import oracle as O
+    spec = O.QuantizerSpec(training=wl['training'], **wl['oracle'])
+    x, W, gz = x0.to(dev), E.to(dev), gz0.to(dev)
+    prob = torch.zeros(wl['K'], device=dev) if wl['oracle'].get('callback') == 'CVQVAECallback' else None
+    one = torch.ones([], device=dev)
+
+    def step():
+        xo = (x if autocast else x.float()).detach().requires_grad_(True)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+            out = O.quantizer_forward(spec, [xo], W, prob)
+        torch.autograd.backward((out['z_ste'][0], out['loss'][0]), (gz.to(out['z_ste'][0].dtype), one))
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return dict(value=wl['N'] / (ms * 1e-3), ms_per_step=ms)
 
 
 def run_cfg5(args, rank, world, local_rank):
@@ -245,7 +286,7 @@ def main():
             return
         r = run_reference(args, wl)
         print(json.dumps(dict(
-            metric=metric, value=r['value'], unit=unit, n_gpus=args.gpus, steps=r['steps'], warmup=min(args.warmup, 2),
+            metric=metric, value=r['value'], unit=unit, n_gpus=args.gpus, steps=r['steps'], warmup=r['warmup'],
             ms_per_step=r['ms'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
             impl='reference', config=base_cfg,
             cpu_baseline=dict(value=r['value'], unit=unit, cores=r['cores'], kind=r['kind'], sample=r['sample']),
@@ -400,6 +441,18 @@ def main():
         ops.assign(toks, book, keys, l2=wl['metric'] == 'L2')
     torch.cuda.synchronize()
     assign_ms = [a.elapsed_time(b) for name, a, b in ops.PROFILE if name == 'vqb_assign'][3:]
+    # ---- every kernel of the step, timed live the same way (eager launches behind an L2-flushing memset that keeps
+    # the GPU busy while the host enqueues the step): the HBM-bound kernels against the measured copy bandwidth, and
+    # the statistics exchange.  All ranks run the same number of steps (the exchange is a collective).
+    ops.PROFILE = []
+    n_prof = 12
+    for i in range(n_prof):
+        flush.zero_()
+        step(i)
+    torch.cuda.synchronize()
+    per_kernel = {}
+    for name, a, b in ops.PROFILE[len(ops.PROFILE) // n_prof * 2:]:      # skip the first two steps
+        per_kernel.setdefault(name, []).append(a.elapsed_time(b))
     ops.PROFILE = None
     del flush
     assign_ms.sort()
@@ -409,7 +462,7 @@ def main():
         peaks = json.load(open(ROOT / 'MEASURED_PEAKS.json'))
     except Exception:  # noqa: BLE001
         pass
-    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)  # kernel timed inside a long step -> sustained figure
+    peak_tf = peaks.get('bf16_tflops', 1590.0)   # the kernel is timed ALONE (event-bracketed launches) -> burst figure
     flops = 2.0 * N * K * D                              # algorithmic: contraction only, un-padded, one plane
     achieved = flops / (assign_avg * 1e-3) / 1e12
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/, per launch)
@@ -427,7 +480,8 @@ def main():
         pass
     roofline = dict(bound='tensor', kernel='assign_tc_kernel (tcgen05 distance GEMM + fused arg-min)',
                     achieved=achieved, peak=peak_tf, unit='TFLOP/s', frac=achieved / peak_tf,
-                    peak_source='MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (B200_PROFILING.md)',
+                    peak_source='MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)' if peaks else 'fallback 1.59 PFLOP/s (B200_PROFILING.md)',
+                    frac_of_sustained=achieved / peaks.get('bf16_tflops_sustained', 1400.0),
                     kernel_ms=assign_avg, kernel_share_of_step=assign_avg / ms,
                     epilogue_gelem_per_s=N * K / (assign_avg * 1e-3) / 1e9, traffic=traffic,
                     algorithmic_bytes=N * D * 2 + K * D * 2 * book.nplanes + N * 8, ncu=ncu_note,
@@ -435,6 +489,45 @@ def main():
                     note=f'algorithmic flops 2*N*K*D (one plane); the fp32 codebook is fed as {book.nplanes} 16-bit '
                          f'planes = {n_terms} MMA terms per tile, so the tensor pipe is ~{n_terms}x busier than '
                          '`frac` (mma_issued_tflops; see ncu.tensor_pipe_active_pct)')
+
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    s_x = 2                                              # bf16 tokens
+    launches_of = {k: len(v) / (n_prof - 2) for k, v in per_kernel.items()}
+    alg_bytes = {   # algorithmic HBM bytes per launch; the L2-resident codebook rows are NOT counted
+        'vqb_gather_ste_loss': N * (D * (s_x + 4) + 8) + (0 if wl['training'] else N * 8),
+        'vqb_quantize_backward': N * (D * (4 + s_x + s_x) + 8),
+        'vqb_scatter_stats': N * (D * s_x + 8) + K * (D + 1) * 4,
+        'vqb_pack_rows': K * D * (4 + 4 + 2 * book.nplanes) + N * 8,
+        'vqb_unpack_keys': N * 16,
+    }
+    membound = []
+    for name, times in sorted(per_kernel.items()):
+        t = sum(times) / len(times)
+        rec = dict(kernel=name, ms=t, launches_per_step=launches_of[name])
+        if name in alg_bytes and launches_of[name] == 1:
+            rec.update(bytes=alg_bytes[name], gbs=alg_bytes[name] / (t * 1e-3) / 1e9,
+                       frac=alg_bytes[name] / (t * 1e-3) / 1e9 / hbm)
+        membound.append(rec)
+    roofline['membound'] = membound
+    roofline['membound_note'] = (f'per-launch CUDA-event times of eager launches, L2 flushed before every step; fractions '
+                                 f'of the measured copy bandwidth ({hbm:.0f} GB/s); at this batch size these launches '
+                                 'move 4-25 MB in a few microseconds and are launch-ramp bound, see DESIGN.md')
+    collective = None
+    if wl['training']:
+        cb = [c for c in q._callbacks if hasattr(c, '_region')]
+        fused = bool(cb and cb[0]._region)
+        key = 'vqb_comm_kmeans_ema_update' if 'vqb_comm_kmeans_ema_update' in per_kernel else 'vqb_comm_cvq_update'
+        t = per_kernel.get(key)
+        payload = (K * D + K) * 4 if args.workload in ('cfg2', 'cfg3') else (K + 1) * 8 + K * D * 4
+        collective = dict(
+            what='per-step exchange of the per-code statistics (reference: all_reduce, vq/utils.py:35, '
+                 'vqkd/quantizers/callbacks.py:63-64, cvqvae/anchors.py:64-67)',
+            bytes=payload if world > 1 else 0, world=world,
+            algo=('two-shot reduce + publish over NVLink peer memory, fused into the codebook-update kernel '
+                  f'({key}); no NCCL call on the data path') if fused else
+                 ('torch.distributed all_reduce (NCCL)' if world > 1 else 'none (single GPU)'),
+            ms=(sum(t) / len(t)) if (t and fused) else None,
+            ms_note='duration of the fused exchange+update launch, including the wait for the slowest rank')
 
     # ---- end-to-end: pinned host inputs -> device -> step -> results back to pinned host ----
     xh = x0.pin_memory()
@@ -495,9 +588,17 @@ def main():
     d2h = 4 + quant_h.numel() * 8 + gx_h.numel() * 2
     clocks = sampler.stop()
 
-    cpu_baseline = None
+    cpu_baseline = gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = run_reference(argparse.Namespace(steps=3, warmup=1), wl)
+        try:
+            gpu_eager = dict(
+                what="the reference's own op sequence (normalize, einsum, argmin, bincount/scatter_add/EMA, embedding, "
+                     'mse_loss, autograd backward) as stock ATen/cuBLAS kernels on this B200, same workload; context only',
+                fp32=run_gpu_eager(wl, dev, x0, E, gz0, autocast=False),
+                autocast_bf16=run_gpu_eager(wl, dev, x0, E, gz0, autocast=True), unit=unit)
+        except Exception as exc:  # noqa: BLE001 - context only
+            gpu_eager = dict(error=repr(exc))
+        r = run_reference(argparse.Namespace(steps=3, warmup=1), wl, budget_s=30.0)
         cpu_baseline = dict(value=r['value'], unit=unit, cores=r['cores'], kind=r['kind'], sample=r['sample'])
 
     if rank == 0:
@@ -505,14 +606,16 @@ def main():
             metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
             dtype='bf16', data='synthetic',
-            config=dict(base_cfg, arithmetic='16-bit tensor-core operands, fp32 accumulation: ' + (
+            config=base_cfg,
+            details=dict(arithmetic='16-bit tensor-core operands, fp32 accumulation: ' + (
                             'bf16 tokens zero-copy (converted to fp16 in shared memory), the fp32 codebook as the fp16 (hi, lo*2^11) plane '
                             'pair (22 significant bits, 2 MMA terms)' if book.pair else
                             f'tokens and the fp32 codebook as exact bf16 planes ({n_terms} MMA terms)') +
                         '; z/loss fp32, token gradient in the token dtype', precision=q.precision,
                         l2_policy=f'rotating {n_sets} input sets, {n_sets * (N * D * 6) >> 20} MB > L2',
                         launch='CUDA graph replay' if graphs else 'eager', kernels_per_step=launches_per_step),
-            clocks=clocks, roofline=roofline, cpu_baseline=cpu_baseline, breakdown_ms=breakdown,
+            clocks=clocks, roofline=roofline, collective=collective, cpu_baseline=cpu_baseline,
+            gpu_eager_baseline=gpu_eager, breakdown_ms=breakdown,
             e2e=dict(value=N * world / (e2e_ms * 1e-3), unit=unit, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h),
             gpu_launches=launches_per_step * args.steps)))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQB200_ABI_VERSION 2 /* 2: fp16 plane formats, vqb_row_inv_norm(f16_rows), vqb_transpose_last2, vqb_compact_tokens */
+#define VQB200_ABI_VERSION 3 /* 2: fp16 plane formats, vqb_row_inv_norm(f16_rows), vqb_transpose_last2, vqb_compact_tokens; 3: vqb_comm_*, g_dtype of vqb_quantize_backward */
 
 typedef enum { VQB_OK = 0, VQB_ERR_ARG = -1, VQB_ERR_CUDA = -2, VQB_ERR_UNSUPPORTED = -3 } vqb_status;
 typedef enum { VQB_F32 = 0, VQB_BF16 = 1 } vqb_dtype;
@@ -161,7 +161,8 @@ int vqb_embedding_gather(const float* W, int64_t K, int D, const int64_t* quant,
  *   gW[q] += g4[0]*2(z-x)/(ND) + J_n(z)^T [ g4[2]*2(n(z)-n(x))/(ND) ]     (fp32 atomics; gW pre-zeroed or NULL)
  * g4[i] are the four DEVICE scalars g_codebook, g_commitment, g_codebook_norm, g_commitment_norm (NULL = 0).  With normalize_x the chain through
  * F.normalize is applied as well: gx = J_n(x)^T g_x' (the backward of NormalizeCallback.before_encode). */
-int vqb_quantize_backward(const float* g_zste, const void* x, int x_dtype, int normalize_x,
+int vqb_quantize_backward(const void* g_zste, int g_dtype /* VQB_F32, or VQB_BF16 with bf16 tokens */,
+                          const void* x, int x_dtype, int normalize_x,
                           const float* W, int64_t K, const int64_t* quant, int64_t N, int D,
                           const float* g_codebook, const float* g_commitment,           /* DEVICE scalars, NULL = 0 */
                           const float* g_codebook_norm, const float* g_commitment_norm,
@@ -226,6 +227,44 @@ int vqb_fsq_forward(const void* x, int x_dtype, int64_t N, const vqb_fsq_params*
 int vqb_fsq_backward(const void* gz, int g_dtype, const void* x, int x_dtype, int64_t N,
                      const vqb_fsq_params* p_host, void* gx, int gx_dtype, void* stream);
 int vqb_fsq_decode(const int32_t* index, int64_t N, const vqb_fsq_params* p_host, float* z_out, void* stream);
+
+/* ---- multi-GPU exchange over NVLink peer memory, fused with the codebook update ------------ *
+ * One process per GPU (the reference's DDP model).  Replaces the statistics collectives of the path
+ *   QuantStatistics all_reduce x2                       vq/algorithms/vq/utils.py:35
+ *   VQ-KD centroid all_reduce                           vq/algorithms/vqkd/quantizers/callbacks.py:63-64
+ *   CVQ-VAE anchors all_reduce / all_gather             vq/algorithms/cvqvae/anchors.py:50-57,64-67
+ * Every rank allocates one REGION of the same size with vqb_comm_alloc (cudaMalloc + CUDA IPC handle), the host
+ * layer exchanges the 64-byte handles (any out-of-band channel: torch.distributed here), maps the peers with
+ * vqb_comm_open and publishes the table of mapped base pointers with vqb_comm_bind.  The first
+ * VQB_COMM_HEADER_BYTES of a region are the library's control block (epoch flags + peer table); everything
+ * behind it is laid out by the caller, IDENTICALLY on every rank, and addressed by byte offsets.
+ * The exchange kernels are two-shot: rank r reduces the slice [r*n/w, (r+1)*n/w) of every peer's buffer in fixed
+ * rank order (all replicas get bit-identical results), applies the update, and stores the result into every
+ * peer's region.  Collective semantics: all ranks must issue the same sequence of vqb_comm_* launches.
+ * Waits are bounded (~2 s, then the kernel traps): a missing peer is an error code, not a hang. */
+#define VQB_COMM_HEADER_BYTES 512
+#define VQB_COMM_MAX_WORLD 16
+#define VQB_IPC_HANDLE_BYTES 64
+int vqb_comm_alloc(size_t bytes, void** region, unsigned char* handle_out /* [VQB_IPC_HANDLE_BYTES] */);
+int vqb_comm_open(const unsigned char* handle, void** peer_region);
+int vqb_comm_close(void* peer_region);
+int vqb_comm_free(void* region);
+int vqb_comm_bind(void* region, const void* const* peer_regions_host /* [world], [rank] == region */, int rank, int world);
+/* stats_off: fp32 [K*D sums | K counts] (per-rank partials of vqb_scatter_stats); w_off: fp32 [K, D] codebook.
+ * = all_reduce(SUM) + vqb_kmeans_ema_update in one launch; afterwards every rank's codebook holds the same rows. */
+int vqb_comm_kmeans_ema_update(void* region, int rank, int world, size_t stats_off, size_t w_off, int64_t K, int D,
+                               float decay, float one_minus_decay, void* stream);
+/* counts_off: int64 [K counts | numel] per-rank partials; anchors_off: fp32 [K, D] per-rank nearest-token rows;
+ * keys_off: (size_t)-1 for sync=False anchors (mean over ranks), else uint64 [K] per-rank packed
+ * (distance, global token index) keys: the minimum key wins and its row is taken from the rank that holds it;
+ * w_off / prob_off: the codebook and the `_probability` buffer.  = the two all-reduces + vqb_cvq_update. */
+int vqb_comm_cvq_update(void* region, int rank, int world, size_t counts_off, size_t anchors_off, size_t keys_off,
+                        size_t w_off, size_t prob_off, int64_t K, int D, float decay, float one_minus_decay,
+                        float eps, void* stream);
+/* packed (score, index) min-loc all-reduce over uint64 [n] (codebook shards; no sign flip needed) */
+int vqb_comm_allreduce_min_keys(void* region, int rank, int world, size_t keys_off, int64_t n, void* stream);
+/* fp32 SUM all-reduce over [n] (buffer padded to a multiple of 4 floats) */
+int vqb_comm_allreduce_sum_f32(void* region, int rank, int world, size_t off, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,15 @@ CASES = {
                      O.QuantizerSpec(distance='Cosine', callback='CVQVAECallback',
                                      losses={'vqgan_loss': dict(type='VQGANLoss')}),
                      768, 128, 32, False, 3, True),
+    # configs/cvqvae/quantizer.py (a mixin) layered on configs/llamagen/vqgan.py: NormalizeCallback + CVQVAECallback,
+    # L2 on normalised tokens — anchors and the column arg-min must see F.normalize(x)
+    'llamagen_cvq_train': (dict(type='VQGANQuantizer', distance=dict(type='L2Distance'),
+                                callbacks=[dict(type='NormalizeCallback'),
+                                           dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='NearestAnchor'))],
+                                losses=dict(vqgan_loss=dict(type='VQGANLoss')), init_weights=dict(type='vqgan')),
+                           O.QuantizerSpec(distance='L2', callback='CVQVAECallback', normalize=True,
+                                           losses={'vqgan_loss': dict(type='VQGANLoss')}),
+                           512, 128, 8, False, 2, True),
     # configs/cluster/model.py:20-31: CodebookLoss only, NearestAnchor(sync=True)
     'cluster_train': (dict(type='VQGANQuantizer', distance=dict(type='CosineDistance'),
                            callbacks=[dict(type='CVQVAECallback', ema=dict(),
@@ -71,6 +80,10 @@ CASES = {
                                       losses={'vqgan_loss': dict(type='CodebookLoss')}),
                       512, 96, 64, False, 2, True),
 }
+
+
+# the k-means lazy init (vqkd/quantizers/callbacks.py:77-112): seeds only, full 10 rounds, fewer tokens than codes
+LAZY_INIT = {'seeds': (2048, 64, 16, 0), 'iters10': (2048, 64, 16, 10), 'small': (40, 64, 16, 10)}
 
 
 def run_case(name, ref_cfg, spec, N, K, D, normalized, steps, training):
@@ -147,6 +160,36 @@ def run_fsq(levels):
                 decode=dec.detach(), codebook_size=q.codebook_size, state_dict_keys=list(q.state_dict().keys()))
 
 
+def run_lazy_init(N, K, D, iters):
+    """The one-off k-means codebook init of VQ-KD (first training forward), reference source vs `O.vqkd_lazy_init`,
+    with the same `random` seed; then the first training step on the initialised codebook."""
+    x, _ = O.synthetic_latents(N, K, D, seed=SEED + N, normalized_codebook=True)
+    cfg = dict(type='VQKDQuantizer', embedding=emb(K, D), distance=dict(type='CosineDistance'),
+               callbacks=[dict(type='VQKDCallback', ema=dict())],
+               losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True))),
+               init_weights=dict(before_init_weights=dict(lazy_init_weights=dict(iters=iters))))
+    torch.manual_seed(SEED)
+    q = R.build_quantizer(cfg, training=True)
+    W0 = q.embedding.weight.detach().clone()
+    seen = {}
+
+    def record(module, args):        # runs after the callback's own pre-hook (registration order)
+        seen.setdefault('W_init', module.embedding.weight.detach().clone())
+
+    q.register_forward_pre_hook(record)
+    random.seed(SEED)
+    z, loss, memo = q(x.clone(), dict())
+    random.seed(SEED)
+    W_init = O.vqkd_lazy_init(x, W0, iters)
+    assert torch.equal(W_init, seen['W_init']), 'oracle k-means init != reference source'
+    spec = O.QuantizerSpec(distance='Cosine', callback='VQKDCallback',
+                           losses={'commitment_loss': dict(type='CommitmentLoss', norm=True)})
+    out = O.quantizer_forward(spec, [x], W_init)
+    assert torch.equal(out['quant'][0], memo['quant']) and torch.equal(out['weight'], q.embedding.weight.detach())
+    return dict(N=N, K=K, D=D, iters=iters, seed=SEED, config=cfg, x=x, W0=W0, W_init=seen['W_init'],
+                quant=memo['quant'].clone(), W_after=q.embedding.weight.detach().clone(), loss=loss.detach().clone())
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     ref = R.load()
@@ -160,6 +203,10 @@ def main():
         rec = run_fsq(levels)
         torch.save(rec, OUT / f'fsq_{rec["codebook_size"]}.pt')
         print(f'fsq_{rec["codebook_size"]}: oracle == reference source bit-for-bit')
+    for tag, args in LAZY_INIT.items():
+        rec = run_lazy_init(*args)
+        torch.save(rec, OUT / f'vqkd_lazy_init_{tag}.pt')
+        print(f'vqkd_lazy_init_{tag}: oracle == reference source bit-for-bit (N={args[0]} K={args[1]} iters={args[3]})')
 
 
 if __name__ == '__main__':

@@ -172,6 +172,27 @@ def vqkd_update(xs, quants, weight, decay):
     return normalize(e)                                           # :128 → :73-75
 
 
+def vqkd_lazy_init(x: torch.Tensor, weight: torch.Tensor, iters: int = 10, distance_kind: str = 'Cosine') -> torch.Tensor:
+    """VQKDCallback.lazy_init_weights on a single rank — vq/algorithms/vqkd/quantizers/callbacks.py:77-112: seeds
+    drawn with `random.sample` (the CALLER seeds `random`), `iters` rounds of normalise-codebook / assign /
+    centroids (unused codes keep their row), final normalise (`_update_embedding`, :73-75).  Fewer tokens than
+    codes: the RAW tokens overwrite the first rows (:91-92).  The CPU offload above 2^30 elements (:97-100)
+    only moves tensors."""
+    import random
+    e = weight.clone()                                            # :87 (`embeddings` clones)
+    if x.shape[0] < e.shape[0]:
+        e[:x.shape[0]] = x                                        # :91-92
+    else:
+        x = normalize(x)                                          # :94
+        indices = random.sample(range(x.shape[0]), e.shape[0])    # :101
+        e = x[indices]                                            # :102
+        for _ in range(iters):                                    # :103-106
+            w = normalize(e)                                      # _update_embedding
+            quant, _ = encode(distance_kind, x, w)
+            e = kmeans_centroids([x], [quant], w)
+    return normalize(e)                                           # :111
+
+
 def nearest_anchor(x: torch.Tensor, d: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     """NearestAnchor._anchors — vq/algorithms/cvqvae/anchors.py:71-85. Returns (anchors, indices)."""
     idx = d.argmin(0)
@@ -227,6 +248,7 @@ class QuantizerSpec:
     anchor_sync: bool = False               # configs/cvqvae/quantizer.py:4 / configs/cluster/model.py:28
     losses: dict = field(default_factory=dict)   # name -> dict(type=..., beta=?, norm=?)
     training: bool = True
+    normalize: bool = False                 # a NormalizeCallback layered in front of `callback` (llamagen + cvqvae mixin)
 
 
 def _losses(spec: QuantizerSpec, z, x):
@@ -259,7 +281,7 @@ def quantizer_forward(spec: QuantizerSpec, xs_in: Sequence[torch.Tensor], weight
     W = weight.detach().clone()
     xs = list(xs_in)
     # ---- before_encode ---------------------------------------------------------------------
-    if spec.callback in ('NormalizeCallback', 'VQKDCallback'):
+    if spec.callback in ('NormalizeCallback', 'VQKDCallback') or spec.normalize:
         xs = [normalize(x) for x in xs]                           # normalize.py:24
         W = normalize(W)                                          # normalize.py:26-28
         if spec.callback == 'VQKDCallback':

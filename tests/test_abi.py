@@ -34,7 +34,7 @@ def test_binding_table_matches_header():
 
 def test_load_and_pure_host_entry_points():
     lib = _lib.load()
-    assert lib.vqb_abi_version() == 2
+    assert lib.vqb_abi_version() == 3
     assert [lib.vqb_operand_dp(d) for d in (5, 8, 16, 17, 32, 33, 64, 256, 700, 768)] == \
         [16, 16, 16, 32, 32, 64, 64, 256, 704, 768]
     assert lib.vqb_operand_rows_pad(1) == 256 and lib.vqb_operand_rows_pad(257) == 512

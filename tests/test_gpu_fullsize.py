@@ -1,9 +1,10 @@
 """Parity at BASELINE.json's FULL sizes.
 
-cfg 1 (VQGAN VectorQuantizer forward, 8192 x 256 fp32 codebook, 64 x 16 x 16 latents) is small enough for the
-CPU oracle, so it is compared directly.  For the larger configurations the checks are size-independent
-properties of the quantizer: identity on the codebook itself, idempotence, permutation equivariance,
-agreement of the tensor-core kernel with the CUDA-core cross-check kernel, and shard-combine associativity.
+cfg 1-4 are compared DIRECTLY with the CPU oracle at their stated size and dtype (one whole quantizer step through
+the drop-in module: indices under the near-tie policy, loss, updated codebook, `_probability`, z, token gradient).
+On top of that come size-independent properties: identity on the codebook itself, idempotence, permutation
+equivariance, agreement of the tensor-core kernel with the CUDA-core cross-check kernel, and shard-combine
+associativity (cfg 5's 68.7 GB distance matrix cannot be materialised by any oracle).
 """
 import pytest
 import torch
@@ -159,3 +160,88 @@ def test_gather_and_backward_geometry_independent_of_row_count(dev, dtype, D):
     torch.testing.assert_close(mse4, m4[0] + m4[1], rtol=1e-5, atol=1e-9)
     torch.testing.assert_close(gx.float(), torch.cat(gxs).float(), rtol=1e-5 if dtype == torch.float32 else 1e-2, atol=1e-7)
     torch.testing.assert_close(gW, gW2, rtol=1e-4, atol=1e-6)
+
+
+# ---- BASELINE.json configs[1..3] at their full size and dtype, one whole step vs the oracle --------------------
+IDX_EPS = 1e-5     # near-tie: the oracle's own distance gap between the two candidates (cosine distances are O(1))
+
+FULL = {
+    # name: (quantizer config, oracle spec kwargs, N, K, D)
+    'cfg2': (dict(type='VQKDQuantizer', distance=dict(type='CosineDistance'),
+                  callbacks=[dict(type='VQKDCallback', ema=dict())],
+                  losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True)))),
+             dict(distance='Cosine', callback='VQKDCallback',
+                  losses={'commitment_loss': dict(type='CommitmentLoss', norm=True)}), 65536, 8192, 32),
+    'cfg3': (dict(type='VQKDQuantizer', distance=dict(type='CosineDistance'),
+                  callbacks=[dict(type='VQKDCallback', ema=dict())],
+                  losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True)))),
+             dict(distance='Cosine', callback='VQKDCallback',
+                  losses={'commitment_loss': dict(type='CommitmentLoss', norm=True)}), 65536, 16384, 8),
+    'cfg4': (dict(type='VQGANQuantizer', distance=dict(type='CosineDistance'),
+                  callbacks=[dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='NearestAnchor'))],
+                  losses=dict(vqgan_loss=dict(type='VQGANLoss')), init_weights=dict(type='vqgan')),
+             dict(distance='Cosine', callback='CVQVAECallback', losses={'vqgan_loss': dict(type='VQGANLoss')}),
+             16384, 8192, 256),
+}
+
+
+@pytest.mark.parametrize('name,training', [('cfg2', False), ('cfg2', True), ('cfg3', True), ('cfg4', True)])
+def test_full_size_step_vs_oracle(dev, name, training):
+    """One whole step of BASELINE.json configs[1] (eval and training), [2] and [3] at their stated size, bf16 tokens,
+    through the drop-in module, against `oracle.quantizer_forward` on the up-cast tokens.
+    Tolerances: indices equal except near-ties (oracle distance gap of the two candidates < 1e-5); loss rel 1e-5;
+    updated codebook rel 1e-5 / `_probability` 1e-6 on the codes no near-tie row touches; z rel 1e-5 and the bf16
+    token gradient 2^-7 on the rows whose index and code row agree."""
+    cfg, ospec, N, K, D = FULL[name]
+    x32, E = O.synthetic_latents(N, K, D, seed=3407, normalized_codebook=True)
+    xb = x32.to(torch.bfloat16)
+    g = torch.Generator().manual_seed(7)
+    gz = torch.randn(N, D, generator=g)
+    is_cvq = ospec['callback'] == 'CVQVAECallback'
+    prob0 = torch.rand(K, generator=g) / K if is_cvq else None    # a warm `_probability` (sums to ~0.5)
+
+    q = vqb.build_quantizer(dict(cfg, embedding=emb(K, D)), training=training).to(dev)
+    q._forward_pre_hooks.clear()
+    with torch.no_grad():
+        q.embedding.weight.copy_(E)
+        if is_cvq:
+            q.get_buffer('_probability').copy_(prob0)
+    xg = xb.to(dev).requires_grad_(True)
+    z, loss, memo = q(xg, dict())
+    torch.autograd.backward((z, loss), (gz.to(dev), torch.ones([], device=dev)))
+    torch.cuda.synchronize()
+
+    spec = O.QuantizerSpec(training=training, **ospec)
+    xo = xb.float().requires_grad_(True)
+    out = O.quantizer_forward(spec, [xo], E, prob0)
+    torch.autograd.backward((out['z_ste'][0], out['loss'][0]), (gz, torch.ones([])))
+    d, q_ref = out['distance'][0], out['quant'][0]
+
+    quant = memo['quant'].cpu()
+    rows, gap = O.index_mismatch_report(d, q_ref, quant)
+    assert (gap < IDX_EPS).all(), f'{name}: {int((gap >= IDX_EPS).sum())} index mismatches outside near-ties (max gap {float(gap.max())})'
+    assert rows.numel() <= N // 200, f'{name}: {rows.numel()} near-tie rows'
+    torch.testing.assert_close(loss.detach().cpu(), out['loss'][0].detach(), rtol=1e-5, atol=1e-7)
+
+    # codes whose statistics a near-tie row (or, CVQ-VAE, a near-tie COLUMN arg-min) may have changed
+    touched = torch.zeros(K, dtype=torch.bool)
+    touched[q_ref[rows]] = True
+    touched[quant[rows]] = True
+    if training and is_cvq:
+        col = ops.unpack_keys(memo['encode']['column_keys']).cpu()
+        a_ref = out['anchor_idx'][0]
+        bad = (col != a_ref).nonzero().flatten()
+        col_gap = d[col[bad], bad] - d[a_ref[bad], bad]
+        assert (col_gap < IDX_EPS).all(), f'{name}: column arg-min mismatches outside near-ties'
+        assert bad.numel() <= K // 100
+        touched[bad] = True
+        torch.testing.assert_close(q.get_buffer('_probability').cpu()[~touched], out['prob'][~touched], rtol=1e-6, atol=1e-9)
+    W_gpu = q.embedding.weight.detach().cpu()
+    torch.testing.assert_close(W_gpu[~touched], out['weight'][~touched], rtol=1e-5, atol=1e-6)
+    assert int(touched.sum()) <= K // 20
+
+    ok = (quant == q_ref) & ~touched[q_ref]
+    assert ok.float().mean() > 0.9
+    torch.testing.assert_close(z.detach().cpu()[ok], out['z_ste'][0].detach()[ok], rtol=1e-5, atol=1e-6)
+    assert xg.grad.dtype == torch.bfloat16
+    torch.testing.assert_close(xg.grad.float().cpu()[ok], xo.grad[ok], rtol=2 ** -7, atol=1e-5)

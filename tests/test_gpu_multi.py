@@ -1,6 +1,8 @@
-"""2-GPU (NCCL) parity tests of the exchange steps against the multi-rank oracle: token-sharded VQ-KD
-EMA update, CVQ-VAE anchors with sync=False (all-reduce mean) and sync=True (packed min-loc all-reduce
-instead of the reference's all_gather of the N x K matrix), and the codebook-sharded assignment.
+"""2-GPU parity tests of the exchange steps against the multi-rank oracle: token-sharded VQ-KD EMA update,
+CVQ-VAE anchors with sync=False (mean over ranks) and sync=True (packed min-loc instead of the reference's
+all_gather of the N x K matrix), the codebook-sharded assignment and the distributed k-means init, each with
+the fused NVLink peer-memory exchange kernels (`VQB_COMM=p2p`, the default) AND with the torch.distributed
+(NCCL) collectives (`VQB_COMM=nccl`).
 Skipped on boxes with fewer than two GPUs (run with `gpurun --gpus 2`)."""
 import os
 import socket
@@ -24,8 +26,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, out):
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+def _worker(rank, world, port, case, out, comm):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), VQB_COMM=comm)
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
@@ -34,11 +36,11 @@ def _worker(rank, world, port, case, out):
         dist.destroy_process_group()
 
 
-def _spawn(case, world=2):
+def _spawn(case, world=2, comm='p2p'):
     ctx = mp.get_context('spawn')
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, out, comm)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(out.get() for _ in range(world))
@@ -64,6 +66,8 @@ def _quantizer_step(cfg, N, K, D, normalized, rank, world, steps=2):
         loss.backward()
         outs.append(dict(quant=memo['quant'].cpu(), loss=loss.detach().cpu(), W=q.embedding.weight.detach().cpu(),
                          prob=q.get_buffer('_probability').cpu() if hasattr(q, '_probability') else None))
+    fused = [bool(c._region) for c in q._callbacks if hasattr(c, '_region')]
+    outs[0]['fused'] = bool(fused and fused[0])
     return outs
 
 
@@ -85,8 +89,34 @@ def _sharded(rank, world):
     x, E = O.synthetic_latents(N, K, D, seed=9)
     lo, hi = parallel.shard_range(K, rank, world)
     quant, keys = parallel.sharded_nearest_code(x.to(dev), E[lo:hi].to(dev), 'L2', shard_lo=lo)
+    quant2, _ = parallel.sharded_nearest_code(x.to(dev), E[lo:hi].to(dev), 'L2', shard_lo=lo)   # region reuse
+    assert torch.equal(quant, quant2)
     z = parallel.sharded_decode(keys, E[lo:hi].to(dev), lo)
     return quant.cpu(), z.cpu()
+
+
+def _lazy_init(rank, world):
+    """Distributed k-means init: every rank keeps ITS tokens; the result must equal the reference's rank-0 k-means
+    over the concatenated tokens (oracle); rank 0 seeds `random` like the oracle run."""
+    import random
+
+    import vector_quantization_b200 as vqb
+    from oracle import oracle as O
+    dev = torch.device('cuda', rank)
+    N, K, D = 1024, 64, 16
+    x_all, _ = O.synthetic_latents(N * world, K, D, seed=11, normalized_codebook=True)
+    cfg = dict(VQKD, embedding=emb(K, D), init_weights=dict(before_init_weights=dict(lazy_init_weights=dict(iters=10))))
+    torch.manual_seed(0)
+    q = vqb.build_quantizer(cfg, training=True).to(dev)
+    seen = {}
+
+    def record(module, args):
+        seen.setdefault('W_init', module.embedding.weight.detach().clone())
+
+    q.register_forward_pre_hook(record)
+    random.seed(123)
+    q(x_all[rank * N:(rank + 1) * N].to(dev), dict())
+    return seen['W_init'].cpu()
 
 
 CASES = {
@@ -94,6 +124,7 @@ CASES = {
     'cvq': lambda r, w: _quantizer_step(CVQ, 384, 96, 32, False, r, w),
     'cluster': lambda r, w: _quantizer_step(CLUSTER, 256, 64, 64, False, r, w),
     'sharded': _sharded,
+    'lazy_init': _lazy_init,
 }
 
 SPECS = {
@@ -106,11 +137,13 @@ SPECS = {
 }
 
 
+@pytest.mark.parametrize('comm', ['p2p', 'nccl'])
 @pytest.mark.parametrize('case', ['vqkd', 'cvq', 'cluster'])
-def test_token_sharded_training_steps_match_multi_rank_oracle(case):
+def test_token_sharded_training_steps_match_multi_rank_oracle(case, comm):
     from oracle import oracle as O
     world, steps = 2, 2
-    res = _spawn(case, world)
+    res = _spawn(case, world, comm)
+    assert res[0][0]['fused'] == (comm == 'p2p'), 'the fused peer-memory exchange must be the path that ran'
     spec_kw, N, K, D, normalized = SPECS[case]
     spec = O.QuantizerSpec(**spec_kw)
     x_all, W = O.synthetic_latents(N * world * steps, K, D, seed=5, normalized_codebook=normalized)
@@ -130,9 +163,24 @@ def test_token_sharded_training_steps_match_multi_rank_oracle(case):
         W, prob = out['weight'], out['prob']
 
 
-def test_codebook_sharded_assignment_and_decode():
+def test_distributed_kmeans_init_matches_rank0_oracle():
+    import random
+
     from oracle import oracle as O
-    res = _spawn('sharded')
+    N, K, D, world = 1024, 64, 16, 2
+    res = _spawn('lazy_init', world)
+    assert torch.equal(res[0], res[1]), 'replicas diverged'
+    x_all, _ = O.synthetic_latents(N * world, K, D, seed=11, normalized_codebook=True)
+    random.seed(123)
+    want = O.vqkd_lazy_init(x_all, torch.zeros(K, D), 10)
+    close = torch.isclose(res[0], want, rtol=1e-4, atol=1e-5).all(1)
+    assert close.float().mean() >= 0.95, f'{int((~close).sum())} of {K} centroids differ'
+
+
+@pytest.mark.parametrize('comm', ['p2p', 'nccl'])
+def test_codebook_sharded_assignment_and_decode(comm):
+    from oracle import oracle as O
+    res = _spawn('sharded', comm=comm)
     x, E = O.synthetic_latents(3000, 2048, 64, seed=9)
     q_ref, d = O.encode('L2', x, E)
     for quant, z in res:

@@ -10,7 +10,7 @@ import torch
 from oracle import oracle as O
 
 GOLDEN = pathlib.Path(__file__).parent / 'golden'
-CASES = ['vqgan_l2', 'llamagen_l2norm', 'vqkd_train', 'vqkd_eval', 'cvqvae_train', 'cluster_train']
+CASES = ['vqgan_l2', 'llamagen_l2norm', 'vqkd_train', 'vqkd_eval', 'cvqvae_train', 'llamagen_cvq_train', 'cluster_train']
 
 
 @pytest.mark.parametrize('name', CASES)
@@ -59,3 +59,14 @@ def test_usage_metrics_known_answers():
     counts = torch.tensor([4, 0, 4, 0])
     assert O.codebook_usage(counts) == 0.5
     assert abs(O.codebook_ppl(counts) - 0.6931471805599453) < 1e-6   # entropy in nats, not exp
+
+
+@pytest.mark.parametrize('tag', ['seeds', 'iters10', 'small'])
+def test_oracle_kmeans_lazy_init_matches_golden(tag):
+    """`O.vqkd_lazy_init` vs the golden written by the reference's own `lazy_init_weights` (same `random` seed)."""
+    import random
+    rec = torch.load(GOLDEN / f'vqkd_lazy_init_{tag}.pt', weights_only=False)
+    random.seed(rec['seed'])
+    W = O.vqkd_lazy_init(rec['x'], rec['W0'], rec['iters'])
+    close = torch.isclose(W, rec['W_init'], rtol=1e-5, atol=1e-6).all(1)
+    assert close.float().mean() >= (0.95 if tag == 'iters10' else 1.0)

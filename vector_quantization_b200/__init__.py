@@ -19,7 +19,8 @@ def build_quantizer(config, training: bool = True):
     """Build a quantizer from a reference-style `quantizer=dict(...)` config node
     (e.g. configs/vqgan/model.py:19-23 + configs/vq/*.py) and run its `init_weights`."""
     config = Config(config)
-    init_weights = config.pop('init_weights', Config())
+    init_weights = config.pop('init_weights', None) or Config()
+    config['init_weights'] = None          # deferred: the mode must be set before the callbacks' before_init_weights
     q = VQITQuantizerRegistry.build(config)
     q.train(training)
     q.init_weights(Config(init_weights))

@@ -10,7 +10,7 @@ import ctypes
 import os
 import pathlib
 import subprocess
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint,
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_ubyte, c_uint,
                     c_ulonglong, c_void_p)
 
 _HERE = pathlib.Path(__file__).resolve().parent
@@ -18,7 +18,7 @@ _HERE = pathlib.Path(__file__).resolve().parent
 LIB_PATH = pathlib.Path(os.environ['VQB200_LIB']) if os.environ.get('VQB200_LIB') else _HERE / 'libvqb200.so'
 CSRC = _HERE / 'csrc'
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 VQB_F32, VQB_BF16 = 0, 1
 BACKEND_TCGEN05, BACKEND_SIMT = 0, 1
 PLANES_F16 = 0x11     # VQB_PLANES_F16: one fp16 plane of a bf16 source
@@ -56,7 +56,7 @@ SIGNATURES = {
     'vqb_gather_ste_loss': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p,
                                     c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
-    'vqb_quantize_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int,
+    'vqb_quantize_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'vqb_l2norm_forward': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p]),
     'vqb_l2norm_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p]),
@@ -72,7 +72,21 @@ SIGNATURES = {
     'vqb_fsq_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, POINTER(FSQParams), c_void_p, c_int,
                                  c_void_p]),
     'vqb_fsq_decode': (c_int, [c_void_p, c_int64, POINTER(FSQParams), c_void_p, c_void_p]),
+    'vqb_comm_alloc': (c_int, [c_size_t, POINTER(c_void_p), POINTER(c_ubyte)]),
+    'vqb_comm_open': (c_int, [POINTER(c_ubyte), POINTER(c_void_p)]),
+    'vqb_comm_close': (c_int, [c_void_p]),
+    'vqb_comm_free': (c_int, [c_void_p]),
+    'vqb_comm_bind': (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int]),
+    'vqb_comm_kmeans_ema_update': (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_int64, c_int, c_float, c_float,
+                                           c_void_p]),
+    'vqb_comm_cvq_update': (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_size_t, c_int64,
+                                    c_int, c_float, c_float, c_float, c_void_p]),
+    'vqb_comm_allreduce_min_keys': (c_int, [c_void_p, c_int, c_int, c_size_t, c_int64, c_void_p]),
+    'vqb_comm_allreduce_sum_f32': (c_int, [c_void_p, c_int, c_int, c_size_t, c_int64, c_void_p]),
 }
+COMM_HEADER_BYTES = 512
+COMM_MAX_WORLD = 16
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 

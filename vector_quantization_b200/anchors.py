@@ -29,6 +29,7 @@ class BaseAnchor(nn.Module):
         self._sync = sync
 
     needs_columns = True   # gather() consumes the per-code nearest-token keys of the column arg-min pass
+    peer_exchange = False  # True: `gather_local` + the fused peer-memory exchange kernel replace gather()'s collectives
 
     @property
     def sync(self) -> bool:
@@ -41,6 +42,14 @@ class BaseAnchor(nn.Module):
 
 @AnchorRegistry.register_()
 class NearestAnchor(BaseAnchor):
+
+    peer_exchange = True
+
+    @torch.no_grad()
+    def gather_local(self, x, column_keys, n_local, out=None):
+        """This rank's nearest-token row per code (before any exchange every key points into the local tokens)."""
+        offset = parallel.rank() * n_local if self._sync else 0
+        return ops.gather_rows_by_key(x, column_keys, offset, out=out)
 
     @torch.no_grad()
     def gather(self, x, column_keys, n_local, num_codes=None):
@@ -111,5 +120,9 @@ class CachedAnchor(BaseAnchor):
         rows, indices = cached_rows_and_indices(x, num_codes, self.cache.to(x.device))
         keys = indices.to(device=rows.device, dtype=torch.int64).contiguous()   # row index in the low 32 key bits
         anchors = ops.gather_rows_by_key(rows.contiguous(), keys, 0)
-        self.register_buffer('_cache', anchors.detach().clone())
-        return anchors if self._sync else parallel.all_reduce_sum_(anchors)
+        if not self._sync:
+            parallel.all_reduce_sum_(anchors)
+        # the reference caches what BaseAnchor.forward returns, i.e. the rank-averaged anchors (anchors.py:161-164)
+        world = parallel.world_size()
+        self.register_buffer('_cache', anchors.detach().clone() if self._sync or world == 1 else anchors / world)
+        return anchors

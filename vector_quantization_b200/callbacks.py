@@ -44,6 +44,9 @@ class BaseCallback:
     # B200 path: set by callbacks whose `after_encode` consumes the per-code nearest token
     needs_column_nearest = False
     column_nearest_global = False
+    # B200 path: True if this callback's `after_encode` copes with RAW tokens when NormalizeCallback defers the
+    # token normalisation into the fused kernels (it must normalise whatever it reads from x itself)
+    accepts_raw_tokens = False
 
     def __init__(self, *args, **kwargs) -> None:
         super().__init__()
@@ -123,6 +126,14 @@ class ComposedCallback(BaseCallback):
     def column_nearest_global(self) -> bool:  # type: ignore[override]
         return any(c.column_nearest_global for c in self._callbacks)
 
+    def lazy_normalize_ok(self) -> bool:
+        """May NormalizeCallback hand RAW tokens down the pipeline (normalisation fused into the gather / backward
+        kernels)?  Only if every callback that reads x in `after_encode` declares that it copes; otherwise the
+        tokens are normalised up front, exactly like the reference (normalize.py:24), so that anchors, column
+        arg-mins and user callbacks see F.normalize(x)."""
+        return all(c.accepts_raw_tokens or type(c).after_encode is BaseCallback.after_encode
+                   for c in self._callbacks) and not self.needs_column_nearest
+
     def overrides(self, hook: str) -> bool:
         """True if any child customises `hook` (the fused decode/loss path checks this)."""
         return any(getattr(type(c), hook) is not getattr(BaseCallback, hook) for c in self._callbacks)
@@ -178,6 +189,31 @@ class UpdateMixin(BaseCallback):
         super().__init__(*args, **kwargs)
         if ema is not None:
             self._ema = ema
+        self._region = None      # parallel.PeerRegion once the multi-GPU exchange is set up; False = unavailable
+
+    def _peer_region(self, device: torch.device, layout) -> 'parallel.PeerRegion | None':
+        """The NVLink peer region of this quantizer (multi-GPU training only), created on first use — a collective
+        call: every rank reaches its first training forward.  `layout`: [(name, shape, dtype)], the codebook 'W'
+        first.  The codebook (and CVQ-VAE's `_probability`) are re-homed INTO the region, because the fused exchange
+        kernels publish the updated rows straight into every rank's copy (the reference rebinds `weight.data` on
+        every update as well, update.py:56)."""
+        if self._region is None:
+            self._region = False
+            if parallel.peer_comm_enabled(device):
+                nbytes = sum(((torch.Size(shape).numel() * torch.empty((), dtype=dt).element_size() + 511) // 512) * 512
+                             for _, shape, dt in layout)
+                region = parallel.try_peer_region(nbytes, device)
+                if region is not None:
+                    for name, shape, dt in layout:
+                        region.alloc(name, shape, dt)
+                    self._region = region
+        region = self._region or None
+        if region is not None:
+            w = self.vector_quantizer.embedding.weight
+            if w.data_ptr() != region.W.data_ptr():      # first use, or the module was moved / reloaded
+                region.W.copy_(w.data)
+                w.data = region.W
+        return region
 
     @classmethod
     def build_pre_hook(cls, config, registry, item):
@@ -235,39 +271,50 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
     """Per training step: counts + sums of normalised tokens per code (warp-aggregated scatter-add) ->
     ONE all-reduce of the fused [K*D | K] buffer -> centroid / normalise / EMA / normalise kernel."""
 
+    accepts_raw_tokens = True    # after_encode accumulates F.normalize(x) rows itself (scatter kernel flag)
+
     @torch.no_grad()
     def lazy_init_weights(self, config, x, memo) -> None:
-        """k-means init (callbacks.py:77-112): gather tokens to rank 0, seed with `random.sample`, `iters`
-        rounds of (normalise codebook -> assign -> centroids), broadcast.  No N x K matrix, no CPU offload."""
+        """k-means init (callbacks.py:77-112) on the kernels of the training step, DISTRIBUTED: the reference gathers
+        every rank's tokens to rank 0 (`distributed_cat`, :26-35), runs k-means there (CPU offload above 2^30
+        distance elements, :97-100) and broadcasts.  Here every rank keeps its tokens: rank 0 draws the K seed
+        indices into the concatenated token order with `random.sample` (the reference's RNG call, so equal seeds
+        give equal seeds) and broadcasts them; each round is one assignment + one statistics pass per rank and an
+        all-reduce of the [K*D | K] sums.  No N x K matrix, no gather, no offload; the result equals the
+        rank-0 k-means up to fp32 summation order."""
         vq = self.vector_quantizer
         if not vq.training:
             return
         x = x.detach().contiguous()
         world, rank = parallel.world_size(), parallel.rank()
-        if world > 1:
-            gathered = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
-            torch.distributed.gather(x, gathered, dst=0)
-            x = torch.cat(gathered) if rank == 0 else x.new_empty(0, x.shape[1])
+        n_local = x.shape[0]                       # equal on every rank (the reference's gather needs that too)
         W = vq.embedding.weight.data
         K = W.shape[0]
         iters = config.get('iters', 10)
-        if rank == 0:
-            if x.shape[0] < K:
-                W[:x.shape[0]] = x.float()
+        metric = vq.distance.metric
+        if n_local * world < K:
+            rows = parallel.all_gather_rows(x.float())            # fewer tokens than codes: raw tokens first (:91-92)
+            W[:rows.shape[0]] = rows
+        else:
+            xn = ops.l2norm_forward(x)
+            if rank == 0:
+                indices = torch.tensor(random.sample(range(n_local * world), K), dtype=torch.int64)
             else:
-                xn = ops.l2norm_forward(x)
-                indices = random.sample(range(xn.shape[0]), K)
-                W.copy_(ops.embedding_gather(xn, torch.tensor(indices, device=x.device)))
-                for _ in range(iters):
-                    keys = ops.new_keys(xn.shape[0], xn.device)
-                    book = Fq.pack_codebook(W, vq.distance.metric, precision=vq.precision, writeback_normalized=True)
-                    quant = ops.unpack_keys(Fq.nearest_code(xn, book, vq.distance.metric, precision=vq.precision,
-                                                            keys=keys, keys_are_reset=True))
-                    stats = ops.scatter_stats(xn, quant, K)
-                    ops.kmeans_ema_update(stats, W, 0.0)  # decay 0: W <- normalize(centroids | old row if unused)
-        if world > 1:
-            torch.distributed.broadcast(W, 0)
-        Fq.pack_codebook(W, vq.distance.metric, precision=vq.precision, writeback_normalized=True)
+                indices = torch.empty(K, dtype=torch.int64)
+            indices = indices.to(x.device)
+            if world > 1:
+                torch.distributed.broadcast(indices, 0)
+            # every rank contributes the seed rows it owns (zero rows elsewhere); the sum is x_cat[indices]
+            seeds = ops.gather_rows_by_key(xn, indices, rank * n_local)
+            W.copy_(parallel.all_reduce_sum_(seeds))
+            for _ in range(iters):
+                keys = ops.new_keys(n_local, xn.device)
+                book = Fq.pack_codebook(W, metric, precision=vq.precision, writeback_normalized=True)
+                quant = ops.unpack_keys(Fq.nearest_code(xn, book, metric, precision=vq.precision, keys=keys,
+                                                        keys_are_reset=True))
+                stats = parallel.all_reduce_sum_(ops.scatter_stats(xn, quant, K))
+                ops.kmeans_ema_update(stats, W, 0.0)  # decay 0: W <- normalize(centroids | old row if unused)
+        Fq.pack_codebook(W, metric, precision=vq.precision, writeback_normalized=True)
 
     @torch.no_grad()
     def after_encode(self, x, quant, memo):
@@ -276,7 +323,16 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
         if not vq.training:
             return quant
         W = vq.embedding.weight.data
-        stats = ops.scatter_stats(x.detach(), quant, W.shape[0], normalize_x=True)
+        K, D = W.shape
+        vq.protect_saved_codebook()
+        region = self._peer_region(x.device, [('W', (K, D), torch.float32), ('stats', (K * D + K,), torch.float32)])
+        if region is not None:
+            # per-rank partial sums straight into the peer region; ONE fused launch then reduces them over NVLink in
+            # fixed rank order, applies the k-means/EMA update and publishes the new rows to every replica
+            ops.scatter_stats(x.detach(), quant, K, normalize_x=True, out=region.stats.zero_())
+            ops.comm_kmeans_ema_update(region, K, D, self._ema.decay)
+            return quant
+        stats = ops.scatter_stats(x.detach(), quant, K, normalize_x=True)
         parallel.all_reduce_sum_(stats)
         ops.kmeans_ema_update(stats, W, self._ema.decay)
         return quant
@@ -323,14 +379,32 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
         if not vq.training:
             return quant
         W = vq.embedding.weight.data
-        K = W.shape[0]
+        K, D = W.shape
         x = x.detach().contiguous()
         N = x.shape[0]
+        vq.protect_saved_codebook()
+        col_keys = memo['encode'].get('column_keys')
+        if getattr(self._anchor, 'peer_exchange', False):
+            region = self._peer_region(x.device, [('W', (K, D), torch.float32), ('prob', (K,), torch.float32),
+                                                  ('counts', (K + 1,), torch.int64), ('anchors', (K, D), torch.float32),
+                                                  ('keys', (K,), torch.int64)])
+            if region is not None:
+                if self.probability.data_ptr() != region.prob.data_ptr():
+                    region.prob.copy_(self.probability)
+                    self.quantizer._buffers['_probability'] = region.prob
+                # per-rank partials in the peer region: usage counts, nearest-token rows (+ their keys when the
+                # anchors are global); ONE fused launch reduces them, updates `_probability` and blends the anchors
+                # into the codebook of every replica
+                ops.bincount_accumulate(quant, region.counts.zero_(), K, total_slot=True)
+                self._anchor.gather_local(x, col_keys, N, out=region.anchors)
+                if self._anchor.sync:
+                    region.keys.copy_(col_keys)
+                ops.comm_cvq_update(region, K, D, decay=self._ema.decay, eps=self._eps, minloc=self._anchor.sync)
+                return quant
         # [K counts | numel] in one int64 buffer -> one all-reduce (utils.py:35 does two)
         cnt = torch.zeros(K + 1, dtype=torch.int64, device=x.device)
         ops.bincount_accumulate(quant, cnt, K, total_slot=True)
         parallel.all_reduce_sum_(cnt)
-        col_keys = memo['encode'].get('column_keys')
         world = parallel.world_size()
         anchors = self._anchor.gather(x, col_keys, N, num_codes=K)
         scale = 1.0 if self._anchor.sync else 1.0 / world

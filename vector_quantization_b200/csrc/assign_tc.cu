@@ -748,10 +748,12 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
   if (nstages > 8) nstages = 8;
   const size_t smem_bytes = 1024 + a_resident + (size_t)nstages * stage_bytes + kStashBytes + kShareBytes + 2 * BN * sizeof(float) +
                             (2 * nstages + 8) * 8 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     VQB_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<BK, WHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int64_t total = ((a_rows + BM - 1) / BM) * ((b_rows + BN - 1) / BN);
   int grid = sm_count();

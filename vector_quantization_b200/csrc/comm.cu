@@ -1,0 +1,477 @@
+// Multi-GPU exchange steps of the hot path over NVLink peer memory (one process per GPU), FUSED with the
+// codebook update that consumes them: the kernel that reduces the per-rank statistics is the kernel that
+// applies the update and publishes the new codebook rows — no separate collective launch, no NCCL on the
+// data path.
+//
+// Every rank owns one "region" (cudaMalloc, exported with CUDA IPC) with the same layout; all ranks map all
+// regions.  Two-shot scheme: rank r owns the code rows [r*K/w, (r+1)*K/w): it reads that slice of every peer's
+// partial statistics over NVLink (fixed rank order => every replica gets bit-identical results), computes the
+// updated rows, and stores them into EVERY peer's codebook (all-gather by remote stores).  Two flag barriers
+// in peer memory bracket the exchange:
+//   A  "my partial statistics are complete"            (before anyone reads them)
+//   B  "I have read all I need and written all my rows" (before anyone consumes the codebook / reuses buffers)
+// Flags carry a monotonically increasing epoch, so they never need resetting and a CUDA graph can replay the
+// kernels.  All spins are bounded (trap after ~2 s): a missing peer is an error, never a hung GPU.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vqb {
+
+constexpr int kMaxWorld = VQB_COMM_MAX_WORLD;
+constexpr int kBatch = 8;   // peers whose loads are issued back to back (one NVLink round trip per batch)
+
+// Control block at offset 0 of every region; the peer table follows at byte 256.
+struct CommCtl {
+  uint32_t sig[2][kMaxWorld];  // sig[set][r] is written by rank r: the epoch it has reached on barrier `set`
+  uint32_t epoch;              // collectives completed by THIS rank
+  uint32_t ticket;             // blocks of the running collective that have finished (self-resetting)
+};
+static_assert(sizeof(CommCtl) <= 256, "control block");
+constexpr size_t kPeerTableOff = 256;
+static_assert(kPeerTableOff + kMaxWorld * sizeof(void*) <= VQB_COMM_HEADER_BYTES, "header");
+
+// per-block copy of the peer table (filled by comm_begin): peer pointers come from shared memory, not from a
+// dependent global load in front of every remote access
+__device__ __forceinline__ char** peer_table() {
+  __shared__ char* table[kMaxWorld];
+  return table;
+}
+
+struct Comm {
+  char* base;  // local region
+  int rank, world;
+  __device__ __forceinline__ char* peer(int r) const { return peer_table()[r]; }
+  __device__ __forceinline__ CommCtl* ctl() const { return reinterpret_cast<CommCtl*>(base); }
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// peer-memory loads: system scope, so that no non-coherent cache level can serve a stale line
+__device__ __forceinline__ float ld_peer(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Barrier A: block 0 announces "everything this rank wrote BEFORE this kernel is complete" (the kernel boundary /
+// griddepcontrol.wait made it visible); EVERY block then waits until all ranks have announced.
+__device__ __forceinline__ uint32_t comm_begin(const Comm& c) {
+  __shared__ uint32_t s_epoch;
+  CommCtl* ctl = c.ctl();
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(&ctl->epoch) + 1;
+  if (threadIdx.x < c.world) peer_table()[threadIdx.x] = reinterpret_cast<char* const*>(c.base + kPeerTableOff)[threadIdx.x];
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  if (blockIdx.x == 0 && threadIdx.x < c.world) {
+    __threadfence_system();
+    st_release_sys(&reinterpret_cast<CommCtl*>(c.peer(threadIdx.x))->sig[0][c.rank], e);
+  }
+  if (threadIdx.x < c.world) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(&ctl->sig[0][threadIdx.x]) - e) < 0) {
+      if (clock64() - t0 > 4000000000ll) {
+        printf("vqb comm: rank %d timed out waiting for rank %d (barrier A, epoch %u)\n", c.rank, (int)threadIdx.x, e);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  return e;
+}
+
+// Barrier B: every block calls this after its last peer access.  The last block to arrive announces "this rank
+// is done" to all peers, waits for all of them, and retires the epoch; the other blocks simply exit (the kernel
+// boundary orders everything that follows behind the last block).
+__device__ __forceinline__ void comm_end(const Comm& c, uint32_t e) {
+  __shared__ bool s_last;
+  CommCtl* ctl = c.ctl();
+  __threadfence_system();   // my remote stores are performed before my arrival is counted
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(&ctl->ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();   // acquire side of the ticket: the other blocks' stores precede the announcement
+  if (threadIdx.x < c.world) {
+    st_release_sys(&reinterpret_cast<CommCtl*>(c.peer(threadIdx.x))->sig[1][c.rank], e);
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(&ctl->sig[1][threadIdx.x]) - e) < 0) {
+      if (clock64() - t0 > 4000000000ll) {
+        printf("vqb comm: rank %d timed out waiting for rank %d (barrier B, epoch %u)\n", c.rank, (int)threadIdx.x, e);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctl->ticket = 0;
+    *reinterpret_cast<volatile uint32_t*>(&ctl->epoch) = e;
+    __threadfence();
+  }
+}
+
+__device__ __forceinline__ void slice_of(int64_t total, const Comm& c, int64_t& lo, int64_t& hi) {
+  const int64_t per = (total + c.world - 1) / c.world;
+  lo = per * c.rank;
+  if (lo > total) lo = total;
+  hi = lo + per;
+  if (hi > total) hi = total;
+}
+
+// ---- VQ-KD: all-reduce(SUM) of [K*D sums | K counts] fused with centroid / normalise / EMA / normalise --------
+// vq/algorithms/vqkd/quantizers/callbacks.py:60-71,126-128,73-75 (the all_reduce at :63-64 and vq/utils.py:35)
+// G lanes per code row, NPL elements per lane (d = lane + j*G): the reduced sums stay in registers, so every
+// remote element crosses NVLink exactly once.
+template <int G, int NPL>
+__global__ void __launch_bounds__(256) comm_kmeans_ema_kernel(Comm c, size_t stats_off, size_t w_off, int64_t K, int D,
+                                                              float decay, float omd) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint32_t e = comm_begin(c);
+  const int lane = threadIdx.x % G;
+  const int64_t rows_per_block = blockDim.x / G;
+  int64_t lo, hi;
+  slice_of(K, c, lo, hi);
+  const float* __restrict__ Wl = reinterpret_cast<const float*>(c.base + w_off);
+  for (int64_t base = lo + blockIdx.x * rows_per_block; base < hi; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t k_raw = base + threadIdx.x / G;
+    const bool valid = k_raw < hi;
+    const int64_t k = valid ? k_raw : hi - 1;
+    float cnt = 0.f, s[NPL], w[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) s[j] = 0.f;
+    constexpr int B = NPL <= 4 ? kBatch : (NPL <= 8 ? 4 : (NPL <= 16 ? 2 : 1));   // B * NPL loads in flight per lane
+    for (int r0 = 0; r0 < c.world; r0 += B) {        // all loads of a batch are issued before the first add
+      float vc[B], v[B][NPL];
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const bool on = r0 + b < c.world;
+        const float* __restrict__ sr = reinterpret_cast<const float*>(c.peer(on ? r0 + b : c.rank) + stats_off);
+        vc[b] = on ? ld_peer(sr + K * (int64_t)D + k) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const int d = lane + j * G;
+          v[b][j] = (on && d < D) ? ld_peer(sr + k * D + d) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < B; ++b) {                  // fixed rank order: every replica computes bit-identical sums
+        cnt += vc[b];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) s[j] += v[b][j];
+      }
+    }
+    const bool occurred = cnt > 0.f;
+    const float den = fmaxf(cnt, 1.f);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int d = lane + j * G;
+      w[j] = d < D ? Wl[k * D + d] : 0.f;
+      s[j] = d < D ? (occurred ? __fdiv_rn(s[j], den) : w[j]) : 0.f;   // centroid, or the old row of an unused code
+      ss = fmaf(s[j], s[j], ss);
+    }
+    ss = group_sum<G>(ss);
+    const float dn = fmaxf(sqrtf(ss), kNormEps);
+    float ss2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      s[j] = __fadd_rn(__fmul_rn(w[j], decay), __fmul_rn(__fdiv_rn(s[j], dn), omd));
+      ss2 = fmaf(s[j], s[j], ss2);
+    }
+    ss2 = group_sum<G>(ss2);
+    const float dn2 = fmaxf(sqrtf(ss2), kNormEps);
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int d = lane + j * G;
+      if (valid && d < D) {
+        const float out = __fdiv_rn(s[j], dn2);
+        for (int r = 0; r < c.world; ++r) reinterpret_cast<float*>(c.peer(r) + w_off)[k * D + d] = out;
+      }
+    }
+  }
+  comm_end(c, e);
+}
+
+// ---- CVQ-VAE: all-reduce of the usage counts + anchors fused with the probability EMA and the anchor blend ---
+// vq/algorithms/cvqvae/quantizer_callback.py:88-103, anchors.py:50-67.
+//   keys_off == SIZE_MAX (sync=False): anchors = mean over ranks of the per-rank nearest-token rows (anchors.py:64-67)
+//   otherwise (sync=True): every rank holds its best (distance, global token index) key per code and that token's
+//   row; the global nearest is the minimum key, its row is taken from the rank that owns it (anchors.py:50-57).
+__global__ void __launch_bounds__(256) comm_cvq_update_kernel(Comm c, size_t counts_off, size_t anchors_off, size_t keys_off,
+                                                              size_t w_off, size_t prob_off, int64_t K, int D, float decay,
+                                                              float omd, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint32_t e = comm_begin(c);
+  int64_t lo, hi;
+  slice_of(K, c, lo, hi);
+  long long total_i = 0;
+  for (int r0 = 0; r0 < c.world; r0 += kBatch) {
+    unsigned long long v[kBatch];
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b)
+      v[b] = r0 + b < c.world ? ld_peer_u64(reinterpret_cast<const unsigned long long*>(c.peer(r0 + b) + counts_off) + K) : 0ull;
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) total_i += (long long)v[b];
+  }
+  const float total = (float)total_i;
+  const bool minloc = keys_off != (size_t)-1;
+  const float anchor_scale = minloc ? 1.f : 1.f / (float)c.world;
+  const float* __restrict__ Wl = reinterpret_cast<const float*>(c.base + w_off);
+  const float* __restrict__ Pl = reinterpret_cast<const float*>(c.base + prob_off);
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = lo + warp; k < hi; k += nwarps) {
+    long long cnt = 0;
+    unsigned long long best = ~0ull;
+    int winner = -1;
+    for (int r0 = 0; r0 < c.world; r0 += kBatch) {
+      unsigned long long v[kBatch], kk[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const bool on = r0 + b < c.world;
+        v[b] = on ? ld_peer_u64(reinterpret_cast<const unsigned long long*>(c.peer(r0 + b) + counts_off) + k) : 0ull;
+        kk[b] = (on && minloc) ? ld_peer_u64(reinterpret_cast<const unsigned long long*>(c.peer(r0 + b) + keys_off) + k) : ~0ull;
+      }
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        cnt += (long long)v[b];
+        if (kk[b] < best) { best = kk[b]; winner = r0 + b; }
+      }
+    }
+    const float freq = __fdiv_rn((float)cnt, total);
+    const float p = __fadd_rn(__fmul_rn(Pl[k], decay), __fmul_rn(freq, omd));
+    float t = __fmul_rn(__fmul_rn(-p, (float)K), 10.f);
+    t = __fsub_rn(__fdiv_rn(t, omd), eps);
+    const float dec = __fsub_rn(1.f, expf(t));
+    const float omdec = __fsub_rn(1.f, dec);
+    __syncwarp();
+    if (lane == 0)
+      for (int r = 0; r < c.world; ++r) reinterpret_cast<float*>(c.peer(r) + prob_off)[k] = p;
+    for (int d = lane; d < D; d += 32) {
+      float a = 0.f;
+      if (minloc) {
+        if (winner >= 0) a = ld_peer(reinterpret_cast<const float*>(c.peer(winner) + anchors_off) + k * D + d);
+      } else {
+        for (int r0 = 0; r0 < c.world; r0 += kBatch) {
+          float v[kBatch];
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b)
+            v[b] = r0 + b < c.world ? ld_peer(reinterpret_cast<const float*>(c.peer(r0 + b) + anchors_off) + k * D + d) : 0.f;
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) a += v[b];
+        }
+      }
+      a *= anchor_scale;
+      const float out = __fadd_rn(__fmul_rn(Wl[k * D + d], dec), __fmul_rn(a, omdec));
+      for (int r = 0; r < c.world; ++r) reinterpret_cast<float*>(c.peer(r) + w_off)[k * D + d] = out;
+    }
+  }
+  comm_end(c, e);
+}
+
+// ---- packed (score, index) min-loc all-reduce over [n] keys (codebook shards) -------------------
+__global__ void __launch_bounds__(256) comm_min_keys_kernel(Comm c, size_t keys_off, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint32_t e = comm_begin(c);
+  int64_t lo, hi;
+  slice_of(n, c, lo, hi);
+  for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long m = ~0ull;
+    for (int r0 = 0; r0 < c.world; r0 += kBatch) {
+      unsigned long long v[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b)
+        v[b] = r0 + b < c.world ? ld_peer_u64(reinterpret_cast<const unsigned long long*>(c.peer(r0 + b) + keys_off) + i) : ~0ull;
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) m = v[b] < m ? v[b] : m;
+    }
+    for (int r = 0; r < c.world; ++r) reinterpret_cast<unsigned long long*>(c.peer(r) + keys_off)[i] = m;
+  }
+  comm_end(c, e);
+}
+
+// ---- plain fp32 SUM all-reduce (k-means init rounds, CachedAnchor means) ---------------------------------------
+__global__ void __launch_bounds__(256) comm_sum_f32_kernel(Comm c, size_t off, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const uint32_t e = comm_begin(c);
+  int64_t lo, hi;
+  slice_of((n + 3) / 4, c, lo, hi);   // in units of float4 (the buffer is padded to 16 B by the host layer)
+  for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = 0; r0 < c.world; r0 += kBatch) {
+      float4 v[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b)
+        v[b] = r0 + b < c.world ? ld_peer4(reinterpret_cast<const float*>(c.peer(r0 + b) + off) + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) { s.x += v[b].x; s.y += v[b].y; s.z += v[b].z; s.w += v[b].w; }
+    }
+    for (int r = 0; r < c.world; ++r) reinterpret_cast<float4*>(c.peer(r) + off)[i] = s;
+  }
+  comm_end(c, e);
+}
+
+static inline int pow2_lanes_c(int n) {
+  int g = 1;
+  while (g < 32 && g < n) g <<= 1;
+  return g;
+}
+static inline int blocks_for(int64_t items, int items_per_block) {
+  int64_t b = (items + items_per_block - 1) / items_per_block;
+  const int64_t cap = sm_count();       // one resident block per SM is plenty for a latency-bound exchange
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+#define VQB_COMM_ARGS_OK(name)                                                                    \
+  VQB_REQUIRE(region != nullptr, name ": null region");                                           \
+  VQB_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, name ": bad rank/world")
+
+extern "C" {
+
+int vqb_comm_alloc(size_t bytes, void** region, unsigned char* handle_out) {
+  VQB_REQUIRE(region && handle_out && bytes >= VQB_COMM_HEADER_BYTES, "vqb_comm_alloc: bad arguments");
+  void* p = nullptr;
+  VQB_CUDA_OK(cudaMalloc(&p, bytes));
+  VQB_CUDA_OK(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == VQB_IPC_HANDLE_BYTES, "ipc handle size");
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return VQB_ERR_CUDA;
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  VQB_CUDA_OK(cudaDeviceSynchronize());
+  *region = p;
+  return VQB_OK;
+}
+
+int vqb_comm_open(const unsigned char* handle, void** peer_region) {
+  VQB_REQUIRE(handle && peer_region, "vqb_comm_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  VQB_CUDA_OK(cudaIpcOpenMemHandle(peer_region, h, cudaIpcMemLazyEnablePeerAccess));
+  return VQB_OK;
+}
+
+int vqb_comm_close(void* peer_region) {
+  if (peer_region) VQB_CUDA_OK(cudaIpcCloseMemHandle(peer_region));
+  return VQB_OK;
+}
+
+int vqb_comm_free(void* region) {
+  if (region) VQB_CUDA_OK(cudaFree(region));
+  return VQB_OK;
+}
+
+int vqb_comm_bind(void* region, const void* const* peer_regions_host, int rank, int world) {
+  VQB_COMM_ARGS_OK("vqb_comm_bind");
+  VQB_REQUIRE(peer_regions_host != nullptr && peer_regions_host[rank] == region, "vqb_comm_bind: peer table must hold the local region at [rank]");
+  VQB_CUDA_OK(cudaMemcpy(static_cast<char*>(region) + kPeerTableOff, peer_regions_host, sizeof(void*) * world,
+                         cudaMemcpyHostToDevice));
+  VQB_CUDA_OK(cudaDeviceSynchronize());
+  return VQB_OK;
+}
+
+int vqb_comm_kmeans_ema_update(void* region, int rank, int world, size_t stats_off, size_t w_off, int64_t K, int D,
+                               float decay, float one_minus_decay, void* stream) {
+  VQB_COMM_ARGS_OK("vqb_comm_kmeans_ema_update");
+  VQB_REQUIRE(K >= 1 && D >= 1 && stats_off % 16 == 0 && w_off % 16 == 0, "vqb_comm_kmeans_ema_update: bad shape/offset");
+  Comm c{static_cast<char*>(region), rank, world};
+  VQB_REQUIRE(D <= 1024, "vqb_comm_kmeans_ema_update: D <= 1024");
+  const int g = pow2_lanes_c(D);           // one lane per element up to 32: the exchange is latency-bound, go wide
+  int npl = 1;
+  while (g * npl < D) npl <<= 1;
+  const int blocks = blocks_for((K + world - 1) / world, 256 / g);
+#define LAUNCH(G_, NPL_)                                                                                                   \
+  VQB_CUDA_OK(launch_pdl(comm_kmeans_ema_kernel<G_, NPL_>, blocks, 256, 0, (cudaStream_t)stream, c, stats_off, w_off, K, D, \
+                         decay, one_minus_decay))
+  if (npl == 1) {
+    switch (g) {
+      case 1: LAUNCH(1, 1); break;
+      case 2: LAUNCH(2, 1); break;
+      case 4: LAUNCH(4, 1); break;
+      case 8: LAUNCH(8, 1); break;
+      case 16: LAUNCH(16, 1); break;
+      default: LAUNCH(32, 1); break;
+    }
+  } else {
+    switch (npl) {
+      case 2: LAUNCH(32, 2); break;
+      case 4: LAUNCH(32, 4); break;
+      case 8: LAUNCH(32, 8); break;
+      case 16: LAUNCH(32, 16); break;
+      default: LAUNCH(32, 32); break;
+    }
+  }
+#undef LAUNCH
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_comm_cvq_update(void* region, int rank, int world, size_t counts_off, size_t anchors_off, size_t keys_off,
+                        size_t w_off, size_t prob_off, int64_t K, int D, float decay, float one_minus_decay, float eps,
+                        void* stream) {
+  VQB_COMM_ARGS_OK("vqb_comm_cvq_update");
+  VQB_REQUIRE(K >= 1 && D >= 1, "vqb_comm_cvq_update: bad shape");
+  Comm c{static_cast<char*>(region), rank, world};
+  const int blocks = blocks_for((K + world - 1) / world, 8);   // one warp per code row
+  VQB_CUDA_OK(launch_pdl(comm_cvq_update_kernel, blocks, 256, 0, (cudaStream_t)stream, c, counts_off, anchors_off, keys_off,
+                         w_off, prob_off, K, D, decay, one_minus_decay, eps));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_comm_allreduce_min_keys(void* region, int rank, int world, size_t keys_off, int64_t n, void* stream) {
+  VQB_COMM_ARGS_OK("vqb_comm_allreduce_min_keys");
+  VQB_REQUIRE(n >= 1 && keys_off % 8 == 0, "vqb_comm_allreduce_min_keys: bad size/offset");
+  Comm c{static_cast<char*>(region), rank, world};
+  const int blocks = blocks_for((n + world - 1) / world, 256);
+  VQB_CUDA_OK(launch_pdl(comm_min_keys_kernel, blocks, 256, 0, (cudaStream_t)stream, c, keys_off, n));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_comm_allreduce_sum_f32(void* region, int rank, int world, size_t off, int64_t n, void* stream) {
+  VQB_COMM_ARGS_OK("vqb_comm_allreduce_sum_f32");
+  VQB_REQUIRE(n >= 1 && off % 16 == 0, "vqb_comm_allreduce_sum_f32: bad size/offset");
+  Comm c{static_cast<char*>(region), rank, world};
+  const int blocks = blocks_for(((n + 3) / 4 + world - 1) / world, 256);
+  VQB_CUDA_OK(launch_pdl(comm_sum_f32_kernel, blocks, 256, 0, (cudaStream_t)stream, c, off, n));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+}  // extern "C"

@@ -200,9 +200,9 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
 //   g_y = g_zste + c_cm (y - z) + J_n(y)^T [c_cmn (u - v)]         c_* = g4[*] * 2 / (N D)
 //   g_z = c_cb (z - y) + J_n(z)^T [c_cbn (v - u)]                   -> atomically added to gW[q]
 //   g_x_in = J_n(x_in)^T g_y  when normalize_x, else g_y            J_n(a)^T g = (g - (g.n(a)) n(a)) / |a|
-template <typename TX, int G, int V, int NV>
+template <typename TX, typename TG, int G, int V, int NV>
 __global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
-    const float* __restrict__ gz, const TX* __restrict__ x, int normalize_x, const float* __restrict__ W, int64_t K,
+    const TG* __restrict__ gz, const TX* __restrict__ x, int normalize_x, const float* __restrict__ W, int64_t K,
     const int64_t* __restrict__ quant, int64_t N, int D, const float* __restrict__ g_cb,
     const float* __restrict__ g_cm, const float* __restrict__ g_cbn, const float* __restrict__ g_cmn, int want_norm,
     TX* __restrict__ gx, float* __restrict__ gW) {
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
       if (d0 < D) {
         load_slice<TX, V>(xrow, d0, D, yr[it]);
         load_slice<float, V>(wrow, d0, D, wr[it]);
-        load_slice<float, V>(gz + n * D, d0, D, gr[it]);
+        load_slice<TG, V>(gz + n * D, d0, D, gr[it]);
       } else {
 #pragma unroll
         for (int i = 0; i < V; ++i) yr[it][i] = wr[it][i] = gr[it][i] = 0.f;
@@ -428,7 +428,7 @@ int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D, int normal
   return VQB_OK;
 }
 
-int vqb_quantize_backward(const float* gz, const void* x, int x_dtype, int normalize_x, const float* W, int64_t K,
+int vqb_quantize_backward(const void* gz, int g_dtype, const void* x, int x_dtype, int normalize_x, const float* W, int64_t K,
                           const int64_t* quant, int64_t N, int D, const float* g_cb, const float* g_cm,
                           const float* g_cbn, const float* g_cmn, int want_norm, void* gx, float* gW, void* stream) {
   VQB_REQUIRE(gz && x && W && quant && gx, "vqb_quantize_backward: null pointer");
@@ -438,13 +438,17 @@ int vqb_quantize_backward(const float* gz, const void* x, int x_dtype, int norma
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = grid_for(N, 256 / geom.G);
   bool launched = false;
-  if (x_dtype == VQB_F32) {
-    VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<float, G, V, NV>, blocks, 256, 0, st,
-        gz, (const float*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm, (float*)gx, gW)))
-  } else if (x_dtype == VQB_BF16) {
-    VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<__nv_bfloat16, G, V, NV>, blocks, 256, 0, st,
-        gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm,
+  if (x_dtype == VQB_F32 && g_dtype == VQB_F32) {
+    VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<float, float, G, V, NV>, blocks, 256, 0, st,
+        (const float*)gz, (const float*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm, (float*)gx, gW)))
+  } else if (x_dtype == VQB_BF16 && g_dtype == VQB_F32) {
+    VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<__nv_bfloat16, float, G, V, NV>, blocks, 256, 0, st,
+        (const float*)gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm,
         (__nv_bfloat16*)gx, gW)))
+  } else if (x_dtype == VQB_BF16 && g_dtype == VQB_BF16) {   // bf16 upstream gradient (autocast training): read as is
+    VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<__nv_bfloat16, __nv_bfloat16, G, V, NV>, blocks, 256, 0, st,
+        (const __nv_bfloat16*)gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn,
+        want_norm, (__nv_bfloat16*)gx, gW)))
   }
   VQB_REQUIRE(launched, "vqb_quantize_backward: unsupported dtype/geometry");
   VQB_LAUNCH_OK();

@@ -157,19 +157,32 @@ def rows_to_nchw(z: torch.Tensor, b: int, c: int, h: int, w: int) -> torch.Tenso
     return _TransposeLast2.apply(z.contiguous().view(b, h * w, c)).view(b, c, h, w)
 
 
+class CodebookRef:
+    """What a pending backward holds instead of the codebook tensor: the codebook is updated IN PLACE by the
+    update kernels (the reference rebinds `weight.data` to a new tensor, update.py:56, so its saved tensors stay
+    intact).  `VectorQuantizer.protect_saved_codebook()` swaps in a private copy (copy-on-write) right before an
+    in-place update if a backward that saved the live codebook is still pending — e.g. two training forwards
+    before the first backward — and costs nothing in the usual forward/backward alternation."""
+    __slots__ = ('tensor', '__weakref__')
+
+    def __init__(self, tensor: torch.Tensor) -> None:
+        self.tensor = tensor
+
+
 class _QuantizeSTELoss(torch.autograd.Function):
     """Outputs the four MSE terms as SEPARATE 0-dim tensors so that autograd hands their upstream gradients
     back as four device scalars (no select_backward / stack kernels between the loss and our backward)."""
 
     @staticmethod
-    def forward(ctx, x, W, index, index_is_keys, key_offset, normalize_x, want_norm):
+    def forward(ctx, x, W, index, index_is_keys, key_offset, normalize_x, want_norm, ref):
         z, mse4, quant, xn = ops.gather_ste_loss(
             x, W, quant=None if index_is_keys else index, keys=index if index_is_keys else None,
             key_offset=key_offset, normalize_x=normalize_x, want_norm=want_norm, want_quant=index_is_keys,
             want_xnorm=normalize_x)
         if quant is None:
             quant = index
-        ctx.save_for_backward(x, W, quant)
+        ctx.save_for_backward(x, quant)
+        ctx.codebook = ref if ref is not None else CodebookRef(W.detach())
         ctx.cfg = (normalize_x, want_norm)
         ctx.set_materialize_grads(False)   # unused outputs arrive as None instead of freshly zero-filled tensors
         if xn is None:
@@ -180,24 +193,27 @@ class _QuantizeSTELoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gz, g0, g1, g2, g3, _gq, _gxn):
-        x, W, quant = ctx.saved_tensors
+        x, quant = ctx.saved_tensors
+        W = ctx.codebook.tensor
         normalize_x, want_norm = ctx.cfg
         if gz is None:
             gz = torch.zeros(x.shape, dtype=torch.float32, device=x.device)
         g4 = [None if g is None else g.contiguous().float() for g in (g0, g1, g2, g3)]
-        gx, gW = ops.quantize_backward(gz.contiguous().float(), x, W, quant, g4, normalize_x=normalize_x,
+        gx, gW = ops.quantize_backward(gz.contiguous(), x, W, quant, g4, normalize_x=normalize_x,
                                        want_norm=want_norm, need_gW=ctx.needs_input_grad[1])
-        return (gx if ctx.needs_input_grad[0] else None), gW, None, None, None, None, None
+        return (gx if ctx.needs_input_grad[0] else None), gW, None, None, None, None, None, None
 
 
 def quantize_ste_loss(x: torch.Tensor, W: torch.Tensor, index: torch.Tensor, want_norm: bool, *,
-                      index_is_keys: bool = False, key_offset: int = 0, normalize_x: bool = False):
+                      index_is_keys: bool = False, key_offset: int = 0, normalize_x: bool = False,
+                      codebook_ref: CodebookRef | None = None):
     """One kernel: [x' = F.normalize(x)] -> gather W[q] -> straight-through -> MSE terms.
     -> (z_ste [N,D] fp32: value x' + (W[q] - x'), gradient to x only;
         mse4 = (codebook, commitment, codebook(norm), commitment(norm)) as four 0-dim tensors;
         quant int64 [N] (unpacked from the keys when index_is_keys);  x' (detached; x itself if not normalised))"""
     z, m0, m1, m2, m3, quant, xn = _QuantizeSTELoss.apply(x.contiguous(), W, index, bool(index_is_keys),
-                                                          int(key_offset), bool(normalize_x), bool(want_norm))
+                                                          int(key_offset), bool(normalize_x), bool(want_norm),
+                                                          codebook_ref)
     return z, (m0, m1, m2, m3), quant, xn
 
 

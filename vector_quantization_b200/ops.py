@@ -19,7 +19,8 @@ __all__ = [
     'Operand', 'as_operand', 'pack_rows', 'assign', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
     'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
-    'fsq_decode', 'transpose_last2', 'compact_tokens', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
+    'fsq_decode', 'transpose_last2', 'compact_tokens', 'comm_kmeans_ema_update', 'comm_cvq_update',
+    'comm_allreduce_min_keys', 'comm_allreduce_sum_f32', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
 ]
 
 
@@ -31,7 +32,9 @@ def _dt(t: torch.Tensor) -> int:
     raise TypeError(f'vector_quantization_b200 supports float32 and bfloat16 tensors, got {t.dtype}')
 
 
-def _cuda(*ts: torch.Tensor | None) -> None:
+def _cuda(*ts: torch.Tensor | None) -> torch.device:
+    """Checks that every tensor is a contiguous CUDA tensor of ONE device and returns that device."""
+    dev = None
     for t in ts:
         if t is None:
             continue
@@ -39,30 +42,43 @@ def _cuda(*ts: torch.Tensor | None) -> None:
             raise _lib.VQBError('vector_quantization_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
         if not t.is_contiguous():
             raise ValueError('expected a contiguous tensor')
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f'all tensors of one call must live on the same device, got {dev} and {t.device}')
+    return dev
 
 
 def _p(t: torch.Tensor | None):
     return c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+class _StreamArg:
+    """Placeholder for the `stream` argument: `_call` substitutes the current stream of the tensors' device."""
+
+
+_S = _StreamArg()
 
 
 LAUNCHES = 0     # kernels launched through the C-ABI (bench.py reports it as gpu_launches)
 PROFILE = None   # when a list: (name, start_event, end_event) per launch, on the launching stream
 
 
-def _call(name: str, fn, *args) -> None:
+def _call(name: str, fn, dev: torch.device, *args) -> None:
+    """One C-ABI launch on the current stream of `dev`, with `dev` as the current CUDA device for the duration of
+    the call (the library launches on, and encodes TMA descriptors for, the current device)."""
     global LAUNCHES
-    if PROFILE is not None:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        status = fn(*args)
-        b.record()
-        PROFILE.append((name, a, b))
-    else:
-        status = fn(*args)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        args = tuple(c_void_p(stream.cuda_stream) if a is _S else a for a in args)
+        if PROFILE is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            status = fn(*args)
+            b.record(stream)
+            PROFILE.append((name, a, b))
+        else:
+            status = fn(*args)
     LAUNCHES += 1
     check(status, name)
 
@@ -102,7 +118,7 @@ def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None 
     fmt='f16x2': the two-plane fp16 (hi, lo * 2^11) pair of NORMALISED rows: 22 significant bits, two MMA terms.
     fmt='f16':  one fp16 plane of un-normalised bf16 rows (the partner of an 'f16x2' operand)."""
     lib = _lib.load()
-    _cuda(src, writeback, reset_keys)
+    dev = _cuda(src, writeback, reset_keys)
     assert src.dim() == 2
     rows, D = src.shape
     if fmt == 'f16x2':
@@ -124,31 +140,31 @@ def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None 
     h = torch.empty((rows_pad,), dtype=torch.float32, device=src.device) if want_half_sqnorm else None
     if writeback is not None:
         assert writeback.dtype == torch.float32 and writeback.shape == src.shape
-    _call('vqb_pack_rows', lib.vqb_pack_rows, _p(src), _dt(src), rows, D, int(normalize), code, _p(dst), _p(h),
-          _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _stream())
+    _call('vqb_pack_rows', lib.vqb_pack_rows, dev, _p(src), _dt(src), rows, D, int(normalize), code, _p(dst), _p(h),
+          _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _S)
     return Operand(dst, rows, D, planes, h, fmt=fmt)
 
 
 def transpose_last2(src: torch.Tensor) -> torch.Tensor:
     """[B, R, C] -> [B, C, R] contiguous (vqb_transpose_last2): the caller's NCHW <-> token-major rearranges."""
     lib = _lib.load()
-    _cuda(src)
+    dev = _cuda(src)
     assert src.dim() == 3 and src.element_size() in (2, 4, 8)
     B, R, C = src.shape
     dst = torch.empty((B, C, R), dtype=src.dtype, device=src.device)
-    _call('vqb_transpose_last2', lib.vqb_transpose_last2, _p(src), src.element_size(), B, R, C, _p(dst), _stream())
+    _call('vqb_transpose_last2', lib.vqb_transpose_last2, dev, _p(src), src.element_size(), B, R, C, _p(dst), _S)
     return dst
 
 
 def compact_tokens(keys: torch.Tensor, codebook_size: int, index_offset: int = 0) -> torch.Tensor:
     """Packed keys -> compact token ids: uint16 for codebooks of at most 65 536 codes, int32 otherwise."""
     lib = _lib.load()
-    _cuda(keys)
+    dev = _cuda(keys)
     assert keys.dtype == torch.int64
     small = codebook_size <= 65536
     out = torch.empty(keys.shape, dtype=torch.uint16 if small else torch.int32, device=keys.device)
-    _call('vqb_compact_tokens', lib.vqb_compact_tokens, _p(keys), keys.numel(), index_offset, _p(out), 2 if small else 4,
-          _stream())
+    _call('vqb_compact_tokens', lib.vqb_compact_tokens, dev, _p(keys), keys.numel(), index_offset, _p(out), 2 if small else 4,
+          _S)
     return out
 
 
@@ -162,7 +178,7 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
     """keys[i] = min(keys[i], key(argmax_j score)), score = <a_i,b_j> - 0.5|b_j|^2 (l2), <a_i,b_j> * (1/|b_j|)
     (scale_columns: b holds RAW rows + `inv_norm`), or <a_i,b_j>."""
     lib = _lib.load()
-    _cuda(a.planes, b.planes, keys)
+    dev = _cuda(a.planes, b.planes, keys)
     assert a.dim == b.dim and keys.dtype == torch.int64 and keys.numel() >= a.rows
     side, mode = None, 0
     if l2:
@@ -171,35 +187,35 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
     elif scale_columns:
         assert b.inv_norm is not None
         side, mode = b.inv_norm, 2
-    _call('vqb_assign', lib.vqb_assign, _p(a.planes), a.abi_planes, a.rows, a.plane_rows, _p(b.planes), b.abi_planes, b.rows,
-          b.plane_rows, a.dim, _p(side), mode, index_offset, _p(keys), backend, _stream())
+    _call('vqb_assign', lib.vqb_assign, dev, _p(a.planes), a.abi_planes, a.rows, a.plane_rows, _p(b.planes), b.abi_planes, b.rows,
+          b.plane_rows, a.dim, _p(side), mode, index_offset, _p(keys), backend, _S)
     return keys
 
 
 def row_inv_norm(x: torch.Tensor, f16_rows: bool = False) -> torch.Tensor:
     """1 / max(|x_r|, eps) per row (zero in the operand padding); f16_rows: for rows packed with fmt='f16'."""
     lib = _lib.load()
-    _cuda(x)
+    dev = _cuda(x)
     rows, D = x.shape
     out = torch.empty((operand_shape(rows, D)[0],), dtype=torch.float32, device=x.device)
-    _call('vqb_row_inv_norm', lib.vqb_row_inv_norm, _p(x), _dt(x), rows, D, int(f16_rows), _p(out), _stream())
+    _call('vqb_row_inv_norm', lib.vqb_row_inv_norm, dev, _p(x), _dt(x), rows, D, int(f16_rows), _p(out), _S)
     return out
 
 
 def unpack_keys(keys: torch.Tensor, index_offset: int = 0, want_score: bool = False):
     lib = _lib.load()
-    _cuda(keys)
+    dev = _cuda(keys)
     n = keys.numel()
     idx = torch.empty((n,), dtype=torch.int64, device=keys.device)
     score = torch.empty((n,), dtype=torch.float32, device=keys.device) if want_score else None
-    _call('vqb_unpack_keys', lib.vqb_unpack_keys, _p(keys), n, index_offset, _p(idx), _p(score), _stream())
+    _call('vqb_unpack_keys', lib.vqb_unpack_keys, dev, _p(keys), n, index_offset, _p(idx), _p(score), _S)
     return (idx, score) if want_score else idx
 
 
 def keys_flip_sign(keys: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
-    _cuda(keys)
-    _call('vqb_keys_flip_sign', lib.vqb_keys_flip_sign, _p(keys), keys.numel(), _stream())
+    dev = _cuda(keys)
+    _call('vqb_keys_flip_sign', lib.vqb_keys_flip_sign, dev, _p(keys), keys.numel(), _S)
     return keys
 
 
@@ -207,7 +223,9 @@ _WS: dict = {}
 
 
 def _loss_ws(device):
-    key = (device.type, device.index)
+    """Partials + self-resetting ticket of the deterministic loss reduction: one pair per (device, stream), so
+    forwards issued concurrently on different streams of a GPU never share the ticket."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     if key not in _WS:
         lib = _lib.load()
         _WS[key] = (torch.empty((int(lib.vqb_loss_partials_count()),), dtype=torch.float32, device=device),
@@ -230,7 +248,7 @@ def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, *, quant: torch.Tensor | N
     """Fused gather + STE + loss (+ token normalisation, + key unpack) — see vqb_gather_ste_loss.
     -> (z_ste [N,D] fp32, mse4 [4], quant int64 [N] | None, x_normalised [N,D] fp32 | None)"""
     lib = _lib.load()
-    _cuda(x, W, quant, keys)
+    dev = _cuda(x, W, quant, keys)
     assert W.dtype == torch.float32 and (quant is None) != (keys is None)
     N, D = x.shape
     z = torch.empty((N, D), dtype=torch.float32, device=x.device)
@@ -238,9 +256,9 @@ def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, *, quant: torch.Tensor | N
     qo = torch.empty((N,), dtype=torch.int64, device=x.device) if want_quant else None
     xn = torch.empty((N, D), dtype=torch.float32, device=x.device) if want_xnorm else None
     partials, ticket = _loss_ws(x.device)
-    _call('vqb_gather_ste_loss', lib.vqb_gather_ste_loss, _p(x), _dt(x), N, D, int(normalize_x), _p(W), W.shape[0],
+    _call('vqb_gather_ste_loss', lib.vqb_gather_ste_loss, dev, _p(x), _dt(x), N, D, int(normalize_x), _p(W), W.shape[0],
           _p(quant), _p(keys), key_offset, _p(qo), _p(xn), _p(z), int(want_norm), _p(mse4), _p(partials), _p(ticket),
-          _stream())
+          _S)
     return z, mse4, qo, xn
 
 
@@ -251,31 +269,33 @@ def quantize_backward(g_z: torch.Tensor, x: torch.Tensor, W: torch.Tensor, quant
     lib = _lib.load()
     if isinstance(g4, torch.Tensor):
         g4 = [g4[i] for i in range(4)]
-    _cuda(g_z, x, W, quant, *g4)
-    assert g_z.dtype == torch.float32 and all(g is None or g.dtype == torch.float32 for g in g4)
+    dev = _cuda(g_z, x, W, quant, *g4)
+    assert all(g is None or g.dtype == torch.float32 for g in g4)
+    if not (g_z.dtype == torch.float32 or (g_z.dtype == torch.bfloat16 and x.dtype == torch.bfloat16)):
+        g_z = g_z.float()
     N, D = x.shape
     gx = torch.empty_like(x)
     gW = torch.zeros_like(W) if need_gW else None
-    _call('vqb_quantize_backward', lib.vqb_quantize_backward, _p(g_z), _p(x), _dt(x), int(normalize_x), _p(W),
+    _call('vqb_quantize_backward', lib.vqb_quantize_backward, dev, _p(g_z), _dt(g_z), _p(x), _dt(x), int(normalize_x), _p(W),
           W.shape[0], _p(quant), N, D, _p(g4[0]), _p(g4[1]), _p(g4[2]), _p(g4[3]), int(want_norm), _p(gx), _p(gW),
-          _stream())
+          _S)
     return gx, gW
 
 
 def l2norm_forward(x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     lib = _lib.load()
-    _cuda(x)
+    dev = _cuda(x)
     y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    _call('vqb_l2norm_forward', lib.vqb_l2norm_forward, _p(x), _dt(x), x.shape[0], x.shape[1], _p(y), _dt(y), _stream())
+    _call('vqb_l2norm_forward', lib.vqb_l2norm_forward, dev, _p(x), _dt(x), x.shape[0], x.shape[1], _p(y), _dt(y), _S)
     return y
 
 
 def l2norm_backward(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
-    _cuda(gy, x)
+    dev = _cuda(gy, x)
     gx = torch.empty_like(x)
-    _call('vqb_l2norm_backward', lib.vqb_l2norm_backward, _p(gy), _dt(gy), _p(x), _dt(x), x.shape[0], x.shape[1], _p(gx), _dt(gx),
-                                  _stream())
+    _call('vqb_l2norm_backward', lib.vqb_l2norm_backward, dev, _p(gy), _dt(gy), _p(x), _dt(x), x.shape[0], x.shape[1], _p(gx), _dt(gx),
+                                  _S)
     return gx
 
 
@@ -283,10 +303,10 @@ def scatter_stats(x: torch.Tensor, quant: torch.Tensor, K: int, *, normalize_x: 
                   out: torch.Tensor | None = None) -> torch.Tensor:
     """fp32 [K*D + K] = per-code feature sums followed by per-code counts (one all-reduce buffer)."""
     lib = _lib.load()
-    _cuda(x, quant, out)
+    dev = _cuda(x, quant, out)
     N, D = x.shape
     stats = out if out is not None else torch.zeros((K * D + K,), dtype=torch.float32, device=x.device)
-    _call('vqb_scatter_stats', lib.vqb_scatter_stats, _p(x), _dt(x), N, D, int(normalize_x), _p(quant), _p(stats), K, _stream())
+    _call('vqb_scatter_stats', lib.vqb_scatter_stats, dev, _p(x), _dt(x), N, D, int(normalize_x), _p(quant), _p(stats), K, _S)
     return stats
 
 
@@ -294,12 +314,12 @@ def bincount_accumulate(quant: torch.Tensor, counts: torch.Tensor, K: int | None
                         total_slot: bool = False) -> torch.Tensor:
     """counts[:K] += bincount(quant); with total_slot, counts has K+1 entries and counts[K] += numel."""
     lib = _lib.load()
-    _cuda(quant, counts)
+    dev = _cuda(quant, counts)
     assert quant.dtype == torch.int64 and counts.dtype == torch.int64
     K = counts.numel() - int(total_slot) if K is None else K
     assert counts.numel() >= K + int(total_slot)
     flat = quant.reshape(-1)
-    _call('vqb_bincount_accumulate', lib.vqb_bincount_accumulate, _p(flat), flat.numel(), _p(counts), K, int(total_slot), _stream())
+    _call('vqb_bincount_accumulate', lib.vqb_bincount_accumulate, dev, _p(flat), flat.numel(), _p(counts), K, int(total_slot), _S)
     return counts
 
 
@@ -309,19 +329,22 @@ def _f32(v: float) -> float:
 
 def kmeans_ema_update(stats: torch.Tensor, W: torch.Tensor, decay: float) -> torch.Tensor:
     lib = _lib.load()
-    _cuda(stats, W)
+    dev = _cuda(stats, W)
     K, D = W.shape
-    _call('vqb_kmeans_ema_update', lib.vqb_kmeans_ema_update, _p(stats), _p(W), K, D, _f32(decay), _f32(1 - decay), _stream())
+    _call('vqb_kmeans_ema_update', lib.vqb_kmeans_ema_update, dev, _p(stats), _p(W), K, D, _f32(decay), _f32(1 - decay), _S)
     return W
 
 
-def gather_rows_by_key(x: torch.Tensor, keys: torch.Tensor, index_offset: int = 0) -> torch.Tensor:
+def gather_rows_by_key(x: torch.Tensor, keys: torch.Tensor, index_offset: int = 0,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
     lib = _lib.load()
-    _cuda(x, keys)
+    dev = _cuda(x, keys, out)
     N, D = x.shape
     K = keys.numel()
-    out = torch.empty((K, D), dtype=torch.float32, device=x.device)
-    _call('vqb_gather_rows_by_key', lib.vqb_gather_rows_by_key, _p(x), _dt(x), N, D, _p(keys), K, index_offset, _p(out), _stream())
+    if out is None:
+        out = torch.empty((K, D), dtype=torch.float32, device=x.device)
+    assert out.dtype == torch.float32 and out.shape == (K, D)
+    _call('vqb_gather_rows_by_key', lib.vqb_gather_rows_by_key, dev, _p(x), _dt(x), N, D, _p(keys), K, index_offset, _p(out), _S)
     return out
 
 
@@ -329,21 +352,54 @@ def cvq_update(W: torch.Tensor, anchors: torch.Tensor, prob: torch.Tensor, count
                total: torch.Tensor, *, decay: float, eps: float, anchor_scale: float = 1.0) -> None:
     """counts: int64 [K]; total: int64 [1] device tensor (both already all-reduced)."""
     lib = _lib.load()
-    _cuda(W, anchors, prob, counts, total)
+    dev = _cuda(W, anchors, prob, counts, total)
     assert counts.dtype == torch.int64 and total.dtype == torch.int64
     K, D = W.shape
-    _call('vqb_cvq_update', lib.vqb_cvq_update, _p(W), _p(anchors), anchor_scale, _p(prob), _p(counts), _p(total), K, D,
-                             _f32(decay), _f32(1 - decay), _f32(eps), _stream())
+    _call('vqb_cvq_update', lib.vqb_cvq_update, dev, _p(W), _p(anchors), anchor_scale, _p(prob), _p(counts), _p(total), K, D,
+                             _f32(decay), _f32(1 - decay), _f32(eps), _S)
 
 
 def embedding_gather(W: torch.Tensor, quant: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
-    _cuda(W, quant)
+    dev = _cuda(W, quant)
     assert W.dtype == torch.float32 and quant.dtype == torch.int64
     flat = quant.reshape(-1).contiguous()
     out = torch.empty((flat.numel(), W.shape[1]), dtype=torch.float32, device=W.device)
-    _call('vqb_embedding_gather', lib.vqb_embedding_gather, _p(W), W.shape[0], W.shape[1], _p(flat), flat.numel(), _p(out), _stream())
+    _call('vqb_embedding_gather', lib.vqb_embedding_gather, dev, _p(W), W.shape[0], W.shape[1], _p(flat), flat.numel(), _p(out), _S)
     return out.reshape(*quant.shape, W.shape[1])
+
+
+# ---- fused peer-memory exchange + codebook update (csrc/comm.cu) ------------------------------------------------
+NO_KEYS = (1 << 64) - 1    # (size_t)-1: "no key buffer" (sync=False anchors)
+
+
+def comm_kmeans_ema_update(region, K: int, D: int, decay: float, *, stats: str = 'stats', W: str = 'W') -> None:
+    """all_reduce(SUM) of every rank's [K*D sums | K counts] + k-means/EMA codebook update, one launch; the new rows
+    land in every rank's region (`region` is a parallel.PeerRegion)."""
+    lib = _lib.load()
+    _call('vqb_comm_kmeans_ema_update', lib.vqb_comm_kmeans_ema_update, region.device, c_void_p(region.base), region.rank,
+          region.world, region.offsets[stats], region.offsets[W], K, D, _f32(decay), _f32(1 - decay), _S)
+
+
+def comm_cvq_update(region, K: int, D: int, *, decay: float, eps: float, minloc: bool, counts: str = 'counts',
+                    anchors: str = 'anchors', keys: str = 'keys', W: str = 'W', prob: str = 'prob') -> None:
+    """Usage-count + anchor exchange fused with the CVQ-VAE probability EMA and anchor blend, one launch."""
+    lib = _lib.load()
+    _call('vqb_comm_cvq_update', lib.vqb_comm_cvq_update, region.device, c_void_p(region.base), region.rank, region.world,
+          region.offsets[counts], region.offsets[anchors], region.offsets[keys] if minloc else NO_KEYS,
+          region.offsets[W], region.offsets[prob], K, D, _f32(decay), _f32(1 - decay), _f32(eps), _S)
+
+
+def comm_allreduce_min_keys(region, n: int, keys: str = 'keys') -> None:
+    lib = _lib.load()
+    _call('vqb_comm_allreduce_min_keys', lib.vqb_comm_allreduce_min_keys, region.device, c_void_p(region.base),
+          region.rank, region.world, region.offsets[keys], n, _S)
+
+
+def comm_allreduce_sum_f32(region, n: int, name: str) -> None:
+    lib = _lib.load()
+    _call('vqb_comm_allreduce_sum_f32', lib.vqb_comm_allreduce_sum_f32, region.device, c_void_p(region.base), region.rank,
+          region.world, region.offsets[name], n, _S)
 
 
 # ---- FSQ -------------------------------------------------------------------------------------
@@ -376,29 +432,29 @@ def fsq_params(levels, eps: float) -> FSQParams:
 
 def fsq_forward(x: torch.Tensor, p: FSQParams, out_dtype: torch.dtype | None = None):
     lib = _lib.load()
-    _cuda(x)
+    dev = _cuda(x)
     N, D = x.shape
     assert D == p.D
     zq = torch.empty((N, D), dtype=out_dtype or x.dtype, device=x.device)
     idx = torch.empty((N,), dtype=torch.int32, device=x.device)
-    _call('vqb_fsq_forward', lib.vqb_fsq_forward, _p(x), _dt(x), N, ctypes.byref(p), _p(zq), _dt(zq), _p(idx), _stream())
+    _call('vqb_fsq_forward', lib.vqb_fsq_forward, dev, _p(x), _dt(x), N, ctypes.byref(p), _p(zq), _dt(zq), _p(idx), _S)
     return zq, idx
 
 
 def fsq_backward(gz: torch.Tensor, x: torch.Tensor, p: FSQParams) -> torch.Tensor:
     lib = _lib.load()
-    _cuda(gz, x)
+    dev = _cuda(gz, x)
     gx = torch.empty_like(x)
-    _call('vqb_fsq_backward', lib.vqb_fsq_backward, _p(gz), _dt(gz), _p(x), _dt(x), x.shape[0], ctypes.byref(p), _p(gx), _dt(gx),
-                               _stream())
+    _call('vqb_fsq_backward', lib.vqb_fsq_backward, dev, _p(gz), _dt(gz), _p(x), _dt(x), x.shape[0], ctypes.byref(p), _p(gx), _dt(gx),
+                               _S)
     return gx
 
 
 def fsq_decode(index: torch.Tensor, p: FSQParams) -> torch.Tensor:
     lib = _lib.load()
-    _cuda(index)
+    dev = _cuda(index)
     index = index.to(torch.int32) if index.dtype != torch.int32 else index
     flat = index.reshape(-1).contiguous()
     z = torch.empty((flat.numel(), p.D), dtype=torch.float32, device=index.device)
-    _call('vqb_fsq_decode', lib.vqb_fsq_decode, _p(flat), flat.numel(), ctypes.byref(p), _p(z), _stream())
+    _call('vqb_fsq_decode', lib.vqb_fsq_decode, dev, _p(flat), flat.numel(), ctypes.byref(p), _p(z), _S)
     return z.reshape(*index.shape, p.D)

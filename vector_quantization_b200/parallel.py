@@ -15,10 +15,15 @@ All helpers are no-ops in a single process and work on CPU tensors with the gloo
 """
 from __future__ import annotations
 
+import ctypes
+import os
+import warnings
+
 import torch
 import torch.distributed as dist
 
-__all__ = ['world_size', 'rank', 'all_reduce_sum_', 'all_gather_rows', 'all_reduce_min_keys_', 'shard_range']
+__all__ = ['world_size', 'rank', 'all_reduce_sum_', 'all_gather_rows', 'all_reduce_min_keys_', 'shard_range',
+           'PeerRegion', 'peer_comm_enabled']
 
 _SIGN = -(1 << 63)  # 0x8000... as int64
 
@@ -77,6 +82,97 @@ def shard_range(total: int, r: int | None = None, w: int | None = None) -> tuple
     return lo, min(total, lo + per)
 
 
+# ---- NVLink peer-memory regions (the fused exchange kernels of csrc/comm.cu) ---------------------------------
+def peer_comm_enabled(device: torch.device) -> bool:
+    """The fused peer-memory exchange is the default whenever several ranks drive CUDA devices of one node;
+    VQB_COMM=nccl keeps the torch.distributed collectives (e.g. multi-node jobs)."""
+    return (_on() and device.type == 'cuda' and os.environ.get('VQB_COMM', 'p2p') != 'nccl'
+            and world_size() <= 16)
+
+
+class _Span:
+    """__cuda_array_interface__ view of a slice of a region (keeps the region alive)."""
+
+    def __init__(self, region: 'PeerRegion', offset: int, shape, typestr: str) -> None:
+        self._region = region
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(region.base + offset, False),
+                                             version=3, strides=None)
+
+
+class PeerRegion:
+    """One cudaMalloc'd region per rank, identical layout everywhere, every rank maps every peer (CUDA IPC over
+    NVLink/NVSwitch).  torch.distributed is used ONCE, to exchange the 64-byte IPC handles; after that the
+    exchange kernels (`ops.comm_*`) address peers directly.  Sub-buffers are carved with `alloc` (same call
+    sequence on every rank) and exposed as torch tensors aliasing the region."""
+
+    _TYPESTR = {torch.float32: '<f4', torch.int64: '<i8', torch.int32: '<i4', torch.uint8: '|u1'}
+
+    def __init__(self, nbytes: int, device: torch.device) -> None:
+        from . import _lib
+        lib = _lib.load()
+        self.device = torch.device(device)
+        self.rank, self.world = rank(), world_size()
+        self.nbytes = _lib.COMM_HEADER_BYTES + ((int(nbytes) + 511) // 512) * 512
+        self._cursor = _lib.COMM_HEADER_BYTES
+        self.offsets: dict[str, int] = {}
+        region = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.vqb_comm_alloc(self.nbytes, ctypes.byref(region), handle), 'vqb_comm_alloc')
+            self.base = int(region.value)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (bytes(handle), self.nbytes))
+            assert all(h[1] == self.nbytes for h in handles), 'peer regions must have the same size on every rank'
+            peers = []
+            for r, (h, _) in enumerate(handles):
+                if r == self.rank:
+                    peers.append(self.base)
+                    continue
+                ptr = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                _lib.check(lib.vqb_comm_open(buf, ctypes.byref(ptr)), 'vqb_comm_open')
+                peers.append(int(ptr.value))
+            self.peers = peers
+            table = (ctypes.c_void_p * self.world)(*peers)
+            _lib.check(lib.vqb_comm_bind(ctypes.c_void_p(self.base), table, self.rank, self.world), 'vqb_comm_bind')
+        dist.barrier()   # nobody launches an exchange before every table is in place
+
+    def alloc(self, name: str, shape, dtype: torch.dtype) -> torch.Tensor:
+        """Carve a 512-byte aligned sub-buffer (zero-initialised) and return a tensor aliasing it."""
+        numel = 1
+        for v in shape:
+            numel *= int(v)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        off = self._cursor
+        if off + nbytes > self.nbytes:
+            raise MemoryError(f'PeerRegion of {self.nbytes} bytes exhausted by {name!r}')
+        self._cursor = off + ((nbytes + 511) // 512) * 512
+        self.offsets[name] = off
+        t = torch.as_tensor(_Span(self, off, shape, self._TYPESTR[dtype]), device=self.device)
+        setattr(self, name, t)
+        return t
+
+
+_REGION_FAILED = False
+
+
+def try_peer_region(nbytes: int, device: torch.device) -> 'PeerRegion | None':
+    """A PeerRegion, or None (with ONE warning) when peer mapping is unavailable; the caller then keeps the
+    torch.distributed collectives.  Collective: every rank calls it at the same point."""
+    global _REGION_FAILED
+    if _REGION_FAILED or not peer_comm_enabled(device):
+        return None
+    try:
+        return PeerRegion(nbytes, device)
+    except Exception as exc:  # noqa: BLE001 - no P2P / IPC in this environment
+        _REGION_FAILED = True
+        warnings.warn(f'vector_quantization_b200: NVLink peer-memory exchange unavailable ({exc}); '
+                      'falling back to torch.distributed collectives')
+        ok = torch.zeros(1, device=device)
+        dist.all_reduce(ok)     # keep the ranks in step
+        return None
+
+
 # ---- host-side mirror of the device key packing (csrc/common.cuh make_key); used by the gloo tests -------
 def pack_keys_host(score: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     """int64 tensor holding (~orderable(score) << 32) | index, bit-identical to the kernels' keys."""
@@ -98,6 +194,20 @@ def unpack_keys_host(keys: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     return score, idx
 
 
+_KEY_REGIONS: dict = {}
+
+
+def _keys_region(n: int, device: torch.device) -> 'PeerRegion | None':
+    """Peer region holding the [n] packed keys of the codebook-sharded assignment (one per (n, device), reused)."""
+    k = (n, device.index)
+    if k not in _KEY_REGIONS:
+        region = try_peer_region(n * 8, device)
+        if region is not None:
+            region.alloc('keys', (n,), torch.int64)
+        _KEY_REGIONS[k] = region
+    return _KEY_REGIONS[k]
+
+
 # ---- codebook-sharded assignment (new functionality, SURVEY.md §8e; BASELINE.json configs[4]) -------------
 def sharded_nearest_code(x: torch.Tensor, W_shard: torch.Tensor, metric: str, *, shard_lo: int | None = None,
                          total_codes: int | None = None, precision: str = 'fp32'):
@@ -110,10 +220,18 @@ def sharded_nearest_code(x: torch.Tensor, W_shard: torch.Tensor, metric: str, *,
     if shard_lo is None:
         assert total_codes is not None
         shard_lo = shard_range(total_codes)[0]
-    keys = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
+    n = x.shape[0]
+    region = _keys_region(n, x.device)
+    keys = region.keys if region is not None else torch.empty((n,), dtype=torch.int64, device=x.device)
     book = Fq.pack_codebook(W_shard, metric, precision=precision, reset_keys=keys, tokens=x)
     Fq.nearest_code(x, book, metric, precision=precision, keys=keys, keys_are_reset=True, index_offset=shard_lo)
-    all_reduce_min_keys_(keys)
+    if region is not None:
+        # per-shard keys live in the peer region: one launch reduces them over NVLink (two-shot min-loc) into every
+        # rank's copy; the result is cloned out so that the next call can reuse the region
+        ops.comm_allreduce_min_keys(region, n)
+        keys = keys.clone()
+    else:
+        all_reduce_min_keys_(keys)
     return ops.unpack_keys(keys), keys
 
 

@@ -14,6 +14,7 @@ library must be present — there is no CPU or eager-PyTorch fallback.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Mapping, Sequence
 
 import torch
@@ -130,6 +131,18 @@ class VectorQuantizer(BaseQuantizer):
         self._embedding = embedding
         self._distance = distance
         self.precision = precision
+        self._pending = weakref.WeakSet()   # CodebookRef of every forward whose backward has not run yet
+
+    def protect_saved_codebook(self) -> None:
+        """Call before ANY in-place write to the codebook: pending backwards that saved the live tensor get a private
+        copy first (see functional.CodebookRef)."""
+        live = self._embedding.weight.data_ptr()
+        shared = [r for r in self._pending if r.tensor.data_ptr() == live]
+        if shared:
+            snapshot = shared[0].tensor.clone()
+            for r in shared:
+                r.tensor = snapshot
+        self._pending.clear()
 
     @classmethod
     def build_pre_hook(cls, config, registry, item):
@@ -159,7 +172,8 @@ class VectorQuantizer(BaseQuantizer):
         return self._embedding.weight.clone()
 
     def _init_weights(self, config) -> bool:
-        InitRegistry.build(config)(self._embedding.weight)
+        if config:                      # an empty node (no `init_weights` in the config) keeps nn.Embedding's own init
+            InitRegistry.build(config)(self._embedding.weight)
         return False
 
     def _weight(self) -> torch.Tensor:
@@ -178,8 +192,11 @@ class VectorQuantizer(BaseQuantizer):
         W = self._weight().data
         metric = self._distance.metric
         keys = torch.empty((x.shape[0],), dtype=torch.int64, device=x.device)
-        book = Fq.pack_codebook(W, metric, precision=self.precision,
-                                writeback_normalized=memo.pop('_normalize_codebook', False), reset_keys=keys, tokens=x)
+        writeback = memo.pop('_normalize_codebook', False)
+        if writeback:
+            self.protect_saved_codebook()   # the codebook is normalised in place
+        book = Fq.pack_codebook(W, metric, precision=self.precision, writeback_normalized=writeback, reset_keys=keys,
+                                tokens=x)
         normalize_tokens = memo.pop('_normalize_x', False)
         want_columns = self.training and self._callbacks.needs_column_nearest
         tokens = None
@@ -214,13 +231,19 @@ class VectorQuantizer(BaseQuantizer):
         # Callbacks that update the codebook in after_encode (training) need int64 indices before the gather;
         # otherwise the packed keys go straight into the fused kernel, which also emits memo['quant'].
         lazy_unpack = not (self.training and self._callbacks.overrides('after_encode'))
-        memo['_lazy_normalize'] = True
+        # NormalizeCallback may defer F.normalize(x) into the fused kernels only when nobody else reads x
+        memo['_lazy_normalize'] = self._callbacks.lazy_normalize_ok()
         memo['_lazy_unpack'] = lazy_unpack
         x, index, memo = self.encode(x, memo)
         memo.pop('_lazy_normalize', None)
         normalize_x = memo.pop('_normalize_x', False)
-        z, mse4, quant, xn = Fq.quantize_ste_loss(x, self._weight(), index, self._loss_terms(),
-                                                  index_is_keys=lazy_unpack, normalize_x=normalize_x)
+        W = self._weight()
+        ref = None
+        if torch.is_grad_enabled() and (x.requires_grad or W.requires_grad):
+            ref = Fq.CodebookRef(W.detach())
+            self._pending.add(ref)
+        z, mse4, quant, xn = Fq.quantize_ste_loss(x, W, index, self._loss_terms(), index_is_keys=lazy_unpack,
+                                                  normalize_x=normalize_x, codebook_ref=ref)
         memo.update(x=xn if normalize_x else x, quant=quant)
         memo['decode'] = get_memo(memo, 'decode')
         loss_memo = get_memo(memo, 'loss')

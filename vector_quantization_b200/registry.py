@@ -129,9 +129,13 @@ class Registry:
             config.setdefault(k, v)
         type_ = config.pop('type')
         item = self.lookup(type_) if isinstance(type_, str) else type_
+        # nn.Module items with an `init_weights` method get it called with the config's `init_weights` node, an
+        # EMPTY Config when the node is absent (as todd does: the VQ-KD config has none, configs/vqkd/model.py:20-26,
+        # yet its callbacks create the k-means lazy init / `_probability` buffer in before_init_weights);
+        # `init_weights=None` defers the call to the caller (vqb.build_quantizer sets the train/eval mode first).
         init_weights = None
         if isinstance(item, type) and issubclass(item, nn.Module) and hasattr(item, 'init_weights'):
-            init_weights = config.pop('init_weights', None)
+            init_weights = config.pop('init_weights', Config())
         hook = getattr(item, 'build_pre_hook', None)
         if hook is not None:
             config = hook(config, self, item)
