@@ -132,7 +132,7 @@ def entropy_loss(d: torch.Tensor, temperature: float) -> torch.Tensor:
 def bin_count(quants: Sequence[torch.Tensor], K: int) -> torch.Tensor:
     """QuantStatistics.bin_count with sync=True over ranks — vq/algorithms/vq/utils.py:40-43,35
     (all_reduce SUM of per-rank `bincount(minlength=K)`)."""
-    out = torch.zeros(K, dtype=torch.int64)
+    out = torch.zeros(K, dtype=torch.int64, device=quants[0].device)
     for q in quants:
         out += q.bincount(minlength=K)
     return out
@@ -141,7 +141,7 @@ def bin_count(quants: Sequence[torch.Tensor], K: int) -> torch.Tensor:
 def frequency(quants: Sequence[torch.Tensor], K: int) -> torch.Tensor:
     """QuantStatistics.frequency — vq/algorithms/vq/utils.py:48-52 (int64 / int64 → fp32)."""
     cnt = bin_count(quants, K)
-    numel = torch.tensor(sum(q.numel() for q in quants), dtype=torch.int64)
+    numel = torch.tensor(sum(q.numel() for q in quants), dtype=torch.int64, device=cnt.device)
     return cnt / numel
 
 

@@ -77,8 +77,8 @@ SIGNATURES = {
     'vqb_comm_close': (c_int, [c_void_p]),
     'vqb_comm_free': (c_int, [c_void_p]),
     'vqb_comm_bind': (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int]),
-    'vqb_comm_kmeans_ema_update': (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_int64, c_int, c_float, c_float,
-                                           c_void_p]),
+    'vqb_comm_kmeans_ema_update': (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_int64, c_int,
+                                           c_float, c_float, c_void_p]),
     'vqb_comm_cvq_update': (c_int, [c_void_p, c_int, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_size_t, c_int64,
                                     c_int, c_float, c_float, c_float, c_void_p]),
     'vqb_comm_allreduce_min_keys': (c_int, [c_void_p, c_int, c_int, c_size_t, c_int64, c_void_p]),

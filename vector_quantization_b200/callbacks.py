@@ -325,7 +325,10 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
         W = vq.embedding.weight.data
         K, D = W.shape
         vq.protect_saved_codebook()
-        region = self._peer_region(x.device, [('W', (K, D), torch.float32), ('stats', (K * D + K,), torch.float32)])
+        layout = [('W', (K, D), torch.float32), ('stats', (K * D + K,), torch.float32)]
+        if (K * D + K) * 4 <= parallel.LL_MAX_BYTES:      # small payload: latency matters, not the 2x wire bytes
+            layout += ops.comm_ll_layout(K, D, parallel.world_size())
+        region = self._peer_region(x.device, layout)
         if region is not None:
             # per-rank partial sums straight into the peer region; ONE fused launch then reduces them over NVLink in
             # fixed rank order, applies the k-means/EMA update and publishes the new rows to every replica

@@ -13,6 +13,7 @@
 // Flags carry a monotonically increasing epoch, so they never need resetting and a CUDA graph can replay the
 // kernels.  All spins are bounded (trap after ~2 s): a missing peer is an error, never a hung GPU.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -73,6 +74,8 @@ __device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long lo
 
 // Barrier A: block 0 announces "everything this rank wrote BEFORE this kernel is complete" (the kernel boundary /
 // griddepcontrol.wait made it visible); EVERY block then waits until all ranks have announced.
+// (Measured on 2 x B200: polling with acquire loads + a fence per thread, as below, 21 us per exchange; relaxed
+// polling + one fence per block, 35 us: the tight relaxed polls of ~600 blocks starve the flag line.)
 __device__ __forceinline__ uint32_t comm_begin(const Comm& c) {
   __shared__ uint32_t s_epoch;
   CommCtl* ctl = c.ctl();
@@ -213,6 +216,147 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_kernel(Comm c, size_t sta
   comm_end(c, e);
 }
 
+// ---- low-latency variant of the VQ-KD exchange (payloads up to a few MB) --------------------------------------
+// The barrier protocol above costs six NVLink hops (flag, read round trip, write + ack, flag: ~20 us measured).
+// Here every 4-byte value travels as an 8-byte (value, epoch) word in ONE naturally aligned store, so the data is its
+// own flag (the "LL" idea of NCCL): no barriers, no fences, two one-way hops.
+//   phase 1  every rank PUSHES the partial sums/counts of the rows it does not own into the owner's staging area
+//   phase 2  the owner polls its staging area (local memory), reduces in fixed rank order, applies the k-means/EMA
+//            update and pushes the new rows into every peer's row staging (its own codebook is written directly)
+//   phase 3  every rank polls its row staging and writes the rows it does not own into its codebook
+// Staging is single-buffered: a rank cannot start epoch e+1 before every owner has consumed its epoch-e words
+// (phase 3 needs all owners' rows, which they send after consuming).  All blocks of the grid must be co-resident
+// (a block spins on words that remote blocks produce); the host sizes the grid from the occupancy query.
+__device__ __forceinline__ void st_ll(unsigned long long* p, float v, uint32_t e) {
+  const unsigned long long w = ((unsigned long long)e << 32) | __float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ float ld_ll(const unsigned long long* p, uint32_t e, const Comm& c) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  if ((uint32_t)(w >> 32) != e) {
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+      if (clock64() - t0 > 4000000000ll) {
+        printf("vqb comm: rank %d timed out polling a low-latency word (epoch %u, found %u)\n", c.rank, e, (uint32_t)(w >> 32));
+        __trap();
+      }
+    } while ((uint32_t)(w >> 32) != e);
+  }
+  return __uint_as_float((uint32_t)w);
+}
+
+template <int G, int NPL>
+__global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t stats_off, size_t w_off, size_t in_off,
+                                                                 size_t out_off, int64_t K, int D, float decay, float omd) {
+  __shared__ uint32_t s_epoch;
+  pdl_wait();
+  pdl_launch_dependents();
+  CommCtl* ctl = c.ctl();
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(&ctl->epoch) + 1;
+  if (threadIdx.x < c.world) peer_table()[threadIdx.x] = reinterpret_cast<char* const*>(c.base + kPeerTableOff)[threadIdx.x];
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  const int per = (int)((K + c.world - 1) / c.world);   // rows per owner
+  const int W1 = D + 1;                                  // staged words per row: D sums + the count
+  const int lo = min((int)K, per * c.rank), hi = min((int)K, lo + per);
+  const float* __restrict__ stats = reinterpret_cast<const float*>(c.base + stats_off);
+  float* __restrict__ Wl = reinterpret_cast<float*>(c.base + w_off);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+
+  // ---- phase 1: push my partials to the owners ----
+  for (int idx = tid; idx < (int)K * W1; idx += nthreads) {
+    const int k = idx / W1, j = idx - k * W1;
+    const int owner = k / per;
+    if (owner == c.rank) continue;
+    const float v = j < D ? stats[(int64_t)k * D + j] : stats[K * (int64_t)D + k];
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(c.peer(owner) + in_off) +
+                              ((int64_t)c.rank * per + (k - owner * per)) * W1 + j;
+    st_ll(dst, v, e);
+  }
+
+  // ---- phase 2: reduce my rows in fixed rank order, update, publish ----
+  const int lane = threadIdx.x % G;
+  const int rows_per_block = blockDim.x / G;
+  const unsigned long long* __restrict__ stage_in = reinterpret_cast<const unsigned long long*>(c.base + in_off);
+  for (int base = lo + blockIdx.x * rows_per_block; base < hi; base += gridDim.x * rows_per_block) {
+    const int k_raw = base + threadIdx.x / G;
+    const bool valid = k_raw < hi;
+    const int k = valid ? k_raw : hi - 1;
+    float cnt = 0.f, s[NPL], w[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) s[j] = 0.f;
+    for (int r = 0; r < c.world; ++r) {
+      if (r == c.rank) {
+        cnt += stats[K * (int64_t)D + k];
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const int d = lane + j * G;
+          if (d < D) s[j] += stats[(int64_t)k * D + d];
+        }
+      } else {
+        const unsigned long long* row = stage_in + ((int64_t)r * per + (k - lo)) * W1;
+        cnt += ld_ll(row + D, e, c);
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const int d = lane + j * G;
+          if (d < D) s[j] += ld_ll(row + d, e, c);
+        }
+      }
+    }
+    const bool occurred = cnt > 0.f;
+    const float den = fmaxf(cnt, 1.f);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int d = lane + j * G;
+      w[j] = d < D ? Wl[(int64_t)k * D + d] : 0.f;
+      s[j] = d < D ? (occurred ? __fdiv_rn(s[j], den) : w[j]) : 0.f;
+      ss = fmaf(s[j], s[j], ss);
+    }
+    ss = group_sum<G>(ss);
+    const float dn = fmaxf(sqrtf(ss), kNormEps);
+    float ss2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      s[j] = __fadd_rn(__fmul_rn(w[j], decay), __fmul_rn(__fdiv_rn(s[j], dn), omd));
+      ss2 = fmaf(s[j], s[j], ss2);
+    }
+    ss2 = group_sum<G>(ss2);
+    const float dn2 = fmaxf(sqrtf(ss2), kNormEps);
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int d = lane + j * G;
+      if (valid && d < D) {
+        const float out = __fdiv_rn(s[j], dn2);
+        Wl[(int64_t)k * D + d] = out;
+        for (int r = 0; r < c.world; ++r)
+          if (r != c.rank) st_ll(reinterpret_cast<unsigned long long*>(c.peer(r) + out_off) + (int64_t)k * D + d, out, e);
+      }
+    }
+  }
+
+  // ---- phase 3: collect the rows of the other owners ----
+  const unsigned long long* __restrict__ stage_out = reinterpret_cast<const unsigned long long*>(c.base + out_off);
+  const int mine0 = lo * D, mine1 = hi * D;
+  for (int idx = tid; idx < (int)K * D; idx += nthreads) {
+    if (idx >= mine0 && idx < mine1) continue;
+    Wl[idx] = ld_ll(stage_out + idx, e, c);
+  }
+
+  // ---- retire the epoch (last block) ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1) {
+      ctl->ticket = 0;
+      *reinterpret_cast<volatile uint32_t*>(&ctl->epoch) = e;
+      __threadfence();
+    }
+  }
+}
+
 // ---- CVQ-VAE: all-reduce of the usage counts + anchors fused with the probability EMA and the anchor blend ---
 // vq/algorithms/cvqvae/quantizer_callback.py:88-103, anchors.py:50-67.
 //   keys_off == SIZE_MAX (sync=False): anchors = mean over ranks of the per-rank nearest-token rows (anchors.py:64-67)
@@ -343,7 +487,15 @@ static inline int pow2_lanes_c(int n) {
 }
 static inline int blocks_for(int64_t items, int items_per_block) {
   int64_t b = (items + items_per_block - 1) / items_per_block;
-  const int64_t cap = sm_count();       // one resident block per SM is plenty for a latency-bound exchange
+  // The exchange is latency-bound (one NVLink round trip per loop iteration of a block): enough co-resident blocks
+  // that every block makes ONE trip.  VQB_COMM_BLOCKS_PER_SM: developer knob.
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("VQB_COMM_BLOCKS_PER_SM");
+    per_sm = e ? atoi(e) : 4;
+    if (per_sm < 1) per_sm = 1;
+  }
+  const int64_t cap = (int64_t)sm_count() * per_sm;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -405,19 +557,29 @@ int vqb_comm_bind(void* region, const void* const* peer_regions_host, int rank, 
   return VQB_OK;
 }
 
-int vqb_comm_kmeans_ema_update(void* region, int rank, int world, size_t stats_off, size_t w_off, int64_t K, int D,
-                               float decay, float one_minus_decay, void* stream) {
+int vqb_comm_kmeans_ema_update(void* region, int rank, int world, size_t stats_off, size_t w_off, size_t ll_in_off,
+                               size_t ll_out_off, int64_t K, int D, float decay, float one_minus_decay, void* stream) {
   VQB_COMM_ARGS_OK("vqb_comm_kmeans_ema_update");
   VQB_REQUIRE(K >= 1 && D >= 1 && stats_off % 16 == 0 && w_off % 16 == 0, "vqb_comm_kmeans_ema_update: bad shape/offset");
   Comm c{static_cast<char*>(region), rank, world};
   VQB_REQUIRE(D <= 1024, "vqb_comm_kmeans_ema_update: D <= 1024");
+  const bool ll = ll_in_off != (size_t)-1 && ll_out_off != (size_t)-1;
+  VQB_REQUIRE(!ll || (ll_in_off % 8 == 0 && ll_out_off % 8 == 0 && K * (int64_t)(D + 1) < (1ll << 31)),
+              "vqb_comm_kmeans_ema_update: bad low-latency staging");
   const int g = pow2_lanes_c(D);           // one lane per element up to 32: the exchange is latency-bound, go wide
   int npl = 1;
   while (g * npl < D) npl <<= 1;
-  const int blocks = blocks_for((K + world - 1) / world, 256 / g);
+  int blocks = blocks_for((K + world - 1) / world, 256 / g);
+  if (ll) {   // every block must be resident: it spins on words produced by REMOTE blocks
+    blocks = sm_count() * 2;
+  }
 #define LAUNCH(G_, NPL_)                                                                                                   \
-  VQB_CUDA_OK(launch_pdl(comm_kmeans_ema_kernel<G_, NPL_>, blocks, 256, 0, (cudaStream_t)stream, c, stats_off, w_off, K, D, \
-                         decay, one_minus_decay))
+  if (ll)                                                                                                                  \
+    VQB_CUDA_OK(launch_pdl(comm_kmeans_ema_ll_kernel<G_, NPL_>, blocks, 256, 0, (cudaStream_t)stream, c, stats_off, w_off, \
+                           ll_in_off, ll_out_off, K, D, decay, one_minus_decay));                                         \
+  else                                                                                                                     \
+    VQB_CUDA_OK(launch_pdl(comm_kmeans_ema_kernel<G_, NPL_>, blocks, 256, 0, (cudaStream_t)stream, c, stats_off, w_off, K, D, \
+                           decay, one_minus_decay))
   if (npl == 1) {
     switch (g) {
       case 1: LAUNCH(1, 1); break;

@@ -373,12 +373,22 @@ def embedding_gather(W: torch.Tensor, quant: torch.Tensor) -> torch.Tensor:
 NO_KEYS = (1 << 64) - 1    # (size_t)-1: "no key buffer" (sync=False anchors)
 
 
-def comm_kmeans_ema_update(region, K: int, D: int, decay: float, *, stats: str = 'stats', W: str = 'W') -> None:
+def comm_kmeans_ema_update(region, K: int, D: int, decay: float, *, stats: str = 'stats', W: str = 'W',
+                           ll_in: str = 'll_in', ll_out: str = 'll_out') -> None:
     """all_reduce(SUM) of every rank's [K*D sums | K counts] + k-means/EMA codebook update, one launch; the new rows
-    land in every rank's region (`region` is a parallel.PeerRegion)."""
+    land in every rank's region (`region` is a parallel.PeerRegion).  With the staging buffers `ll_in` / `ll_out`
+    in the region the low-latency (flag-in-data) protocol is used, otherwise the barrier protocol."""
     lib = _lib.load()
+    ll = ll_in in region.offsets and ll_out in region.offsets
     _call('vqb_comm_kmeans_ema_update', lib.vqb_comm_kmeans_ema_update, region.device, c_void_p(region.base), region.rank,
-          region.world, region.offsets[stats], region.offsets[W], K, D, _f32(decay), _f32(1 - decay), _S)
+          region.world, region.offsets[stats], region.offsets[W], region.offsets[ll_in] if ll else NO_KEYS,
+          region.offsets[ll_out] if ll else NO_KEYS, K, D, _f32(decay), _f32(1 - decay), _S)
+
+
+def comm_ll_layout(K: int, D: int, world: int):
+    """Staging buffers of the low-latency exchange: (name, shape, dtype) entries for PeerRegion.alloc."""
+    per = (K + world - 1) // world
+    return [('ll_in', (world * per * (D + 1),), torch.int64), ('ll_out', (K * D,), torch.int64)]
 
 
 def comm_cvq_update(region, K: int, D: int, *, decay: float, eps: float, minloc: bool, counts: str = 'counts',

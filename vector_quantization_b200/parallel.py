@@ -26,6 +26,9 @@ __all__ = ['world_size', 'rank', 'all_reduce_sum_', 'all_gather_rows', 'all_redu
            'PeerRegion', 'peer_comm_enabled']
 
 _SIGN = -(1 << 63)  # 0x8000... as int64
+# statistics payloads up to this size use the low-latency (flag-in-data) exchange protocol, larger ones the
+# bandwidth-efficient barrier protocol (csrc/comm.cu); VQB_COMM_LL=0 forces the barrier protocol
+LL_MAX_BYTES = (4 << 20) if os.environ.get('VQB_COMM_LL', '1') != '0' else 0
 
 
 def _on() -> bool:
