@@ -300,6 +300,14 @@ def main():
     from vector_quantization_b200 import ops
 
     assert torch.cuda.is_available(), 'bench.py --impl b200 needs a CUDA device (no CPU fallback)'
+    numa, all_cpus = None, os.sched_getaffinity(0)
+    try:   # run on the CPUs next to this rank's GPU, so that pinned host buffers are allocated NUMA-local
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = f'{len(os.sched_getaffinity(0))} CPUs next to GPU {local_rank}'
+    except Exception as exc:  # noqa: BLE001
+        numa = f'not set ({exc})'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -518,7 +526,22 @@ def main():
         cb = [c for c in q._callbacks if hasattr(c, '_region')]
         fused = bool(cb and cb[0]._region)
         key = 'vqb_comm_kmeans_ema_update' if 'vqb_comm_kmeans_ema_update' in per_kernel else 'vqb_comm_cvq_update'
-        t = per_kernel.get(key)
+        t = None
+        if fused and key == 'vqb_comm_kmeans_ema_update':
+            # the exchange+update launch alone: a burst of back-to-back launches on every rank (no host skew between
+            # the ranks inside the burst), CUDA events, max over ranks
+            region = cb[0]._region
+            for _ in range(5):
+                ops.comm_kmeans_ema_update(region, K, D, 0.99)
+            barrier()
+            e0.record()
+            for _ in range(50):
+                ops.comm_kmeans_ema_update(region, K, D, 0.99)
+            e1.record()
+            barrier()
+            tt = torch.tensor([e0.elapsed_time(e1) / 50], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = [float(tt)]
         payload = (K * D + K) * 4 if args.workload in ('cfg2', 'cfg3') else (K + 1) * 8 + K * D * 4
         collective = dict(
             what='per-step exchange of the per-code statistics (reference: all_reduce, vq/utils.py:35, '
@@ -528,7 +551,11 @@ def main():
                   f'({key}); no NCCL call on the data path') if fused else
                  ('torch.distributed all_reduce (NCCL)' if world > 1 else 'none (single GPU)'),
             ms=(sum(t) / len(t)) if (t and fused) else None,
-            ms_note='duration of the fused exchange+update launch, including the wait for the slowest rank')
+            protocol=('low-latency: 8-byte (value, epoch) words, no barrier/fence, 2 one-way NVLink hops'
+                      if fused and 'll_in' in cb[0]._region.offsets else
+                      ('barrier: flag, peer reads, peer writes + fence, flag' if fused else None)),
+            ms_note='one fused exchange+update launch, measured as a burst of 50 back-to-back launches on every rank '
+                    '(max over ranks); inside the step the launch also absorbs the wait for the slowest rank')
 
     # ---- end-to-end: pinned host inputs -> device -> step -> results back to pinned host ----
     xh = x0.pin_memory()
@@ -591,6 +618,7 @@ def main():
 
     cpu_baseline = gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)         # the CPU baseline uses every host core again
         try:
             gpu_eager = dict(
                 what="the reference's own op sequence (normalize, einsum, argmin, bincount/scatter_add/EMA, embedding, "
@@ -618,7 +646,7 @@ def main():
             clocks=clocks, roofline=roofline, collective=collective, cpu_baseline=cpu_baseline,
             gpu_eager_baseline=gpu_eager, breakdown_ms=breakdown,
             e2e=dict(value=N * world / (e2e_ms * 1e-3), unit=unit, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
-                     d2h_bytes_per_step=d2h),
+                     d2h_bytes_per_step=d2h, cpu_affinity=numa),
             gpu_launches=launches_per_step * args.steps)))
     if world > 1:
         # graphs that captured NCCL collectives must be gone before the communicator is torn down; a watchdog

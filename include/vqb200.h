@@ -78,6 +78,7 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D,
                   float* half_sqnorm,       /* optional [rows_pad]: 0.5*||packed row||^2 (fp32); +inf in padding */
                   float* writeback_f32,     /* optional [rows, D]: the (normalised) fp32 row; may alias src when src is fp32 */
                   unsigned long long* keys_to_reset, int64_t n_keys, /* optional: fill with 0xFF.. (fused memset for vqb_assign) */
+                  void* zero_fill, int64_t zero_bytes, /* optional: fused zero-fill (16-byte aligned, multiple of 16 bytes) of the step's statistics buffer */
                   void* stream);
 
 /* ---- nearest-code assignment ------------------------------------------------------------ *
@@ -182,7 +183,9 @@ int vqb_l2norm_backward(const void* gy, int g_dtype, const void* x, int x_dtype,
  * stats = fp32 [K*D sums | K counts] in ONE buffer (one all-reduce), pre-zeroed by the caller.
  * normalize_x: accumulate F.normalize(x) rows (callbacks.py:124). */
 int vqb_scatter_stats(const void* x, int x_dtype, int64_t N, int D, int normalize_x,
-                      const int64_t* quant, float* stats, int64_t K, void* stream);
+                      const int64_t* quant,          /* [N] indices, or NULL when `keys` is given */
+                      const unsigned long long* keys, int64_t key_index_offset, /* packed keys of vqb_assign */
+                      float* stats, int64_t K, void* stream);
 /* int64 histogram accumulate — CodebookMixin.forward, vq/tasks/image_tokenization/runners/metrics.py:37-45 */
 int vqb_bincount_accumulate(const int64_t* quant, int64_t n, int64_t* counts, int64_t K,
                             int add_total, /* 1: counts[K] += n (numel slot of the fused [K | 1] all-reduce buffer) */

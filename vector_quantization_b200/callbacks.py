@@ -47,6 +47,9 @@ class BaseCallback:
     # B200 path: True if this callback's `after_encode` copes with RAW tokens when NormalizeCallback defers the
     # token normalisation into the fused kernels (it must normalise whatever it reads from x itself)
     accepts_raw_tokens = False
+    # B200 path: True if `after_encode` takes the PACKED (score, index) keys of the assignment in place of int64
+    # indices (`quant is memo['encode']['keys']`); the fused gather kernel then emits memo['quant'] on its way
+    accepts_packed_keys = False
 
     def __init__(self, *args, **kwargs) -> None:
         super().__init__()
@@ -133,6 +136,10 @@ class ComposedCallback(BaseCallback):
         arg-mins and user callbacks see F.normalize(x)."""
         return all(c.accepts_raw_tokens or type(c).after_encode is BaseCallback.after_encode
                    for c in self._callbacks) and not self.needs_column_nearest
+
+    def packed_keys_ok(self) -> bool:
+        """May `after_encode` receive the packed keys instead of int64 indices (no separate unpack launch)?"""
+        return all(c.accepts_packed_keys or type(c).after_encode is BaseCallback.after_encode for c in self._callbacks)
 
     def overrides(self, hook: str) -> bool:
         """True if any child customises `hook` (the fused decode/loss path checks this)."""
@@ -272,6 +279,7 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
     ONE all-reduce of the fused [K*D | K] buffer -> centroid / normalise / EMA / normalise kernel."""
 
     accepts_raw_tokens = True    # after_encode accumulates F.normalize(x) rows itself (scatter kernel flag)
+    accepts_packed_keys = True   # ... and reads the code of a token straight from the packed keys
 
     @torch.no_grad()
     def lazy_init_weights(self, config, x, memo) -> None:
@@ -316,6 +324,30 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
                 ops.kmeans_ema_update(stats, W, 0.0)  # decay 0: W <- normalize(centroids | old row if unused)
         Fq.pack_codebook(W, metric, precision=vq.precision, writeback_normalized=True)
 
+    def _stats_buffer(self, device: torch.device):
+        """(region | None, stats): the per-step [K*D sums | K counts] buffer — inside the NVLink peer region when the
+        fused multi-GPU exchange is active, a persistent private buffer otherwise (padded to 16 bytes for the
+        fused zero-fill)."""
+        W = self.vector_quantizer.embedding.weight.data
+        K, D = W.shape
+        layout = [('W', (K, D), torch.float32), ('stats', ((K * D + K + 3) // 4 * 4,), torch.float32)]
+        if (K * D + K) * 4 <= parallel.LL_MAX_BYTES:      # small payload: latency matters, not the 2x wire bytes
+            layout += ops.comm_ll_layout(K, D, parallel.world_size())
+        region = self._peer_region(device, layout)
+        if region is not None:
+            return region, region.stats
+        buf = getattr(self, '_stats', None)
+        if buf is None or buf.device != device or buf.numel() != (K * D + K + 3) // 4 * 4:
+            buf = self._stats = torch.zeros((K * D + K + 3) // 4 * 4, dtype=torch.float32, device=device)
+        return None, buf
+
+    def before_encode(self, x, memo):
+        x = super().before_encode(x, memo)
+        if self.vector_quantizer.training and x.is_cuda:
+            # the statistics buffer is zeroed by the codebook-pack launch of `_encode` (no memset of its own)
+            memo['_zero_fill'] = self._stats_buffer(x.device)[1]
+        return x
+
     @torch.no_grad()
     def after_encode(self, x, quant, memo):
         quant = super().after_encode(x, quant, memo)
@@ -325,17 +357,17 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
         W = vq.embedding.weight.data
         K, D = W.shape
         vq.protect_saved_codebook()
-        layout = [('W', (K, D), torch.float32), ('stats', (K * D + K,), torch.float32)]
-        if (K * D + K) * 4 <= parallel.LL_MAX_BYTES:      # small payload: latency matters, not the 2x wire bytes
-            layout += ops.comm_ll_layout(K, D, parallel.world_size())
-        region = self._peer_region(x.device, layout)
+        packed = quant is memo['encode'].get('keys')          # forward() hands the packed keys down (no unpack launch)
+        index = dict(quant=None, keys=quant) if packed else dict(quant=quant)
+        region, stats = self._stats_buffer(x.device)
+        if not memo['encode'].pop('_zeroed', False):
+            stats.zero_()                                     # `_encode` was bypassed or overridden
+        ops.scatter_stats(x.detach(), **index, K=K, normalize_x=True, out=stats)
         if region is not None:
-            # per-rank partial sums straight into the peer region; ONE fused launch then reduces them over NVLink in
-            # fixed rank order, applies the k-means/EMA update and publishes the new rows to every replica
-            ops.scatter_stats(x.detach(), quant, K, normalize_x=True, out=region.stats.zero_())
+            # the per-rank partial sums sit in the peer region: ONE fused launch reduces them over NVLink in fixed rank
+            # order, applies the k-means/EMA update and publishes the new rows to every replica
             ops.comm_kmeans_ema_update(region, K, D, self._ema.decay)
             return quant
-        stats = ops.scatter_stats(x.detach(), quant, K, normalize_x=True)
         parallel.all_reduce_sum_(stats)
         ops.kmeans_ema_update(stats, W, self._ema.decay)
         return quant
@@ -363,6 +395,10 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
     @property
     def column_nearest_global(self) -> bool:  # type: ignore[override]
         return bool(self._anchor.sync)
+
+    @property
+    def accepts_packed_keys(self) -> bool:  # type: ignore[override]
+        return not self.quantizer.training     # after_encode is a no-op outside training
 
     def before_init_weights(self, config) -> None:
         super().before_init_weights(config)

@@ -231,9 +231,13 @@ __device__ __forceinline__ void st_ll(unsigned long long* p, float v, uint32_t e
   const unsigned long long w = ((unsigned long long)e << 32) | __float_as_uint(v);
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __forceinline__ float ld_ll(const unsigned long long* p, uint32_t e, const Comm& c) {
+__device__ __forceinline__ unsigned long long ld_ll_raw(const unsigned long long* p) {
   unsigned long long w;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+// value of a low-latency word: `w` is what a first (batched) load returned; re-polls only if it had not arrived yet
+__device__ __forceinline__ float ld_ll(const unsigned long long* p, unsigned long long w, uint32_t e, const Comm& c) {
   if ((uint32_t)(w >> 32) != e) {
     const long long t0 = clock64();
     do {
@@ -287,21 +291,41 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
     float cnt = 0.f, s[NPL], w[NPL];
 #pragma unroll
     for (int j = 0; j < NPL; ++j) s[j] = 0.f;
-    for (int r = 0; r < c.world; ++r) {
-      if (r == c.rank) {
-        cnt += stats[K * (int64_t)D + k];
+    constexpr int B = NPL <= 4 ? kBatch : (NPL <= 8 ? 4 : (NPL <= 16 ? 2 : 1));
+    for (int r0 = 0; r0 < c.world; r0 += B) {          // every poll of a batch is in flight before the first check
+      unsigned long long wc[B], wv[B][NPL];
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-          const int d = lane + j * G;
-          if (d < D) s[j] += stats[(int64_t)k * D + d];
+      for (int b = 0; b < B; ++b) {
+        const int r = r0 + b;
+        if (r < c.world && r != c.rank) {
+          const unsigned long long* row = stage_in + ((int64_t)r * per + (k - lo)) * W1;
+          wc[b] = ld_ll_raw(row + D);
+#pragma unroll
+          for (int j = 0; j < NPL; ++j) {
+            const int d = lane + j * G;
+            wv[b][j] = d < D ? ld_ll_raw(row + d) : 0ull;
+          }
         }
-      } else {
-        const unsigned long long* row = stage_in + ((int64_t)r * per + (k - lo)) * W1;
-        cnt += ld_ll(row + D, e, c);
+      }
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-          const int d = lane + j * G;
-          if (d < D) s[j] += ld_ll(row + d, e, c);
+      for (int b = 0; b < B; ++b) {                      // fixed rank order
+        const int r = r0 + b;
+        if (r >= c.world) continue;
+        if (r == c.rank) {
+          cnt += stats[K * (int64_t)D + k];
+#pragma unroll
+          for (int j = 0; j < NPL; ++j) {
+            const int d = lane + j * G;
+            if (d < D) s[j] += stats[(int64_t)k * D + d];
+          }
+        } else {
+          const unsigned long long* row = stage_in + ((int64_t)r * per + (k - lo)) * W1;
+          cnt += ld_ll(row + D, wc[b], e, c);
+#pragma unroll
+          for (int j = 0; j < NPL; ++j) {
+            const int d = lane + j * G;
+            if (d < D) s[j] += ld_ll(row + d, wv[b][j], e, c);
+          }
         }
       }
     }
@@ -340,9 +364,19 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
   // ---- phase 3: collect the rows of the other owners ----
   const unsigned long long* __restrict__ stage_out = reinterpret_cast<const unsigned long long*>(c.base + out_off);
   const int mine0 = lo * D, mine1 = hi * D;
-  for (int idx = tid; idx < (int)K * D; idx += nthreads) {
-    if (idx >= mine0 && idx < mine1) continue;
-    Wl[idx] = ld_ll(stage_out + idx, e, c);
+  for (int idx0 = tid; idx0 < (int)K * D; idx0 += 4 * nthreads) {
+    unsigned long long w4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + u * nthreads;
+      const bool on = idx < (int)K * D && !(idx >= mine0 && idx < mine1);
+      w4[u] = on ? ld_ll_raw(stage_out + idx) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + u * nthreads;
+      if (idx < (int)K * D && !(idx >= mine0 && idx < mine1)) Wl[idx] = ld_ll(stage_out + idx, w4[u], e, c);
+    }
   }
 
   // ---- retire the epoch (last block) ----

@@ -26,13 +26,16 @@ template <typename T, int G>
 __global__ void __launch_bounds__(256) pack_rows_kernel(
     const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
     __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
-    unsigned long long* __restrict__ keys, int64_t n_keys) {
+    unsigned long long* __restrict__ keys, int64_t n_keys, uint4* __restrict__ zero_fill, int64_t n_zero16) {
   pdl_wait();               // PDL: the source rows / key buffer may still be in use by the preceding launch
   pdl_launch_dependents();
   // fused memset of the assignment keys
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_keys;
        i += (int64_t)gridDim.x * blockDim.x)
     keys[i] = ~0ull;
+  // fused zero-fill of the step's statistics buffer
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_zero16; i += (int64_t)gridDim.x * blockDim.x)
+    zero_fill[i] = make_uint4(0u, 0u, 0u, 0u);
 
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
@@ -92,11 +95,13 @@ template <typename T, int G, int NV>
 __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
     const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
     __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
-    unsigned long long* __restrict__ keys, int64_t n_keys) {
+    unsigned long long* __restrict__ keys, int64_t n_keys, uint4* __restrict__ zero_fill, int64_t n_zero16) {
   pdl_wait();               // the source rows / the key buffer may still be in use by the preceding launch
   pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_keys; i += (int64_t)gridDim.x * blockDim.x)
     keys[i] = ~0ull;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_zero16; i += (int64_t)gridDim.x * blockDim.x)
+    zero_fill[i] = make_uint4(0u, 0u, 0u, 0u);
   const int lane = threadIdx.x % G;
   const int64_t rows_per_block = blockDim.x / G;
   for (int64_t r = blockIdx.x * rows_per_block + threadIdx.x / G; r < rows_pad;
@@ -333,8 +338,12 @@ size_t vqb_operand_bytes(int64_t rows, int D, int planes) {
 
 int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes,
                   void* dst_planes, float* half_sqnorm, float* writeback, unsigned long long* keys,
-                  int64_t n_keys, void* stream) {
+                  int64_t n_keys, void* zero_fill, int64_t zero_bytes, void* stream) {
   VQB_REQUIRE(src && dst_planes, "vqb_pack_rows: null pointer");
+  VQB_REQUIRE(zero_fill == nullptr || ((uintptr_t)zero_fill % 16 == 0 && zero_bytes % 16 == 0 && zero_bytes >= 0),
+              "vqb_pack_rows: zero_fill must be 16-byte aligned and a multiple of 16 bytes");
+  uint4* zf = (uint4*)zero_fill;
+  const int64_t nz = zero_fill ? zero_bytes / 16 : 0;
   VQB_REQUIRE(rows >= 0 && D >= 1 && D <= 8192, "vqb_pack_rows: bad shape rows=%lld D=%d", (long long)rows, D);
   VQB_REQUIRE(planes_valid(planes), "vqb_pack_rows: planes must be 1..3, VQB_PLANES_F16 or VQB_PLANES_F16X2 (got %d)", planes);
   VQB_REQUIRE(!is_f16x2(planes) || normalize, "vqb_pack_rows: VQB_PLANES_F16X2 needs normalize = 1 (|v| <= 1)");
@@ -359,11 +368,11 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
     if (gv == G_ && nv == NV_) {                                                                                     \
       if (src_dtype == VQB_F32)                                                                                      \
         launch_pdl(pack_rows_vec_kernel<float, G_, NV_>, blocks, 256, 0, st, (const float*)src, rows, rows_pad, D, Dp, \
-            normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys, keys ? n_keys : 0);        \
+            normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz);        \
       else                                                                                                           \
         launch_pdl(pack_rows_vec_kernel<__nv_bfloat16, G_, NV_>, blocks, 256, 0, st, (const __nv_bfloat16*)src, rows, \
             rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys,            \
-            keys ? n_keys : 0);                                                                                      \
+            keys ? n_keys : 0, zf, nz);                                                                                      \
       VQB_LAUNCH_OK();                                                                                               \
       return VQB_OK;                                                                                                 \
     }
@@ -376,11 +385,11 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
     if (src_dtype == VQB_F32)
       launch_pdl(pack_rows_kernel<float, G>, blocks, 256, 0, st, (const float*)src, rows, rows_pad, D, Dp, normalize,
                                                           planes, (__nv_bfloat16*)dst_planes, half_sqnorm,
-                                                          writeback, keys, keys ? n_keys : 0);
+                                                          writeback, keys, keys ? n_keys : 0, zf, nz);
     else
       launch_pdl(pack_rows_kernel<__nv_bfloat16, G>, blocks, 256, 0, st, 
           (const __nv_bfloat16*)src, rows, rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes,
-          half_sqnorm, writeback, keys, keys ? n_keys : 0);
+          half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz);
   }));
   VQB_LAUNCH_OK();
   return VQB_OK;

@@ -13,6 +13,7 @@ namespace vqb {
 template <typename TX, int G, int V>
 __global__ void __launch_bounds__(256) scatter_stats_kernel(const TX* __restrict__ x, int64_t N, int D,
                                                             int normalize_x, const int64_t* __restrict__ quant,
+                                                            const unsigned long long* __restrict__ keys, int64_t key_offset,
                                                             float* __restrict__ stats, int64_t K) {
   pdl_wait();               // PDL: inputs come from the preceding launches
   pdl_launch_dependents();
@@ -30,7 +31,13 @@ __global__ void __launch_bounds__(256) scatter_stats_kernel(const TX* __restrict
     const int64_t n_raw = base + threadIdx.x / G;
     const bool valid = n_raw < N;
     const int64_t n = valid ? n_raw : N - 1;
-    int64_t q64 = quant[n];
+    int64_t q64;
+    if (quant) {
+      q64 = quant[n];
+    } else {   // packed keys of vqb_assign: no finite score (NaN token) -> index 0, like torch.argmin
+      const unsigned long long kk = keys[n];
+      q64 = kk == kNoKey ? 0 : (int64_t)key_index(kk) - key_offset;
+    }
     const bool inrange = valid && q64 >= 0 && q64 < K;
     const int q = inrange ? (int)q64 : -1 - (lane_in_warp / G);  // unique negative id: never aggregated
     const TX* __restrict__ xrow = x + n * D;
@@ -214,8 +221,9 @@ using namespace vqb;
 extern "C" {
 
 int vqb_scatter_stats(const void* x, int x_dtype, int64_t N, int D, int normalize_x, const int64_t* quant,
-                      float* stats, int64_t K, void* stream) {
-  VQB_REQUIRE(x && quant && stats, "vqb_scatter_stats: null pointer");
+                      const unsigned long long* keys, int64_t key_index_offset, float* stats, int64_t K, void* stream) {
+  VQB_REQUIRE(x && stats, "vqb_scatter_stats: null pointer");
+  VQB_REQUIRE((quant != nullptr) != (keys != nullptr), "vqb_scatter_stats: pass exactly one of quant / keys");
   VQB_REQUIRE(N >= 1 && D >= 1 && K >= 1, "vqb_scatter_stats: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (D % 4 == 0);
@@ -224,10 +232,10 @@ int vqb_scatter_stats(const void* x, int x_dtype, int64_t N, int D, int normaliz
 #define LAUNCH(TX)                                                                                              \
   if (vec) {                                                                                                    \
     VQB_DISPATCH_G(g, (launch_pdl(scatter_stats_kernel<TX, G, 4>, blocks, 256, 0, st, (const TX*)x, N, D, normalize_x,  \
-                                                                               quant, stats, K)));              \
+                                                                               quant, keys, key_index_offset, stats, K)));              \
   } else {                                                                                                      \
     VQB_DISPATCH_G(g, (launch_pdl(scatter_stats_kernel<TX, G, 1>, blocks, 256, 0, st, (const TX*)x, N, D, normalize_x,  \
-                                                                               quant, stats, K)));              \
+                                                                               quant, keys, key_index_offset, stats, K)));              \
   }
   if (x_dtype == VQB_F32) { LAUNCH(float) }
   else if (x_dtype == VQB_BF16) { LAUNCH(__nv_bfloat16) }

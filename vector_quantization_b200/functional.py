@@ -57,7 +57,7 @@ def _pair_ok(W: torch.Tensor, normalize: bool, precision: str, tokens: torch.Ten
 @torch.no_grad()
 def pack_codebook(W: torch.Tensor, metric: str, *, precision: str = DEFAULT_PRECISION,
                   writeback_normalized: bool = False, reset_keys: torch.Tensor | None = None,
-                  tokens: torch.Tensor | None = None) -> ops.Operand:
+                  tokens: torch.Tensor | None = None, zero_fill: torch.Tensor | None = None) -> ops.Operand:
     """Codebook operand: cosine -> planes of F.normalize(W) (optionally written back to W in place, which is
     NormalizeCallback's `weight.data = normalize(weight)`, normalize.py:26-28); L2 -> planes of W and 0.5|e|^2.
     `tokens`: the token tensor this codebook will be matched against (selects the plane format)."""
@@ -66,7 +66,7 @@ def pack_codebook(W: torch.Tensor, metric: str, *, precision: str = DEFAULT_PREC
     pair = cos and _pair_ok(W, normalize, precision, tokens)
     return ops.pack_rows(W, normalize=normalize, planes=None if pair else _planes_for(W, normalize, precision),
                          want_half_sqnorm=not cos, writeback=W if writeback_normalized else None,
-                         reset_keys=reset_keys, fmt='f16x2' if pair else 'bf16')
+                         reset_keys=reset_keys, fmt='f16x2' if pair else 'bf16', zero_fill=zero_fill)
 
 
 @torch.no_grad()

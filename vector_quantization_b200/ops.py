@@ -111,15 +111,20 @@ def operand_shape(rows: int, D: int) -> tuple[int, int]:
 
 def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None = None,
               want_half_sqnorm: bool = False, writeback: torch.Tensor | None = None,
-              reset_keys: torch.Tensor | None = None, fmt: str = 'bf16') -> Operand:
+              reset_keys: torch.Tensor | None = None, fmt: str = 'bf16',
+              zero_fill: torch.Tensor | None = None) -> Operand:
     """fp32/bf16 rows -> operand planes (see vqb_pack_rows).
     fmt='bf16': exact bf16 planes; `planes=None` picks the exact representation (1 plane for un-normalised bf16
                 input, 3 planes otherwise).
     fmt='f16x2': the two-plane fp16 (hi, lo * 2^11) pair of NORMALISED rows: 22 significant bits, two MMA terms.
     fmt='f16':  one fp16 plane of un-normalised bf16 rows (the partner of an 'f16x2' operand)."""
     lib = _lib.load()
-    dev = _cuda(src, writeback, reset_keys)
+    dev = _cuda(src, writeback, reset_keys, zero_fill)
     assert src.dim() == 2
+    zero_bytes = 0
+    if zero_fill is not None:      # fused memset of e.g. the step's statistics buffer (padded to 16 bytes by the owner)
+        zero_bytes = zero_fill.numel() * zero_fill.element_size()
+        assert zero_bytes % 16 == 0 and zero_fill.data_ptr() % 16 == 0
     rows, D = src.shape
     if fmt == 'f16x2':
         if not normalize:
@@ -141,7 +146,7 @@ def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None 
     if writeback is not None:
         assert writeback.dtype == torch.float32 and writeback.shape == src.shape
     _call('vqb_pack_rows', lib.vqb_pack_rows, dev, _p(src), _dt(src), rows, D, int(normalize), code, _p(dst), _p(h),
-          _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _S)
+          _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _p(zero_fill), zero_bytes, _S)
     return Operand(dst, rows, D, planes, h, fmt=fmt)
 
 
@@ -299,14 +304,17 @@ def l2norm_backward(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return gx
 
 
-def scatter_stats(x: torch.Tensor, quant: torch.Tensor, K: int, *, normalize_x: bool = False,
-                  out: torch.Tensor | None = None) -> torch.Tensor:
-    """fp32 [K*D + K] = per-code feature sums followed by per-code counts (one all-reduce buffer)."""
+def scatter_stats(x: torch.Tensor, quant: torch.Tensor | None, K: int, *, normalize_x: bool = False,
+                  out: torch.Tensor | None = None, keys: torch.Tensor | None = None, key_offset: int = 0) -> torch.Tensor:
+    """fp32 [K*D + K] = per-code feature sums followed by per-code counts (one all-reduce buffer).  The code of a
+    token comes from `quant` (int64 indices) or straight from the packed `keys` of the assignment."""
     lib = _lib.load()
-    dev = _cuda(x, quant, out)
+    dev = _cuda(x, quant, out, keys)
+    assert (quant is None) != (keys is None)
     N, D = x.shape
     stats = out if out is not None else torch.zeros((K * D + K,), dtype=torch.float32, device=x.device)
-    _call('vqb_scatter_stats', lib.vqb_scatter_stats, dev, _p(x), _dt(x), N, D, int(normalize_x), _p(quant), _p(stats), K, _S)
+    _call('vqb_scatter_stats', lib.vqb_scatter_stats, dev, _p(x), _dt(x), N, D, int(normalize_x), _p(quant), _p(keys),
+          key_offset, _p(stats), K, _S)
     return stats
 
 

@@ -96,11 +96,12 @@ class BaseQuantizer(nn.Module):
     def encode(self, x: torch.Tensor, memo: dict):
         x = self._callbacks.before_encode(x, memo)
         enc = get_memo(memo, 'encode')
-        for flag in ('_normalize_codebook', '_normalize_x', '_lazy_unpack'):  # requests of the callbacks / forward
+        for flag in ('_normalize_codebook', '_normalize_x', '_lazy_unpack', '_zero_fill'):  # requests of the callbacks / forward
             if flag in memo:
                 enc[flag] = memo[flag]
         memo.pop('_normalize_codebook', None)
         memo.pop('_lazy_unpack', None)
+        memo.pop('_zero_fill', None)
         quant, memo['encode'] = self._encode(x, enc)
         quant = self._callbacks.after_encode(x, quant, memo)
         return x, quant, memo
@@ -195,8 +196,11 @@ class VectorQuantizer(BaseQuantizer):
         writeback = memo.pop('_normalize_codebook', False)
         if writeback:
             self.protect_saved_codebook()   # the codebook is normalised in place
+        zero_fill = memo.pop('_zero_fill', None)
         book = Fq.pack_codebook(W, metric, precision=self.precision, writeback_normalized=writeback, reset_keys=keys,
-                                tokens=x)
+                                tokens=x, zero_fill=zero_fill)
+        if zero_fill is not None:
+            memo['_zeroed'] = True
         normalize_tokens = memo.pop('_normalize_x', False)
         want_columns = self.training and self._callbacks.needs_column_nearest
         tokens = None
@@ -228,9 +232,9 @@ class VectorQuantizer(BaseQuantizer):
             if self._callbacks.overrides(hook):
                 raise NotImplementedError(f'callbacks overriding {hook} are not supported by the fused decode/loss path')
         x = _check_tokens(x, self.embedding_dim)
-        # Callbacks that update the codebook in after_encode (training) need int64 indices before the gather;
-        # otherwise the packed keys go straight into the fused kernel, which also emits memo['quant'].
-        lazy_unpack = not (self.training and self._callbacks.overrides('after_encode'))
+        # The packed keys go straight into the fused gather kernel, which also emits memo['quant'] — unless a callback
+        # that overrides after_encode needs int64 indices first (VQKDCallback reads the keys itself).
+        lazy_unpack = self._callbacks.packed_keys_ok()
         # NormalizeCallback may defer F.normalize(x) into the fused kernels only when nobody else reads x
         memo['_lazy_normalize'] = self._callbacks.lazy_normalize_ok()
         memo['_lazy_unpack'] = lazy_unpack
