@@ -231,6 +231,15 @@ int vqb_fsq_backward(const void* gz, int g_dtype, const void* x, int x_dtype, in
                      const vqb_fsq_params* p_host, void* gx, int gx_dtype, void* stream);
 int vqb_fsq_decode(const int32_t* index, int64_t N, const vqb_fsq_params* p_host, float* z_out, void* stream);
 
+/* ---- compatibility mode: the materialised distance matrix ---------------------------------- *
+ * out[n, k] = torch.cdist(x, W)[n, k]  (cosine = 0)         vq/algorithms/vq/distances.py:28-32
+ *           = 1 - <x_n/|x_n|, W_k/|W_k|>  (cosine = 1)       vq/algorithms/vq/distances.py:35-46
+ * i.e. `memo['encode']['distance']` of VectorQuantizer._encode (vq/algorithms/vq/quantizers.py:97-98), which the
+ * hot path never builds.  Produced on demand for its consumers (EntropyLoss, MultinomialAnchor, user callbacks,
+ * the `materialize_distance` debug switch); fp32 CUDA-core kernel, exact fp32 products. */
+int vqb_distance_matrix(const void* x, int x_dtype, int64_t N, int D, const float* W, int64_t K, int cosine,
+                        float* out /* fp32 [N, K] */, void* stream);
+
 /* ---- multi-GPU exchange over NVLink peer memory, fused with the codebook update ------------ *
  * One process per GPU (the reference's DDP model).  Replaces the statistics collectives of the path
  *   QuantStatistics all_reduce x2                       vq/algorithms/vq/utils.py:35

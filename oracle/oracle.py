@@ -193,6 +193,21 @@ def vqkd_lazy_init(x: torch.Tensor, weight: torch.Tensor, iters: int = 10, dista
     return normalize(e)                                           # :111
 
 
+def vqgan_vqkd_update(weight: torch.Tensor, decay) -> torch.Tensor:
+    """VQGAN_VQKDCallback.after_encode (training) — vq/algorithms/exp/vqgan_vqkd/quantizer_callback.py:124-134 with
+    `_update_embedding` normalising again (:75-77): no statistics, the codebook is only pulled towards the sphere."""
+    e = normalize(weight.clone())                                 # :131-132
+    e = ema(weight.clone(), e, decay)                             # :133
+    return normalize(e)                                           # :134 -> :75-77
+
+
+def multinomial_anchor(x: torch.Tensor, d: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """MultinomialAnchor._anchors — vq/algorithms/cvqvae/anchors.py:88-104 (consumes the torch RNG)."""
+    indices = einops.rearrange(d, 'x e -> e x').softmax(1).multinomial(1)
+    indices = einops.rearrange(indices, 'e 1 -> e')
+    return x[indices], indices
+
+
 def nearest_anchor(x: torch.Tensor, d: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     """NearestAnchor._anchors — vq/algorithms/cvqvae/anchors.py:71-85. Returns (anchors, indices)."""
     idx = d.argmin(0)

@@ -63,3 +63,45 @@ def test_cached_anchor_sampling_rule_equals_reference_source(N, K):
         assert torch.equal(got, want), step
         cache = got
         assert torch.equal(ref_anchor.cache, cache)
+
+
+def test_entropy_loss_and_multinomial_anchor_restatements_equal_reference_source():
+    """The compat-mode consumers of the distance matrix: `O.entropy_loss` vs the reference's EntropyLoss (which reads
+    `memo['distance']` of the memo it is handed, losses.py:142) and `O.multinomial_anchor` vs MultinomialAnchor under
+    the same torch seed."""
+    from oracle import oracle as O
+    ref = ref_loader.load()
+    x, E = O.synthetic_latents(96, 24, 8, seed=3)
+    d = O.distance('L2', x, E)
+    want = ref.vq.losses.EntropyLoss(temperature=0.7)(None, None, dict(distance=d))
+    assert torch.equal(O.entropy_loss(d, 0.7), want)
+    anchor = ref.cvqvae.anchors.MultinomialAnchor()
+    torch.manual_seed(5)
+    a_ref, _ = anchor(x, E, d, None, torch.zeros(24))
+    torch.manual_seed(5)
+    a_or, _ = O.multinomial_anchor(x, d)
+    assert torch.equal(a_ref, a_or)
+
+
+def test_reference_vqgan_vqkd_callback_cannot_be_imported_upstream():
+    """vq/algorithms/exp/vqgan_vqkd/quantizer_callback.py:38-42 declares
+    `class VQGAN_VQKDCallback(LazyInitWeightsMixin, UpdateMixin, NormalizeCallback)`; NormalizeCallback already
+    derives from UpdateMixin, so Python cannot linearise the bases: the module raises TypeError at import in the
+    reference itself (experimental, not imported by any config).  Our VQGAN_VQKDCallback therefore follows the
+    SOURCE TEXT (`O.vqgan_vqkd_update`); there is no executable upstream behaviour to pin against."""
+    import importlib
+    import sys
+    import types
+    from oracle import oracle as O
+    ref_loader.load()
+    for name, path in (('vq.algorithms.exp', 'vq/algorithms/exp'), ('vq.algorithms.exp.vqgan_vqkd', 'vq/algorithms/exp/vqgan_vqkd')):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [str(ref_loader.REF / path)]
+            sys.modules[name] = m
+    with pytest.raises(TypeError, match='MRO'):
+        importlib.import_module('vq.algorithms.exp.vqgan_vqkd.quantizer_callback')
+    W = torch.randn(16, 8)
+    out = O.vqgan_vqkd_update(W, 0.99)
+    torch.testing.assert_close(out.norm(dim=1), torch.ones(16), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(out, torch.nn.functional.normalize(W * 0.99 + torch.nn.functional.normalize(W) * 0.01))

@@ -29,6 +29,7 @@ class BaseAnchor(nn.Module):
         self._sync = sync
 
     needs_columns = True   # gather() consumes the per-code nearest-token keys of the column arg-min pass
+    needs_distance = False  # True: gather() reads the materialised [N, K] distance matrix (compatibility mode)
     peer_exchange = False  # True: `gather_local` + the fused peer-memory exchange kernel replace gather()'s collectives
 
     @property
@@ -36,7 +37,7 @@ class BaseAnchor(nn.Module):
         return self._sync
 
     def gather(self, x: torch.Tensor, column_keys: torch.Tensor | None, n_local: int,
-               num_codes: int | None = None) -> torch.Tensor:
+               num_codes: int | None = None, distance: torch.Tensor | None = None) -> torch.Tensor:
         raise NotImplementedError
 
 
@@ -52,7 +53,7 @@ class NearestAnchor(BaseAnchor):
         return ops.gather_rows_by_key(x, column_keys, offset, out=out)
 
     @torch.no_grad()
-    def gather(self, x, column_keys, n_local, num_codes=None):
+    def gather(self, x, column_keys, n_local, num_codes=None, distance=None):
         """-> [K, D] fp32 anchors, already summed over ranks (identical on every rank)."""
         if self._sync:
             offset = parallel.rank() * n_local          # column_keys were built with this offset
@@ -65,11 +66,25 @@ class NearestAnchor(BaseAnchor):
 
 @AnchorRegistry.register_()
 class MultinomialAnchor(BaseAnchor):
-    """anchors.py:88-104 samples from softmax over the materialised distance columns — registered for config
-    compatibility, not implemented on the B200 path (no shipped config uses it)."""
+    """anchors.py:88-104, COMPATIBILITY MODE: one token per code drawn from softmax over the tokens of that code's
+    distance COLUMN.  The quantizer materialises the [N, K] matrix on demand (`vqb_distance_matrix`); the sampling
+    is the reference's own call sequence (`d.T.softmax(1).multinomial(1)`), so the device RNG stream is consumed
+    exactly as the reference consumes it; the rows are fetched by the row-gather kernel.  sync=True gathers tokens
+    and distances of every rank first (anchors.py:50-53), sync=False averages the per-rank anchors (anchors.py:64-67)."""
 
-    def gather(self, x, column_keys, n_local, num_codes=None):
-        raise NotImplementedError('MultinomialAnchor needs the materialised N x K distance matrix')
+    needs_columns = False
+    needs_distance = True
+
+    @torch.no_grad()
+    def gather(self, x, column_keys, n_local, num_codes=None, distance=None):
+        assert distance is not None, 'MultinomialAnchor.gather needs the materialised distance matrix'
+        d = distance.detach()
+        if self._sync and parallel.world_size() > 1:
+            x = parallel.all_gather_rows(x)
+            d = parallel.all_gather_rows(d)
+        indices = d.t().softmax(1).multinomial(1).flatten()        # anchors.py:98-101
+        anchors = ops.gather_rows_by_key(x.contiguous(), indices.to(torch.int64).contiguous(), 0)
+        return anchors if self._sync else parallel.all_reduce_sum_(anchors)
 
 
 def cached_rows_and_indices(x: torch.Tensor, num_codes: int, cache: torch.Tensor):
@@ -113,7 +128,7 @@ class CachedAnchor(BaseAnchor):
         return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     @torch.no_grad()
-    def gather(self, x, column_keys, n_local, num_codes=None):
+    def gather(self, x, column_keys, n_local, num_codes=None, distance=None):
         assert num_codes is not None, 'CachedAnchor.gather needs the codebook size'
         if self._sync and parallel.world_size() > 1:
             x = parallel.all_gather_rows(x)

@@ -22,7 +22,7 @@ from . import ops, parallel
 from .registry import AnchorRegistry, Config, VQITQuantizerCallbackRegistry, get_config
 
 __all__ = ['BaseCallback', 'ComposedCallback', 'UpdateMixin', 'NormalizeCallback', 'LazyInitWeightsMixin',
-           'VQKDCallback', 'CVQVAECallback', 'EMA']
+           'VQKDCallback', 'VQGAN_VQKDCallback', 'CVQVAECallback', 'EMA']
 
 HOOKS = ('bind', 'before_init_weights', 'after_init_weights', 'before_encode', 'after_encode', 'before_decode',
          'after_decode', 'before_loss', 'after_loss')
@@ -129,6 +129,11 @@ class ComposedCallback(BaseCallback):
     def column_nearest_global(self) -> bool:  # type: ignore[override]
         return any(c.column_nearest_global for c in self._callbacks)
 
+    @property
+    def needs_distance(self) -> bool:
+        """Some child reads the materialised [N, K] distance matrix (compatibility mode, e.g. MultinomialAnchor)."""
+        return any(getattr(c, 'needs_distance', False) for c in self._callbacks)
+
     def lazy_normalize_ok(self) -> bool:
         """May NormalizeCallback hand RAW tokens down the pipeline (normalisation fused into the gather / backward
         kernels)?  Only if every callback that reads x in `after_encode` declares that it copes; otherwise the
@@ -234,7 +239,15 @@ class UpdateMixin(BaseCallback):
         return hasattr(self, '_ema')
 
     def _update_embedding(self, e: torch.Tensor) -> None:
+        self._check_sync(e)
         self.vector_quantizer.embedding.weight.data = e
+
+    def _check_sync(self, t: torch.Tensor, what: str = 'codebook') -> None:
+        """The reference's only runtime cross-rank check (`todd.Store.DRY_RUN` + `todd.utils.is_sync`, update.py:54-55,
+        cvqvae/anchors.py:52-53,62-63): with VQB_DRY_RUN=1 every codebook update asserts that all replicas hold the
+        same values."""
+        if parallel.DRY_RUN:
+            parallel.assert_sync(t, what)
 
 
 @VQITQuantizerCallbackRegistry.register_()
@@ -367,9 +380,37 @@ class VQKDCallback(LazyInitWeightsMixin, NormalizeCallback):
             # the per-rank partial sums sit in the peer region: ONE fused launch reduces them over NVLink in fixed rank
             # order, applies the k-means/EMA update and publishes the new rows to every replica
             ops.comm_kmeans_ema_update(region, K, D, self._ema.decay)
+            self._check_sync(region.W)
             return quant
         parallel.all_reduce_sum_(stats)
         ops.kmeans_ema_update(stats, W, self._ema.decay)
+        self._check_sync(W)
+        return quant
+
+
+@VQITQuantizerCallbackRegistry.register_()
+class VQGAN_VQKDCallback(VQKDCallback):  # noqa: N801 - the reference's registry name
+    """vq/algorithms/exp/vqgan_vqkd/quantizer_callback.py:38-134: the k-means lazy init of VQKDCallback (:79-114,
+    the same distributed implementation here) on a codebook that is trained by GRADIENT; per training step only
+    `W <- normalize(ema(W, normalize(W)))` (:124-134) — no statistics, no exchange.  That is the k-means/EMA update
+    kernel with every code "unused" (a zero statistics buffer: the centroid of an unused code is its old row)."""
+
+    def before_encode(self, x, memo):
+        return NormalizeCallback.before_encode(self, x, memo)     # no statistics buffer to zero
+
+    @torch.no_grad()
+    def after_encode(self, x, quant, memo):
+        vq = self.vector_quantizer
+        if not vq.training:
+            return quant
+        W = vq.embedding.weight.data
+        K, D = W.shape
+        zeros = getattr(self, '_zeros', None)
+        if zeros is None or zeros.device != W.device or zeros.numel() != K * D + K:
+            zeros = self._zeros = torch.zeros(K * D + K, dtype=torch.float32, device=W.device)
+        vq.protect_saved_codebook()
+        ops.kmeans_ema_update(zeros, W, self._ema.decay)
+        self._check_sync(W)
         return quant
 
 
@@ -395,6 +436,10 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
     @property
     def column_nearest_global(self) -> bool:  # type: ignore[override]
         return bool(self._anchor.sync)
+
+    @property
+    def needs_distance(self) -> bool:
+        return bool(self._anchor.needs_distance) and self.quantizer.training
 
     @property
     def accepts_packed_keys(self) -> bool:  # type: ignore[override]
@@ -439,14 +484,18 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
                 if self._anchor.sync:
                     region.keys.copy_(col_keys)
                 ops.comm_cvq_update(region, K, D, decay=self._ema.decay, eps=self._eps, minloc=self._anchor.sync)
+                self._check_sync(region.W)
                 return quant
         # [K counts | numel] in one int64 buffer -> one all-reduce (utils.py:35 does two)
         cnt = torch.zeros(K + 1, dtype=torch.int64, device=x.device)
         ops.bincount_accumulate(quant, cnt, K, total_slot=True)
         parallel.all_reduce_sum_(cnt)
         world = parallel.world_size()
-        anchors = self._anchor.gather(x, col_keys, N, num_codes=K)
+        anchors = self._anchor.gather(x, col_keys, N, num_codes=K, distance=memo['encode'].get('distance'))
         scale = 1.0 if self._anchor.sync else 1.0 / world
+        if self._anchor.sync:
+            self._check_sync(anchors, 'anchors')
         ops.cvq_update(W, anchors, self.probability, cnt[:K], cnt[K:], decay=self._ema.decay, eps=self._eps,
                        anchor_scale=scale)
+        self._check_sync(W)
         return quant

@@ -20,9 +20,11 @@ class BaseDistance(nn.Module):
     metric: str = ''
 
     def forward(self, x: torch.Tensor, e: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError(
-            f'{type(self).__name__}: the N x K distance matrix is not materialised on the B200 path; the '
-            'quantizer consumes `metric` directly (EntropyLoss/MultinomialAnchor compat: SURVEY.md §8f-4)')
+        """COMPATIBILITY MODE: the materialised [N, K] matrix, as the reference's modules return it.  The quantizer
+        itself never calls this (it hands `metric` to the fused assignment kernel); it serves user code that calls
+        `quantizer.distance(x, e)` and the on-demand `memo['encode']['distance']`."""
+        from . import functional as Fq
+        return Fq.distance_matrix(x, e, self.metric)
 
 
 @VQITQuantizerDistanceRegistry.register_()

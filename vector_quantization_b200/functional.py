@@ -134,6 +134,63 @@ def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, preci
     return ops.assign(codebook, toks, keys, l2=not cos, index_offset=index_offset)
 
 
+class _DistanceMatrix(torch.autograd.Function):
+    """COMPATIBILITY MODE: the materialised [N, K] distance matrix of the reference
+    (`torch.cdist(x, e)` / `1 - normalize(x) @ normalize(e).T`, vq/algorithms/vq/distances.py:28-46) for the few
+    components that consume it.  Forward: the hand-written fp32 kernel `vqb_distance_matrix`.  Backward (only
+    EntropyLoss differentiates through the matrix): the two [N, K] x [K, D] products are plain library GEMMs — this
+    path exists for parity of rarely used components, not for speed."""
+
+    @staticmethod
+    def forward(ctx, x, W, metric):
+        d = ops.distance_matrix(x, W, metric)
+        ctx.save_for_backward(x, W, d)
+        ctx.metric = metric
+        return d
+
+    @staticmethod
+    def backward(ctx, G):
+        x, W, d = ctx.saved_tensors
+        G = G.contiguous().float()
+        xf = x.float()
+        if ctx.metric == 'Cosine':
+            xn, en = ops.l2norm_forward(x), ops.l2norm_forward(W)
+            gx = ops.l2norm_backward(-(G @ en), xf) if ctx.needs_input_grad[0] else None
+            gW = ops.l2norm_backward(-(G.t() @ xn), W) if ctx.needs_input_grad[1] else None
+        else:   # d = sqrt(|x|^2 - 2 x.e + |e|^2):  dd/dx = (x - e) / d
+            H = torch.where(d > 0, G / d, torch.zeros_like(G))
+            gx = (H.sum(1, keepdim=True) * xf - H @ W) if ctx.needs_input_grad[0] else None
+            gW = (H.sum(0).unsqueeze(1) * W - H.t() @ xf) if ctx.needs_input_grad[1] else None
+        return (None if gx is None else gx.to(x.dtype)), gW, None
+
+
+def distance_matrix(x: torch.Tensor, W: torch.Tensor, metric: str) -> torch.Tensor:
+    """Compatibility mode: differentiable fp32 [N, K] distance matrix (see _DistanceMatrix)."""
+    return _DistanceMatrix.apply(x.contiguous(), W.contiguous(), metric)
+
+
+class _EmbeddingGather(torch.autograd.Function):
+    """z = W[quant] with the gradient scattered back into the codebook rows (the unfused decode of the hook-compatible
+    template path; the fused forward never needs it).  Backward = the statistics scatter kernel."""
+
+    @staticmethod
+    def forward(ctx, W, quant):
+        ctx.save_for_backward(quant)
+        ctx.shape = W.shape
+        return ops.embedding_gather(W, quant)
+
+    @staticmethod
+    def backward(ctx, g):
+        (quant,) = ctx.saved_tensors
+        K, D = ctx.shape
+        stats = ops.scatter_stats(g.reshape(-1, D).contiguous().float(), quant.reshape(-1).contiguous(), K)
+        return stats[:K * D].view(K, D), None
+
+
+def embedding_lookup(W: torch.Tensor, quant: torch.Tensor) -> torch.Tensor:
+    return _EmbeddingGather.apply(W, quant.contiguous())
+
+
 class _TransposeLast2(torch.autograd.Function):
     """[B, R, C] -> [B, C, R]; the backward is the same kernel on the gradient."""
 

@@ -61,6 +61,9 @@ class BaseLoss(nn.Module):
         """{mse4 index: coefficient}"""
         raise NotImplementedError
 
+    uses_mse4 = True          # False: the loss is evaluated by its own forward(z, x, memo) (EntropyLoss)
+    needs_distance = False    # True: forward reads the materialised distance matrix (compatibility mode)
+
     @property
     def needs_norm(self) -> bool:
         return any(i >= CODEBOOK_NORM for i in self.terms())
@@ -137,16 +140,32 @@ class VQGANLoss(BaseLoss):
 
 @VQITQuantizerLossRegistry.register_()
 class EntropyLoss(BaseLoss):
-    """vq/algorithms/vq/losses.py:130-153 consumes the full N x K distance matrix, which this
-    implementation never materialises.  Registered (no shipped config uses it) but not implemented yet
-    (SURVEY.md §8f item 4)."""
+    """vq/algorithms/vq/losses.py:130-153, COMPATIBILITY MODE.  It consumes the full [N, K] distance matrix, which
+    the quantizer materialises on demand for it (`vqb_distance_matrix`, differentiable); the softmax / entropy
+    arithmetic below is the reference's, call for call, on that matrix (no shipped config uses this loss, and the
+    reference looks the matrix up in the LOSS memo, `memo['distance']`, where nothing upstream puts it — here
+    `BaseQuantizer.loss` places the encode memo's matrix there)."""
+
+    uses_mse4 = False
+    needs_distance = True
 
     def __init__(self, *args, temperature: float, **kwargs) -> None:
         super().__init__(*args, **kwargs)
         self._temperature = temperature
 
     def terms(self):
-        raise NotImplementedError('EntropyLoss needs the materialised N x K distance matrix (not on the B200 path yet)')
+        return {}
+
+    def forward(self, z: torch.Tensor, x: torch.Tensor, memo: dict) -> torch.Tensor:
+        affinity = memo['distance']
+        flat_affinity = affinity.reshape(-1, affinity.shape[-1])
+        flat_affinity = flat_affinity / self._temperature
+        probs = flat_affinity.softmax(-1)
+        log_probs = torch.log_softmax(flat_affinity + 1e-5, -1)
+        avg_probs = probs.mean(0)
+        avg_entropy = -torch.sum(avg_probs * torch.log(avg_probs + 1e-5))
+        sample_entropy = -torch.mean(torch.sum(probs * log_probs, -1))
+        return (sample_entropy - avg_entropy) * self.scale
 
 
 def build_losses(config: Mapping):

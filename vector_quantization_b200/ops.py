@@ -19,7 +19,7 @@ __all__ = [
     'Operand', 'as_operand', 'pack_rows', 'assign', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
     'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
-    'fsq_decode', 'transpose_last2', 'compact_tokens', 'comm_kmeans_ema_update', 'comm_cvq_update',
+    'fsq_decode', 'transpose_last2', 'compact_tokens', 'distance_matrix', 'comm_kmeans_ema_update', 'comm_cvq_update',
     'comm_allreduce_min_keys', 'comm_allreduce_sum_f32', 'BACKEND_TCGEN05', 'BACKEND_SIMT',
 ]
 
@@ -375,6 +375,18 @@ def embedding_gather(W: torch.Tensor, quant: torch.Tensor) -> torch.Tensor:
     out = torch.empty((flat.numel(), W.shape[1]), dtype=torch.float32, device=W.device)
     _call('vqb_embedding_gather', lib.vqb_embedding_gather, dev, _p(W), W.shape[0], W.shape[1], _p(flat), flat.numel(), _p(out), _S)
     return out.reshape(*quant.shape, W.shape[1])
+
+
+def distance_matrix(x: torch.Tensor, W: torch.Tensor, metric: str) -> torch.Tensor:
+    """Compatibility mode: the materialised fp32 [N, K] distance matrix (`torch.cdist` / `1 - cos`)."""
+    lib = _lib.load()
+    dev = _cuda(x, W)
+    assert W.dtype == torch.float32 and x.dim() == 2 and W.dim() == 2 and x.shape[1] == W.shape[1]
+    N, D = x.shape
+    out = torch.empty((N, W.shape[0]), dtype=torch.float32, device=x.device)
+    _call('vqb_distance_matrix', lib.vqb_distance_matrix, dev, _p(x), _dt(x), N, D, _p(W), W.shape[0],
+          int(metric == 'Cosine'), _p(out), _S)
+    return out
 
 
 # ---- fused peer-memory exchange + codebook update (csrc/comm.cu) ------------------------------------------------

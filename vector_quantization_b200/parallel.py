@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ['world_size', 'rank', 'all_reduce_sum_', 'all_gather_rows', 'all_reduce_min_keys_', 'shard_range',
-           'PeerRegion', 'peer_comm_enabled']
+           'PeerRegion', 'peer_comm_enabled', 'assert_sync']
 
 _SIGN = -(1 << 63)  # 0x8000... as int64
 # statistics payloads up to this size use the low-latency (flag-in-data) exchange protocol, larger ones the
@@ -86,6 +86,21 @@ def shard_range(total: int, r: int | None = None, w: int | None = None) -> tuple
 
 
 # ---- NVLink peer-memory regions (the fused exchange kernels of csrc/comm.cu) ---------------------------------
+# VQB_DRY_RUN=1: the reference's DRY_RUN replica-consistency assertions (update.py:54-55, anchors.py:52-53,62-63)
+DRY_RUN = os.environ.get('VQB_DRY_RUN', '0') not in ('', '0')
+
+
+def assert_sync(t: torch.Tensor, what: str = 'tensor') -> None:
+    """`todd.utils.is_sync`: every rank holds the same values (elementwise MIN == MAX over the ranks)."""
+    if not _on():
+        return
+    lo, hi = t.detach().clone(), t.detach().clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if not torch.equal(lo, hi):
+        raise AssertionError(f'{what} differs across ranks (max spread {float((hi - lo).abs().max())})')
+
+
 def peer_comm_enabled(device: torch.device) -> bool:
     """The fused peer-memory exchange is the default whenever several ranks drive CUDA devices of one node;
     VQB_COMM=nccl keeps the torch.distributed collectives (e.g. multi-node jobs)."""

@@ -115,8 +115,34 @@ class BaseQuantizer(nn.Module):
         z = self._callbacks.after_decode(z, memo)
         return z, memo
 
+    def _loss(self, z: torch.Tensor, x: torch.Tensor, memo: dict):
+        """reference base.py:151-160: evaluate the configured losses, record them in the (loss) memo, sum."""
+        losses = self._losses(z, x, memo)
+        memo.update(losses)
+        loss = x.new_zeros([], dtype=torch.float32)
+        for v in losses.values():
+            loss = loss + v
+        return loss, memo
+
+    def loss(self, z: torch.Tensor, x: torch.Tensor, memo: dict):
+        """reference base.py:162-171."""
+        z, x = self._callbacks.before_loss(z, x, memo)
+        loss_memo = get_memo(memo, 'loss')
+        distance = memo.get('encode', {}).get('distance') if isinstance(memo.get('encode'), dict) else None
+        if distance is not None:
+            loss_memo.setdefault('distance', distance)     # where EntropyLoss looks it up (losses.py:142)
+        loss, memo['loss'] = self._loss(z, x, loss_memo)
+        memo['loss'].pop('distance', None)
+        loss = self._callbacks.after_loss(loss, memo)
+        return loss, memo
+
     def forward(self, x: torch.Tensor, memo: dict):
-        raise NotImplementedError
+        """reference base.py:173-182 (the template; VectorQuantizer overrides it with the fused kernels)."""
+        x, quant, memo = self.encode(x, memo)
+        memo.update(x=x, quant=quant)
+        z, memo = self.decode(quant, memo)
+        loss, memo = self.loss(z, x, memo)
+        return z, loss, memo
 
 
 @VQITQuantizerRegistry.register_()
@@ -125,13 +151,16 @@ class VectorQuantizer(BaseQuantizer):
     kernel launches: pack+assign (tcgen05, no N x K matrix), [stats/update], fused gather+STE+loss."""
 
     def __init__(self, *args, embedding: nn.Embedding, distance: BaseDistance, precision: str = Fq.DEFAULT_PRECISION,
-                 **kwargs) -> None:
+                 materialize_distance: bool = False, **kwargs) -> None:
         super().__init__(*args, **kwargs)
         if precision not in Fq.PRECISION_PLANES:
             raise ValueError(f'precision must be one of {sorted(Fq.PRECISION_PLANES)}')
         self._embedding = embedding
         self._distance = distance
         self.precision = precision
+        # COMPATIBILITY / DEBUG switch: also build the reference's memo['encode']['distance'] ([N, K], quantizers.py:98)
+        # for user callbacks that read it.  Implied by an EntropyLoss or a MultinomialAnchor in the config.
+        self.materialize_distance = bool(materialize_distance)
         self._pending = weakref.WeakSet()   # CodebookRef of every forward whose backward has not run yet
 
     def protect_saved_codebook(self) -> None:
@@ -185,8 +214,24 @@ class VectorQuantizer(BaseQuantizer):
             raise VQBError('the codebook must live on a CUDA device; there is no CPU fallback')
         return W
 
-    @torch.no_grad()
+    @property
+    def wants_distance(self) -> bool:
+        return (self.materialize_distance or self._callbacks.needs_distance
+                or any(loss.needs_distance for loss in self._losses.values()))
+
     def _encode(self, x: torch.Tensor, memo: dict):
+        if self.wants_distance:
+            # compatibility mode: the reference's differentiable [N, K] matrix against the codebook as it is BEFORE
+            # this step's update (`self.embeddings` clones, quantizers.py:84-85,97-98)
+            W = self._weight()
+            if memo.get('_normalize_codebook', False):
+                self.protect_saved_codebook()
+                ops.pack_rows(W.data, normalize=True, planes=1, writeback=W.data)     # NormalizeCallback, in place
+            memo['distance'] = Fq.distance_matrix(_check_tokens(x, self.embedding_dim), W.clone(), self._distance.metric)
+        return self._encode_nograd(x, memo)
+
+    @torch.no_grad()
+    def _encode_nograd(self, x: torch.Tensor, memo: dict):
         """Nearest code per token.  Launches: codebook pack (normalise-in-place + operand planes + key reset),
         [token pack unless zero-copy], tcgen05 assignment, [key unpack unless deferred to the gather kernel]."""
         x = _check_tokens(x.detach(), self.embedding_dim)
@@ -218,8 +263,38 @@ class VectorQuantizer(BaseQuantizer):
         return ops.unpack_keys(keys), memo
 
     def _decode(self, quant: torch.Tensor, memo: dict):
-        """Decode-only gather (decode_from_quant); any index shape.  Inference path: no autograd."""
-        return ops.embedding_gather(self._weight().data, quant.contiguous()), memo
+        """`nn.Embedding` gather, any index shape (decode_from_quant).  Differentiable w.r.t. the codebook when it
+        requires grad (the unfused template path); plain gather kernel otherwise."""
+        W = self._weight()
+        if torch.is_grad_enabled() and W.requires_grad:
+            return Fq.embedding_lookup(W, quant), memo
+        return ops.embedding_gather(W.data, quant.contiguous()), memo
+
+    def _loss(self, z: torch.Tensor, x: torch.Tensor, memo: dict):
+        """Standalone `loss(z, x)` of the reference template (base.py:151-160) on ARBITRARY (z, x): the fused kernel
+        is reused with z as the "codebook" and the identity assignment, which yields exactly mse(z, x) with the
+        codebook-role gradient routed to z and the commitment-role gradient to x."""
+        x2, z2 = x.reshape(-1, x.shape[-1]), z.reshape(-1, z.shape[-1]).float()
+        index = torch.arange(x2.shape[0], dtype=torch.int64, device=x2.device)
+        _, mse4, _, _ = Fq.quantize_ste_loss(_check_tokens(x2, self.embedding_dim), z2.contiguous(), index,
+                                             self._loss_terms())
+        losses = {name: (m.from_mse4(mse4) if m.uses_mse4 else m(z, x, memo)) for name, m in self._losses.items()}
+        memo.update(losses)
+        loss = mse4[0].new_zeros([])
+        for v in losses.values():
+            loss = loss + v
+        return loss, memo
+
+    def _forward_template(self, x: torch.Tensor, memo: dict):
+        """The reference's unfused template (base.py:173-182 + quantizers.py:110-117) for configurations whose
+        callbacks hook decode / loss: every hook point is honoured; each stage is still a kernel of the C-ABI."""
+        x = _check_tokens(x, self.embedding_dim)
+        x, quant, memo = self.encode(x, memo)
+        memo.update(x=x, quant=quant)
+        z, memo = self.decode(quant, memo)
+        loss, memo = self.loss(z, x, memo)
+        z = x + (z - x).detach()                       # ste, utils/ste.py:9-10
+        return z, loss, memo
 
     def _loss_terms(self):
         want_norm = False
@@ -228,15 +303,14 @@ class VectorQuantizer(BaseQuantizer):
         return want_norm
 
     def forward(self, x: torch.Tensor, memo: dict):
-        for hook in ('before_decode', 'after_decode', 'before_loss', 'after_loss'):
-            if self._callbacks.overrides(hook):
-                raise NotImplementedError(f'callbacks overriding {hook} are not supported by the fused decode/loss path')
+        if any(self._callbacks.overrides(h) for h in ('before_decode', 'after_decode', 'before_loss', 'after_loss')):
+            return self._forward_template(x, memo)
         x = _check_tokens(x, self.embedding_dim)
         # The packed keys go straight into the fused gather kernel, which also emits memo['quant'] — unless a callback
         # that overrides after_encode needs int64 indices first (VQKDCallback reads the keys itself).
         lazy_unpack = self._callbacks.packed_keys_ok()
         # NormalizeCallback may defer F.normalize(x) into the fused kernels only when nobody else reads x
-        memo['_lazy_normalize'] = self._callbacks.lazy_normalize_ok()
+        memo['_lazy_normalize'] = self._callbacks.lazy_normalize_ok() and not self.wants_distance
         memo['_lazy_unpack'] = lazy_unpack
         x, index, memo = self.encode(x, memo)
         memo.pop('_lazy_normalize', None)
@@ -252,10 +326,14 @@ class VectorQuantizer(BaseQuantizer):
         memo['decode'] = get_memo(memo, 'decode')
         loss_memo = get_memo(memo, 'loss')
         loss = None
+        distance = memo['encode'].get('distance')
+        if distance is not None:
+            loss_memo['distance'] = distance              # where EntropyLoss looks it up (losses.py:142)
         for name, module in self._losses.items():
-            value = module.from_mse4(mse4)
+            value = module.from_mse4(mse4) if module.uses_mse4 else module(z, memo['x'], loss_memo)
             loss_memo[name] = value
             loss = value if loss is None else loss + value
+        loss_memo.pop('distance', None)
         if loss is None:
             loss = mse4[0].new_zeros([])
         return z, loss, memo

@@ -18,7 +18,7 @@ from . import functional as Fq
 from . import ops
 from .quantizers import VectorQuantizer, get_memo
 
-__all__ = ['quantize', 'encode_to_quant', 'save_tokens', 'load_tokens', 'save_llamagen_codes']
+__all__ = ['quantize', 'encode_to_quant', 'save_tokens', 'load_tokens', 'save_llamagen_codes', 'TokenStreamWriter']
 
 
 def quantize(quantizer, x: torch.Tensor, memo: dict):
@@ -41,8 +41,7 @@ def encode_to_quant(quantizer, x: torch.Tensor, memo: dict, *, compact: bool = F
     quantizer_memo['x_shape'] = (b, _, h, w) = tuple(x.shape)
     rows = Fq.nchw_to_rows(x)
     # keep the packed keys (no int64 unpack launch) unless a training callback consumes the indices in after_encode
-    lazy = (compact and isinstance(quantizer, VectorQuantizer)
-            and not (quantizer.training and quantizer._callbacks.overrides('after_encode')))
+    lazy = compact and isinstance(quantizer, VectorQuantizer) and quantizer._callbacks.packed_keys_ok()
     if lazy:
         quantizer_memo['_lazy_unpack'] = True
     rows, quant, memo['quantizer'] = quantizer.encode(rows, quantizer_memo)
@@ -65,6 +64,84 @@ def save_tokens(path: str | pathlib.Path, id_: Sequence[Any], category: torch.Te
     if tokens.dtype != torch.int64:
         tokens = tokens.to(torch.int32).to(torch.int64) if tokens.dtype == torch.uint16 else tokens.to(torch.int64)
     torch.save(dict(id_=id_, category=category, tokens=tokens.cpu()), str(path))
+
+
+class TokenStreamWriter:
+    """Streaming variant of `TokenizeCallback` (runners/callbacks.py:29-53): one `{iter}_{rank}.pth` `Tokens` file per
+    iteration under `token_dir`, written WITHOUT stalling the GPU.  `write` enqueues an asynchronous device-to-host
+    copy of the token ids into a pinned staging buffer on a side stream and returns; a background thread waits for
+    the copy (CUDA event) and does the `torch.save`.  `depth` staging buffers bound the memory; `close()` (or
+    leaving the `with` block) drains the queue.  The files are exactly what `save_tokens` writes."""
+
+    def __init__(self, token_dir: str | pathlib.Path, rank: int = 0, depth: int = 4) -> None:
+        import queue
+        import threading
+        self.token_dir = pathlib.Path(token_dir)
+        self.token_dir.mkdir(parents=True, exist_ok=True)       # TokenizeCallback.bind
+        self.rank = rank
+        self._free: 'queue.Queue' = queue.Queue()
+        for _ in range(depth):
+            self._free.put(None)                                # staging slots, allocated lazily at the first size seen
+        self._jobs: 'queue.Queue' = queue.Queue()
+        self._stream = None
+        self._error = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self) -> None:
+        while True:
+            job = self._jobs.get()
+            if job is None:
+                return
+            path, id_, category, host, event, shape = job
+            try:
+                if event is not None:
+                    event.synchronize()
+                tokens = host.reshape(shape)
+                if tokens.dtype != torch.int64:
+                    tokens = tokens.to(torch.int32).to(torch.int64) if tokens.dtype == torch.uint16 else tokens.to(torch.int64)
+                torch.save(dict(id_=id_, category=category, tokens=tokens.clone()), str(path))
+            except Exception as exc:  # noqa: BLE001 - surfaced by the next write()/close()
+                self._error = exc
+            finally:
+                self._free.put(host)
+
+    def write(self, iter_: int, id_: Sequence[Any], category: torch.Tensor, quant: torch.Tensor,
+              x_shape: Sequence[int]) -> pathlib.Path:
+        if self._error is not None:
+            raise self._error
+        b, _, h, w = x_shape
+        host = self._free.get()                                 # blocks only when `depth` writes are in flight
+        flat = quant.reshape(-1)
+        if host is None or host.numel() != flat.numel() or host.dtype != flat.dtype:
+            host = torch.empty(flat.numel(), dtype=flat.dtype).pin_memory() if flat.is_cuda else torch.empty_like(flat)
+        event = None
+        if flat.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=flat.device)
+            self._stream.wait_stream(torch.cuda.current_stream(flat.device))
+            with torch.cuda.stream(self._stream):
+                host.copy_(flat, non_blocking=True)
+                flat.record_stream(self._stream)
+                event = torch.cuda.Event()
+                event.record(self._stream)
+        else:
+            host.copy_(flat)
+        path = self.token_dir / f'{iter_}_{self.rank}.pth'
+        self._jobs.put((path, list(id_), category.detach().cpu(), host, event, (b, h, w)))
+        return path
+
+    def close(self) -> None:
+        self._jobs.put(None)
+        self._thread.join()
+        if self._error is not None:
+            raise self._error
+
+    def __enter__(self) -> 'TokenStreamWriter':
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
 
 
 def load_tokens(path: str | pathlib.Path) -> dict:
