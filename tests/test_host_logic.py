@@ -100,7 +100,7 @@ def test_composed_callback_priority_order():
 
 
 def test_unsupported_components_fail_loudly():
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(vqb._lib.VQBError):          # the distance modules materialise on the GPU only (compat mode)
         vqb.L2Distance()(torch.zeros(2, 2), torch.zeros(2, 2))
     q = vqb.build_quantizer(VQGAN)
     with pytest.raises(vqb._lib.VQBError):          # CPU tensors: no fallback
@@ -233,3 +233,44 @@ def test_operand_format_selection(monkeypatch):
     book = Fq.pack_codebook(W, 'L2', tokens=xb)                                          # un-normalised rows: no fp16
     assert book.fmt == 'bf16' and calls[-1]['planes'] == 3 and calls[-1]['want_half_sqnorm']
     assert Fq.pack_codebook(W, 'L2', tokens=xb, writeback_normalized=True).fmt == 'bf16'  # LlamaGen L2 stays on bf16 planes
+
+
+def test_compat_components_build_from_reference_style_configs():
+    """EntropyLoss / MultinomialAnchor / VQGAN_VQKDCallback / materialize_distance: registry names, flags that switch
+    the quantizer into the distance-materialising compatibility mode, and the packed-key / raw-token gating."""
+    emb = dict(type='torch_nn_modules_sparse_Embedding', num_embeddings=64, embedding_dim=8)
+    q = vqb.build_quantizer(dict(
+        type='VQGANQuantizer', embedding=emb, distance=dict(type='CosineDistance'),
+        callbacks=[dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='MultinomialAnchor'))],
+        losses=dict(vqgan_loss=dict(type='VQGANLoss'), ent=dict(type='EntropyLoss', temperature=0.5)),
+        init_weights=dict(type='vqgan')))
+    assert q.wants_distance and q._callbacks.needs_distance and not q._callbacks.needs_column_nearest
+    assert not q._loss_terms() and not q._losses['ent'].uses_mse4
+    plain = vqb.build_quantizer(VQGAN)
+    assert not plain.wants_distance
+    plain.materialize_distance = True
+    assert plain.wants_distance
+    q2 = vqb.build_quantizer(dict(type='VQGANQuantizer', embedding=emb, distance=dict(type='L2Distance'),
+                                  callbacks=[dict(type='VQGAN_VQKDCallback', ema=dict(decay=0.9))],
+                                  losses=dict(l=dict(type='VQGANLoss')), init_weights=dict(type='vqgan')))
+    cb = list(q2._callbacks)[0]
+    assert type(cb).__name__ == 'VQGAN_VQKDCallback' and cb._ema.decay == 0.9
+    assert q2._callbacks.lazy_normalize_ok() and q2._callbacks.packed_keys_ok() and len(q2._forward_pre_hooks) == 1
+    # NormalizeCallback + CVQVAECallback (llamagen + cvqvae mixin): tokens must be normalised up front
+    q3 = vqb.build_quantizer(dict(type='VQGANQuantizer', embedding=emb, distance=dict(type='L2Distance'),
+                                  callbacks=[dict(type='NormalizeCallback'),
+                                             dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='NearestAnchor'))],
+                                  losses=dict(l=dict(type='VQGANLoss')), init_weights=dict(type='vqgan')))
+    assert not q3._callbacks.lazy_normalize_ok() and not q3._callbacks.packed_keys_ok()
+    q3.eval()
+    assert q3._callbacks.packed_keys_ok()
+
+
+def test_token_stream_writer_on_host_tensors(tmp_path):
+    from vector_quantization_b200 import tokenizer
+    with tokenizer.TokenStreamWriter(tmp_path, rank=3) as w:
+        for it in range(5):
+            w.write(it, [f'a{it}', f'b{it}'], torch.tensor([1, 2]), torch.arange(32, dtype=torch.int32) + it, (2, 8, 4, 4))
+    rec = tokenizer.load_tokens(tmp_path / '2_3.pth')
+    assert rec['tokens'].shape == (2, 4, 4) and rec['tokens'].dtype == torch.int64 and int(rec['tokens'][0, 0, 0]) == 2
+    assert rec['id_'] == ['a2', 'b2'] and len(list(tmp_path.glob('*.pth'))) == 5
