@@ -27,17 +27,18 @@ def test_distance_matrix_forward_and_backward_vs_oracle(dev, metric, N, K, D):
     x, E = O.synthetic_latents(N, K, D, seed=N + K)
     g = torch.Generator().manual_seed(1)
     G = torch.randn(N, K, generator=g)
-    xo, Eo = x.clone().requires_grad_(True), E.clone().requires_grad_(True)
+    # the oracle's formula evaluated in float64: an fp32 CPU cdist is itself only good to ~1e-6 * (|x|^2 + |e|^2) / d
+    xo, Eo = x.double().requires_grad_(True), E.double().requires_grad_(True)
     d_ref = O.distance(metric, xo, Eo)
-    (d_ref * G).sum().backward()
+    (d_ref * G.double()).sum().backward()
     xg, Eg = x.to(dev).requires_grad_(True), E.to(dev).requires_grad_(True)
     d = Fq.distance_matrix(xg, Eg, metric)
     (d * G.to(dev)).sum().backward()
-    torch.testing.assert_close(d.detach().cpu(), d_ref.detach(), rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(d.detach().cpu(), d_ref.detach().float(), rtol=1e-5, atol=2e-5)
     far = (d_ref.detach() > 1e-3)              # cdist's gradient is singular at d = 0
     assert far.float().mean() > 0.99
-    torch.testing.assert_close(xg.grad.cpu(), xo.grad, rtol=2e-4, atol=2e-4)
-    torch.testing.assert_close(Eg.grad.cpu(), Eo.grad, rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(xg.grad.cpu(), xo.grad.float(), rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(Eg.grad.cpu(), Eo.grad.float(), rtol=2e-4, atol=2e-4)
     # the distance modules return the same matrix (what `quantizer.distance(x, e)` gives user code)
     mod = vqb.L2Distance() if metric == 'L2' else vqb.CosineDistance()
     assert torch.equal(mod(x.to(dev), E.to(dev)), d.detach())
@@ -145,8 +146,12 @@ def test_cvqvae_training_step_with_multinomial_anchor(dev):
     p = O.ema(torch.zeros(K), O.frequency([quant], K), 0.99)
     dec = (1 - torch.exp(-p * K * 10 / (1 - 0.99) - 1e-3)).unsqueeze(1)
     anchors = (W - E * dec) / (1 - dec)                             # solve the blend for the anchor row
-    nearest = torch.cdist(anchors, x).min(1).values
-    assert (nearest < 1e-3 * x.norm(dim=1).max()).all(), 'every anchor must be one of the token rows'
+    light = (1 - dec).flatten() > 0.5                               # rarely used codes: the anchor dominates the blend
+    assert light.sum() >= 4
+    nearest = torch.cdist(anchors[light].double(), x.double()).min(1).values
+    assert (nearest < 1e-4 * x.norm(dim=1).max()).all(), 'every anchor must be one of the token rows'
+    heavy = ~light                                                  # frequently used codes barely move
+    torch.testing.assert_close(W[heavy], (E * dec)[heavy], rtol=0, atol=float((1 - dec)[heavy].max() * x.abs().max()) + 1e-6)
     torch.testing.assert_close(q.get_buffer('_probability').cpu(), p, rtol=1e-6, atol=1e-9)
 
 
@@ -206,7 +211,7 @@ def test_hooked_template_forward_equals_fused_forward(dev):
     assert m1.get('seen_after_decode') and torch.equal(m0['quant'], m1['quant'])
     torch.testing.assert_close(z1, z0, rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(l1, 2 * l0, rtol=1e-5, atol=1e-8)
-    torch.testing.assert_close(gx1 - 1, 2 * (gx0 - 1), rtol=1e-4, atol=1e-7)   # d(z.sum())/dx = 1 on both paths
+    torch.testing.assert_close(gx1 - 1, 2 * (gx0 - 1), rtol=1e-4, atol=1e-6)   # d(z.sum())/dx = 1 on both paths
     torch.testing.assert_close(gW1, 2 * gW0, rtol=1e-4, atol=1e-7)
 
 
