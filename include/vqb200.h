@@ -79,6 +79,8 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D,
                   float* writeback_f32,     /* optional [rows, D]: the (normalised) fp32 row; may alias src when src is fp32 */
                   unsigned long long* keys_to_reset, int64_t n_keys, /* optional: fill with 0xFF.. (fused memset for vqb_assign) */
                   void* zero_fill, int64_t zero_bytes, /* optional: fused zero-fill (16-byte aligned, multiple of 16 bytes) of the step's statistics buffer */
+                  float* lo_norm_max, /* optional, VQB_PLANES_F16X2: *lo_norm_max = max(*lo_norm_max, max_j |row_j - hi_j|_2), the error
+                                         bound of a contraction that uses the hi plane only (pre-zeroed DEVICE scalar) */
                   void* stream);
 
 /* ---- nearest-code assignment ------------------------------------------------------------ *
@@ -106,6 +108,37 @@ int vqb_assign(const void* a_planes, int a_nplanes, int64_t a_rows, int64_t a_pl
                int side_mode /* 0 none, 1: score -= b_side[j] (L2, 0.5|b_j|^2), 2: score *= b_side[j] (1/|b_j|) */,
                int64_t b_index_offset,
                unsigned long long* keys, int backend, void* stream);
+
+/* vqb_assign plus the two hooks of the CERTIFIED ONE-TERM pass (D >= 128 is bound by the tensor pipe, and an fp32
+ * codebook costs two MMA terms as an fp16 pair):
+ *   second_keys  optional [a_rows], all-ones initialised: receives the packed key of the RUNNER-UP score of every row
+ *                (index field unspecified).  Run the contraction with the hi plane only (b_nplanes = VQB_PLANES_F16 on a
+ *                pair buffer), then vqb_certify: a row whose best - runner-up exceeds twice the operand error bound has
+ *                provably the same arg-max as the two-term contraction; the others are re-run exactly.
+ *   a_rows_dev   optional DEVICE int: the number of valid A rows is min(a_rows, *a_rows_dev) (the re-run of the
+ *                uncertified rows: their count only exists on the device; a_rows is the capacity of the buffer). */
+int vqb_assign_ex(const void* a_planes, int a_nplanes, int64_t a_rows, int64_t a_plane_rows,
+                  const void* b_planes, int b_nplanes, int64_t b_rows, int64_t b_plane_rows,
+                  int D, const float* b_side, int side_mode, int64_t b_index_offset,
+                  unsigned long long* keys, unsigned long long* second_keys, const int* a_rows_dev, int backend,
+                  void* stream);
+/* Lists, in ASCENDING row order (deterministic: every rank of a sharded run builds the same list), the rows r with
+ *   score(keys[r]) - score(second_keys[r]) <= 2 * eps_r,   eps_r = (*delta + noise) * s_r,
+ * s_r = 1 / row_inv_norm[r] (the token norm: scores are <x_r, e_j>) or 1 when row_inv_norm is NULL (scores already
+ * carry the 1/|x| column scale); *delta = max_j |e_j - hi_j| from vqb_pack_rows.  *count receives their number and
+ * compact_keys[0 .. count) is reset to all-ones for the exact re-run.  workspace: vqb_certify_workspace_bytes(rows). */
+int64_t vqb_certify_workspace_bytes(int64_t rows);
+int vqb_certify(const unsigned long long* keys, const unsigned long long* second_keys, int64_t rows,
+                const float* row_inv_norm, const float* delta, float noise, int* row_list, int* count,
+                unsigned long long* compact_keys, void* workspace, void* stream);
+/* dst[p][i][:] = src[p][row_list[i]][:] for i < *count (16-bit planes, Dp a multiple of 8) */
+int vqb_gather_plane_rows(const void* src, int nplanes, int64_t src_plane_rows, int Dp, const int* row_list,
+                          const int* count, int64_t cap, void* dst, int64_t dst_plane_rows, void* stream);
+/* dst[i] = src[row_list[i]] for i < *count (fp32 side vectors of the gathered rows) */
+int vqb_gather_f32(const float* src, const int* row_list, const int* count, int64_t cap, float* dst, void* stream);
+/* keys[row_list[i]] = compact_keys[i] for i < *count */
+int vqb_scatter_keys(const unsigned long long* compact_keys, const int* row_list, const int* count, int64_t cap,
+                     unsigned long long* keys, void* stream);
 
 /* out[r] = 1 / max(||x_r||, 1e-12), zero in the padding up to vqb_operand_rows_pad(rows): the side_mode-2 column
  * scale that lets the column arg-min of NearestAnchor use RAW (un-normalised, one exact bf16 plane) tokens. */

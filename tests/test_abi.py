@@ -44,7 +44,7 @@ def test_load_and_pure_host_entry_points():
 
 def test_bad_arguments_return_error_codes_not_crashes():
     lib = _lib.load()
-    assert lib.vqb_pack_rows(None, 0, 10, 8, 0, 1, None, None, None, None, 0, None, 0, None) == -1
+    assert lib.vqb_pack_rows(None, 0, 10, 8, 0, 1, None, None, None, None, 0, None, 0, None, None) == -1
     assert b'null pointer' in lib.vqb_last_error()
     assert lib.vqb_assign(None, 1, 1, 0, None, 1, 1, 0, 8, None, 0, 0, None, 0, None) == -1
 

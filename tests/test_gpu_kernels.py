@@ -518,3 +518,68 @@ def test_fsq(dev, levels, N):
     zd = ops.fsq_decode(ik, p)
     assert torch.equal(zd.cpu(), fsq.decode(ik.cpu().long()).float())
     torch.testing.assert_close(zd, zk, rtol=0, atol=2e-7)
+
+
+# ---- certified one-term pass (D >= 128, fp16-pair codebook): identical to the two-term contraction -----------------
+@pytest.mark.parametrize('clustered', [True, False], ids=['clustered', 'random'])
+@pytest.mark.parametrize('N,K,D', [(4096, 2048, 128), (3000, 1000, 256), (2048, 4096, 768), (513, 300, 200)])
+def test_certified_one_term_assignment_equals_two_term(dev, N, K, D, clustered):
+    """ONE MMA term (hi plane) + certificate + exact re-run of the uncertified rows == the two-term fp16-pair
+    contraction, index for index, for the row arg-min (tokens x codebook) and the column arg-min (codebook x tokens
+    with the 1/|x| column scale).  On random data a few per cent of the rows fail the certificate and take the
+    re-run; on clustered data almost none do."""
+    from vector_quantization_b200 import functional as Fq
+    x, E = O.synthetic_latents(N, K, D, seed=N + D, normalized_codebook=True, clustered=clustered)
+    xb = x.to(torch.bfloat16).to(dev)
+    book = ops.pack_rows(E.to(dev), normalize=True, fmt='f16x2', want_lo_norm=True)
+    assert 0 < float(book.lo_norm_max) < 2.0 ** -11
+    toks = ops.pack_rows(xb, fmt='f16')
+    toks.inv_norm = ops.row_inv_norm(xb, f16_rows=True)
+    # row arg-min
+    want = ops.assign(toks, book, ops.new_keys(N, dev), l2=False)
+    got = Fq.certified_assign(toks, book, ops.new_keys(N, dev), a_inv_norm=toks.inv_norm)
+    flagged_rows = int(Fq.LAST_CERTIFY['count'])
+    assert torch.equal(ops.unpack_keys(got), ops.unpack_keys(want))
+    # column arg-min (NearestAnchor): codes as rows, raw tokens as columns with the 1/|x_n| scale
+    want_c = ops.assign(book, toks, ops.new_keys(K, dev), l2=False, scale_columns=True)
+    got_c = Fq.certified_assign(book, toks, ops.new_keys(K, dev), scale_columns=True)
+    flagged_cols = int(Fq.LAST_CERTIFY['count'])
+    assert torch.equal(ops.unpack_keys(got_c), ops.unpack_keys(want_c))
+    if clustered:
+        assert flagged_rows <= N // 50
+    else:
+        assert 0 < flagged_rows < N // 2 and 0 < flagged_cols < K, (flagged_rows, flagged_cols)
+    # ... and it is the oracle's arg-min under the near-tie policy
+    q_ref, d = O.encode('Cosine', xb.float().cpu(), E)
+    rows, gap = O.index_mismatch_report(d, q_ref, ops.unpack_keys(got).cpu())
+    assert (gap < 1e-5).all() and rows.numel() <= max(2, N // 200)
+
+
+def test_certified_pass_through_the_module(dev):
+    """cfg-4-like CVQ-VAE step (D = 256, cosine, bf16 tokens): the module takes the certified path for both passes and
+    still matches the oracle step."""
+    from vector_quantization_b200 import functional as Fq
+    import vector_quantization_b200 as vqb
+    N, K, D = 2048, 512, 256
+    x, E = O.synthetic_latents(N, K, D, seed=21, normalized_codebook=True)
+    cfg = dict(type='VQGANQuantizer', embedding=dict(type='torch_nn_modules_sparse_Embedding', num_embeddings=K, embedding_dim=D),
+               distance=dict(type='CosineDistance'),
+               callbacks=[dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='NearestAnchor'))],
+               losses=dict(vqgan_loss=dict(type='VQGANLoss')), init_weights=dict(type='vqgan'))
+    q = vqb.build_quantizer(cfg, training=True).to(dev)
+    with torch.no_grad():
+        q.embedding.weight.copy_(E)
+    Fq.LAST_CERTIFY.clear()
+    xb = x.to(torch.bfloat16)
+    z, loss, memo = q(xb.to(dev).requires_grad_(True), dict())
+    assert 'count' in Fq.LAST_CERTIFY, 'the certified one-term pass did not run'
+    spec = O.QuantizerSpec(distance='Cosine', callback='CVQVAECallback', losses={'vqgan_loss': dict(type='VQGANLoss')})
+    out = O.quantizer_forward(spec, [xb.float()], E, torch.zeros(K))
+    rows, gap = O.index_mismatch_report(out['distance'][0], out['quant'][0], memo['quant'].cpu())
+    assert (gap < 1e-5).all() and rows.numel() <= 4
+    torch.testing.assert_close(loss.detach().cpu(), out['loss'][0].detach(), rtol=1e-5, atol=1e-7)
+    if rows.numel() == 0:
+        col = ops.unpack_keys(memo['encode']['column_keys']).cpu()
+        same = col == out['anchor_idx'][0]
+        assert same.float().mean() > 0.99
+        torch.testing.assert_close(q.embedding.weight.detach().cpu()[same], out['weight'][same], rtol=1e-5, atol=1e-6)

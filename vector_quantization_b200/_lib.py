@@ -44,7 +44,16 @@ SIGNATURES = {
     'vqb_operand_rows_pad': (c_int64, [c_int64]),
     'vqb_operand_bytes': (c_size_t, [c_int64, c_int, c_int]),
     'vqb_pack_rows': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+                              c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    'vqb_assign_ex': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p,
+                              c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'vqb_certify_workspace_bytes': (c_int64, [c_int64]),
+    'vqb_certify': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p]),
+    'vqb_gather_plane_rows': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                      c_void_p]),
+    'vqb_gather_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'vqb_scatter_keys': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'vqb_assign': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p,
                            c_int, c_int64, c_void_p, c_int, c_void_p]),
     'vqb_row_inv_norm': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),

@@ -9,7 +9,8 @@ namespace vqb {
 
 int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_plane_rows, const void* b_planes, int pb,
                      int64_t b_rows, int64_t b_plane_rows, int D, const float* b_side, int side_mode,
-                     int64_t b_index_offset, unsigned long long* keys, cudaStream_t st);
+                     int64_t b_index_offset, unsigned long long* keys, unsigned long long* second_keys,
+                     const int* a_rows_dev, cudaStream_t st);
 
 constexpr int SA = 128;  // A rows per block (one per thread)
 constexpr int SB = 32;   // B rows per inner tile
@@ -89,11 +90,26 @@ __global__ void __launch_bounds__(SA) assign_simt_kernel(const __nv_bfloat16* __
 
 using namespace vqb;
 
+extern "C" int vqb_assign_ex(const void* a_planes, int pa, int64_t a_rows, int64_t a_plane_rows, const void* b_planes,
+                             int pb, int64_t b_rows, int64_t b_plane_rows, int D, const float* b_half_sqnorm,
+                             int side_mode, int64_t b_index_offset, unsigned long long* keys,
+                             unsigned long long* second_keys, const int* a_rows_dev, int backend, void* stream);
+
 extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, int64_t a_plane_rows, const void* b_planes,
                           int pb, int64_t b_rows, int64_t b_plane_rows, int D, const float* b_half_sqnorm,
                           int side_mode, int64_t b_index_offset, unsigned long long* keys, int backend,
                           void* stream) {
+  return vqb_assign_ex(a_planes, pa, a_rows, a_plane_rows, b_planes, pb, b_rows, b_plane_rows, D, b_half_sqnorm, side_mode,
+                       b_index_offset, keys, nullptr, nullptr, backend, stream);
+}
+
+extern "C" int vqb_assign_ex(const void* a_planes, int pa, int64_t a_rows, int64_t a_plane_rows, const void* b_planes,
+                             int pb, int64_t b_rows, int64_t b_plane_rows, int D, const float* b_half_sqnorm,
+                             int side_mode, int64_t b_index_offset, unsigned long long* keys,
+                             unsigned long long* second_keys, const int* a_rows_dev, int backend, void* stream) {
   VQB_REQUIRE(a_planes && b_planes && keys, "vqb_assign: null pointer");
+  VQB_REQUIRE(backend == VQB_BACKEND_TCGEN05 || (second_keys == nullptr && a_rows_dev == nullptr),
+              "vqb_assign_ex: runner-up keys / device row count need the tcgen05 backend");
   VQB_REQUIRE(a_rows >= 1 && b_rows >= 1 && D >= 1, "vqb_assign: bad shape a_rows=%lld b_rows=%lld D=%d",
               (long long)a_rows, (long long)b_rows, D);
   VQB_REQUIRE(planes_valid(pa) && planes_valid(pb), "vqb_assign: planes must be 1..3, VQB_PLANES_F16 or VQB_PLANES_F16X2");
@@ -110,7 +126,7 @@ extern "C" int vqb_assign(const void* a_planes, int pa, int64_t a_rows, int64_t 
   VQB_REQUIRE(side_mode >= 0 && side_mode <= 2, "vqb_assign: side_mode must be 0 (none), 1 (subtract) or 2 (scale)");
   if (backend == VQB_BACKEND_TCGEN05)
     return assign_tc_launch(a_planes, pa, a_rows, a_plane_rows, b_planes, pb, b_rows, b_plane_rows, D, b_half_sqnorm,
-                            side_mode, b_index_offset, keys, st);
+                            side_mode, b_index_offset, keys, second_keys, a_rows_dev, st);
   VQB_REQUIRE(backend == VQB_BACKEND_SIMT, "vqb_assign: unknown backend %d", backend);
   const int Dp = (int)vqb_operand_dp(D);
   const int64_t a_tiles = (a_rows + SA - 1) / SA;

@@ -266,33 +266,30 @@ __device__ __forceinline__ float chunk_max(const float (&s)[32]) {
   const float m0 = fmax3(m[0], m[1], m[2]), m1 = fmax3(m[3], m[4], m[5]), m2 = fmax3(m[6], m[7], m[8]);
   return fmax3(fmax3(m0, m1, m2), m[9], m[10]);
 }
+template <bool CERT>
 __device__ __forceinline__ void chunk_commit(float mx, const float (&s)[32], uint32_t col_base, uint32_t stash_saddr,
-                                             float& best, uint32_t& best_col) {
+                                             float& best, uint32_t& best_col, float& second) {
   const bool better = mx > best;  // strict: an equal score later in the scan never displaces an earlier chunk
+  // certified one-term mode: runner-up over the chunk maxima (the loser of every comparison); the runner-up INSIDE the
+  // winning chunk is added at flush time from the stash
+  if constexpr (CERT) second = fmaxf(second, fminf(best, mx));
   best = fmaxf(best, mx);
   best_col = better ? col_base : best_col;
   // warp-uniform skip: after the first few code tiles most chunks improve no row of the warp
   if (__any_sync(0xffffffffu, better)) stash_chunk((uint32_t)better, stash_saddr, s);
 }
-template <int SIDE, bool MASK>
-__device__ __forceinline__ void chunk_argmax(const uint32_t (&r)[32], uint32_t side_saddr, uint32_t col_base,
-                                             int n_valid, uint32_t stash_saddr, float& best, uint32_t& best_col) {
-  float s[32];
-  chunk_scores<SIDE, MASK>(r, side_saddr, n_valid, s);
-  chunk_commit(chunk_max(s), s, col_base, stash_saddr, best, best_col);
-}
 // Two adjacent chunks at once: their max trees are independent, so the scheduler can interleave the two
 // dependent FMNMX3 chains (the reduction is latency-bound with 2 epilogue warps per SM sub-partition).
-template <int SIDE, bool MASK>
+template <int SIDE, bool MASK, bool CERT>
 __device__ __forceinline__ void pair_argmax(const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t side_saddr,
                                             uint32_t col_base, int nv0, int nv1, uint32_t stash_saddr, float& best,
-                                            uint32_t& best_col) {
+                                            uint32_t& best_col, float& second) {
   float s0[32], s1[32];
   chunk_scores<SIDE, MASK>(r0, side_saddr, nv0, s0);
   chunk_scores<SIDE, MASK>(r1, side_saddr + 128, nv1, s1);
   const float mx0 = chunk_max(s0), mx1 = chunk_max(s1);
-  chunk_commit(mx0, s0, col_base, stash_saddr, best, best_col);
-  chunk_commit(mx1, s1, col_base + 32, stash_saddr, best, best_col);
+  chunk_commit<CERT>(mx0, s0, col_base, stash_saddr, best, best_col, second);
+  chunk_commit<CERT>(mx1, s1, col_base + 32, stash_saddr, best, best_col, second);
 }
 
 // first position of `best` inside the stashed winning chunk (lowest index wins ties, like torch.argmin)
@@ -309,13 +306,27 @@ __device__ __forceinline__ uint32_t resolve_index(uint32_t stash_saddr, float be
   return (uint32_t)j;
 }
 
+// largest stashed score other than the one at position j (the runner-up inside the winning chunk)
+__device__ __forceinline__ float stash_runner_up(uint32_t stash_saddr, int j) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = lds128(stash_saddr + q * 512);
+    m = fmaxf(m, 4 * q == j ? -INFINITY : v.x);
+    m = fmaxf(m, 4 * q + 1 == j ? -INFINITY : v.y);
+    m = fmaxf(m, 4 * q + 2 == j ? -INFINITY : v.z);
+    m = fmaxf(m, 4 * q + 3 == j ? -INFINITY : v.w);
+  }
+  return m;
+}
+
 // One warp's 4 x 32 columns of a 128 x 256 accumulator; TMEM loads are double-buffered so that the load of
 // chunk c+1 is in flight while chunk c is reduced.  The accumulator is released to the MMA warp as soon
 // as the last load has landed in registers.
-template <int SIDE, bool MASK>
+template <int SIDE, bool MASK, bool CERT>
 __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr, uint32_t gcol0, int b_rows,
                                             uint64_t* tmem_empty_bar, int lane, uint32_t stash_saddr, float& best,
-                                            uint32_t& best_col) {
+                                            uint32_t& best_col, float& second) {
   uint32_t ra[32], rb[32];
   auto nv = [&](int c) -> int {
     if constexpr (!MASK) return 32;
@@ -329,23 +340,24 @@ __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr,
   tmem_ld_wait(rb);
   tmem_ld32(taddr + 64, rc);
   tmem_ld32(taddr + 96, rd);
-  pair_argmax<SIDE, MASK>(ra, rb, side_saddr, gcol0, nv(0), nv(1), stash_saddr, best, best_col);
+  pair_argmax<SIDE, MASK, CERT>(ra, rb, side_saddr, gcol0, nv(0), nv(1), stash_saddr, best, best_col, second);
   tmem_ld_wait(rc);
   tmem_ld_wait(rd);
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(tmem_empty_bar);  // every load of this warp is in registers: buffer is free
-  pair_argmax<SIDE, MASK>(rc, rd, side_saddr + 256, gcol0 + 64, nv(2), nv(3), stash_saddr, best, best_col);
+  pair_argmax<SIDE, MASK, CERT>(rc, rd, side_saddr + 256, gcol0 + 64, nv(2), nv(3), stash_saddr, best, best_col, second);
 }
 
 // Epilogue role: 8 warps drain every tile; warp%4 selects the TMEM lane quarter (hardware rule) and
 // (warp-2)/4 the 128-column half of the accumulator.
-template <int SIDE>
+template <int SIDE, bool CERT>
 __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_base, uint8_t* stash_smem,
                                               uint8_t* share_smem, float* side_smem, uint64_t* tmem_full, uint64_t* tmem_empty, int t0,
                                               int t1, int b_tiles, int a_rows, int b_rows,
                                               const float* __restrict__ b_half_sqnorm, uint32_t b_index_offset,
-                                              unsigned long long* __restrict__ keys) {
+                                              unsigned long long* __restrict__ keys,
+                                              unsigned long long* __restrict__ second_keys) {
   const int ew = warp - 2;
   const int quarter = warp & 3;                // TMEM lanes [32*quarter, 32*quarter+32): the only ones this warp may read
   const uint32_t col0 = (uint32_t)(ew >> 2) * 128;
@@ -355,7 +367,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
   const uint32_t stash_saddr = smem_u32(stash_smem) + (uint32_t)ew * 4096 + (uint32_t)lane * 16;
   const int row_in_tile = quarter * 32 + lane;
   const bool last_partial = b_tiles * BN > b_rows;
-  float best = -INFINITY;
+  float best = -INFINITY, second = -INFINITY;
   uint32_t best_col = 0xffffffffu;
   int at = t0 / b_tiles, bt = t0 - at * b_tiles;
   uint32_t par0 = 0, par1 = 0;                 // per-accumulator phase parity
@@ -384,7 +396,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
         if (t + 1 < t1) side_val = __ldg(b_half_sqnorm + (bt + 1 == b_tiles ? 0 : bt + 1) * BN + gtid);
         named_bar_sync(1, 256);
       }
-      {
+      if constexpr (!CERT) {   // (the certified mode needs every half's own candidates: no exchange)
         uint32_t pb_, pat, pbt, pad;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pb_), "=r"(pat), "=r"(pbt), "=r"(pad) : "r"(partner_share));
         const float pbest = __uint_as_float(pb_);
@@ -400,22 +412,35 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
       const uint32_t side_saddr = side_base + buf * (BN * 4);
       const uint32_t gcol0 = (uint32_t)(bt * BN) + col0;
       if (last_partial && bt == b_tiles - 1)
-        tile_argmax<SIDE, true>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+        tile_argmax<SIDE, true, CERT>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col, second);
       else
-        tile_argmax<SIDE, false>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col);
+        tile_argmax<SIDE, false, CERT>(taddr, side_saddr, gcol0, b_rows, tmem_empty + buf, lane, stash_saddr, best, best_col, second);
       if (warp == 2 && lane == 0) TS(2, t - t0, 1);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_share), "r"(__float_as_uint(best)), "r"((uint32_t)at),
-                   "r"((uint32_t)bt), "r"(0u)
-                   : "memory");
+      if constexpr (!CERT)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_share), "r"(__float_as_uint(best)), "r"((uint32_t)at),
+                     "r"((uint32_t)bt), "r"(0u)
+                     : "memory");
       if (buf) par1 ^= 1; else par0 ^= 1;
     }
     if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish
       const int row = at * BM + row_in_tile;
       if (row < a_rows && best_col != 0xffffffffu) {
-        const uint32_t idx = best_col + resolve_index(stash_saddr, best);
-        atomicMin(keys + row, make_key(best, idx + b_index_offset));
+        const uint32_t j = resolve_index(stash_saddr, best);
+        const unsigned long long kb = make_key(best, best_col + j + b_index_offset);
+        if constexpr (CERT) {
+          // runner-up = max(loser of every chunk comparison, second largest of the winning chunk); whoever loses the
+          // race for keys[row] (this candidate or the previous holder) is a runner-up candidate as well
+          second = fmaxf(second, stash_runner_up(stash_saddr, (int)j));
+          const unsigned long long old = atomicMin(keys + row, kb);
+          const unsigned long long loser = old > kb ? old : kb;
+          const unsigned long long ks = make_key(second, 0xffffffffu);
+          atomicMin(second_keys + row, ks < loser ? ks : loser);
+        } else {
+          atomicMin(keys + row, kb);
+        }
       }
       best = -INFINITY;
+      second = -INFINITY;
       best_col = 0xffffffffu;
       bt = 0;
       ++at;
@@ -436,7 +461,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ TermTable terms, uint32_t idesc, int pa, int pb, int kblocks, int nstages,
                  int64_t a_rows,
                  int64_t a_rows_pad, int64_t b_rows, int64_t b_rows_pad, const float* __restrict__ b_half_sqnorm,
-                 int side_mode, int64_t b_index_offset, unsigned long long* __restrict__ keys, int a_convert) {
+                 int side_mode, int64_t b_index_offset, unsigned long long* __restrict__ keys, int a_convert,
+                 unsigned long long* __restrict__ second_keys, const int* __restrict__ a_rows_dev) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
   // WHOLE: a stage holds every B plane of one code tile; the row tile's A planes are RESIDENT in one of two
@@ -462,9 +488,6 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   pdl_launch_dependents();
   if (threadIdx.x == 0) TS(0, 63, 3);   // kernel start (timeline builds only)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int64_t a_tiles = (a_rows + BM - 1) / BM, b_tiles = (b_rows + BN - 1) / BN;
-  const int64_t total = a_tiles * b_tiles;
-  const int64_t t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -491,6 +514,15 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();
+  // The row count may live on the device (the exact re-run of the rows a one-term pass could not certify: their number
+  // is only known to the preceding kernel); the TMA descriptor then covers the buffer's capacity.
+  if (a_rows_dev != nullptr) {
+    const int64_t n = *a_rows_dev;
+    a_rows = n < a_rows ? n : a_rows;
+  }
+  const int64_t a_tiles = (a_rows + BM - 1) / BM, b_tiles = (b_rows + BN - 1) / BN;
+  const int64_t total = a_tiles * b_tiles;
+  const int64_t t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer (warp-converged, one elected lane issues) =====================
@@ -630,12 +662,19 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue: fused arg-max =====================
-#define VQB_EPI(SIDE_)                                                                                              \
-  epilogue_loop<SIDE_>(warp, lane, tmem_base, stash_smem, share_smem, side_smem, tmem_full, tmem_empty, (int)t0, (int)t1,       \
-                       (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys)
-    if (b_half_sqnorm == nullptr || side_mode == 0) VQB_EPI(0);
-    else if (side_mode == 1) VQB_EPI(1);
-    else VQB_EPI(2);
+#define VQB_EPI(SIDE_, CERT_)                                                                                       \
+  epilogue_loop<SIDE_, CERT_>(warp, lane, tmem_base, stash_smem, share_smem, side_smem, tmem_full, tmem_empty, (int)t0,        \
+                              (int)t1, (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys, \
+                              second_keys)
+    if (second_keys != nullptr) {   // certified one-term mode (cosine family: no side term, or the column scale)
+      if (b_half_sqnorm == nullptr || side_mode == 0) VQB_EPI(0, true);
+      else if (side_mode == 1) VQB_EPI(1, true);
+      else VQB_EPI(2, true);
+    } else {
+      if (b_half_sqnorm == nullptr || side_mode == 0) VQB_EPI(0, false);
+      else if (side_mode == 1) VQB_EPI(1, false);
+      else VQB_EPI(2, false);
+    }
 #undef VQB_EPI
   }
 
@@ -722,7 +761,7 @@ static TermTable make_terms(int pa, int pb) {
 template <int BK, bool WHOLE>
 static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, const void* b_planes, int pb,
                   int64_t b_rows, int64_t b_pad, int Dp, const float* h, int side_mode, int64_t off,
-                  unsigned long long* keys, cudaStream_t st) {
+                  unsigned long long* keys, unsigned long long* second_keys, const int* a_rows_dev, cudaStream_t st) {
   // one bf16 plane (e.g. zero-copy tokens) against fp16 planes: the kernel converts the resident A tile in
   // shared memory (whole-tile mode only)
   const int a_convert = (pa == 1 && is_f16(pb)) ? 1 : 0;
@@ -759,20 +798,21 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
   int grid = sm_count();
   if (total < grid) grid = (int)total;
   VQB_CUDA_OK(launch_pdl(assign_tc_kernel<BK, WHOLE>, grid, kThreads, smem_bytes, st, ma, mb, terms, idesc, pa, pb, Dp / BK,
-                         nstages, a_rows, a_pad, b_rows, b_pad, h, side_mode, off, keys, a_convert));
+                         nstages, a_rows, a_pad, b_rows, b_pad, h, side_mode, off, keys, a_convert, second_keys, a_rows_dev));
   VQB_LAUNCH_OK();
   return VQB_OK;
 }
 
 int assign_tc_launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, const void* b_planes, int pb,
                      int64_t b_rows, int64_t b_pad, int D, const float* h, int side_mode, int64_t off,
-                     unsigned long long* keys, cudaStream_t st) {
+                     unsigned long long* keys, unsigned long long* second_keys, const int* a_rows_dev, cudaStream_t st) {
   const int Dp = (int)vqb_operand_dp(D);
   // resident-A mode: two A slots plus at least two whole-B-tile stages must fit in shared memory
   const bool whole =
       Dp <= 64 && (size_t)(2 * plane_count(pa) * BM + 2 * plane_count(pb) * BN) * Dp * 2 <= 196608 - kStashBytes;
 #define VQB_LAUNCH(BK_, W_) \
-  return launch<BK_, W_>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, side_mode, off, keys, st)
+  return launch<BK_, W_>(a_planes, pa, a_rows, a_pad, b_planes, pb, b_rows, b_pad, Dp, h, side_mode, off, keys, second_keys, \
+                         a_rows_dev, st)
   if (Dp == 16) { if (whole) VQB_LAUNCH(16, true); VQB_LAUNCH(16, false); }
   if (Dp == 32) { if (whole) VQB_LAUNCH(32, true); VQB_LAUNCH(32, false); }
   if (whole) VQB_LAUNCH(64, true);

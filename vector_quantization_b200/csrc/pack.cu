@@ -26,7 +26,8 @@ template <typename T, int G>
 __global__ void __launch_bounds__(256) pack_rows_kernel(
     const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
     __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
-    unsigned long long* __restrict__ keys, int64_t n_keys, uint4* __restrict__ zero_fill, int64_t n_zero16) {
+    unsigned long long* __restrict__ keys, int64_t n_keys, uint4* __restrict__ zero_fill, int64_t n_zero16,
+    float* __restrict__ lo_norm_max) {
   pdl_wait();               // PDL: the source rows / key buffer may still be in use by the preceding launch
   pdl_launch_dependents();
   // fused memset of the assignment keys
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
     ss = group_sum<G>(ss);
     const float denom = normalize ? fmaxf(sqrtf(ss), kNormEps) : 1.f;
     const float f16_scale = planes == VQB_PLANES_F16 ? f16_row_scale(group_max<G>(amax)) : 1.f;
-    float ss2 = 0.f;
+    float ss2 = 0.f, lo2 = 0.f;
     for (int d = lane; d < Dp; d += G) {
       float v = 0.f;
       if (real && d < D) {
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
       } else if (is_f16x2(planes)) {
         // fp16 pair: hi = fp16(v), lo' = fp16((v - hi) * 2^11); the subtraction is exact
         const __half hi = __float2half_rn(v);
+        lo2 = fmaf(v - __half2float(hi), v - __half2float(hi), lo2);
         const __half lo = __float2half_rn((v - __half2float(hi)) * (float)(1 << kPairShift));
         dst[r * Dp + d] = __ushort_as_bfloat16(__half_as_ushort(hi));
         dst[(rows_pad + r) * Dp + d] = __ushort_as_bfloat16(__half_as_ushort(lo));
@@ -86,6 +88,10 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
       ss2 = group_sum<G>(ss2);
       if (lane == 0) half_sqnorm[r] = real ? 0.5f * ss2 : INFINITY;
     }
+    if (lo_norm_max) {   // max_j |row_j - hi_j|_2: the error bound of a one-term (hi plane only) contraction
+      lo2 = group_sum<G>(lo2);
+      if (lane == 0 && real) atomicMax(reinterpret_cast<int*>(lo_norm_max), __float_as_int(sqrtf(lo2)));
+    }
   }
 }
 
@@ -95,7 +101,8 @@ template <typename T, int G, int NV>
 __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
     const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
     __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
-    unsigned long long* __restrict__ keys, int64_t n_keys, uint4* __restrict__ zero_fill, int64_t n_zero16) {
+    unsigned long long* __restrict__ keys, int64_t n_keys, uint4* __restrict__ zero_fill, int64_t n_zero16,
+    float* __restrict__ lo_norm_max) {
   pdl_wait();               // the source rows / the key buffer may still be in use by the preceding launch
   pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_keys; i += (int64_t)gridDim.x * blockDim.x)
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
         for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[it][i]));
       f16_scale = f16_row_scale(group_max<G>(amax));
     }
-    float ss2 = 0.f;
+    float ss2 = 0.f, lo2 = 0.f;
 #pragma unroll
     for (int it = 0; it < NV; ++it) {
       const int d0 = (it * G + lane) * 8;
@@ -181,6 +188,8 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
           for (int i = 0; i < 4; ++i) {
             hh[i] = __floats2half2_rn(rem[2 * i], rem[2 * i + 1]);
             const float2 back = __half22float2(hh[i]);
+            lo2 = fmaf(rem[2 * i] - back.x, rem[2 * i] - back.x, lo2);
+            lo2 = fmaf(rem[2 * i + 1] - back.y, rem[2 * i + 1] - back.y, lo2);
             hl[i] = __floats2half2_rn((rem[2 * i] - back.x) * kUp, (rem[2 * i + 1] - back.y) * kUp);
           }
           *reinterpret_cast<uint4*>(dst + r * Dp + d0) = raw_hi;
@@ -207,6 +216,10 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
     if (half_sqnorm) {
       ss2 = group_sum<G>(ss2);
       if (lane == 0) half_sqnorm[r] = real ? 0.5f * ss2 : INFINITY;
+    }
+    if (lo_norm_max) {
+      lo2 = group_sum<G>(lo2);
+      if (lane == 0 && real) atomicMax(reinterpret_cast<int*>(lo_norm_max), __float_as_int(sqrtf(lo2)));
     }
   }
 }
@@ -338,7 +351,7 @@ size_t vqb_operand_bytes(int64_t rows, int D, int planes) {
 
 int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes,
                   void* dst_planes, float* half_sqnorm, float* writeback, unsigned long long* keys,
-                  int64_t n_keys, void* zero_fill, int64_t zero_bytes, void* stream) {
+                  int64_t n_keys, void* zero_fill, int64_t zero_bytes, float* lo_norm_max, void* stream) {
   VQB_REQUIRE(src && dst_planes, "vqb_pack_rows: null pointer");
   VQB_REQUIRE(zero_fill == nullptr || ((uintptr_t)zero_fill % 16 == 0 && zero_bytes % 16 == 0 && zero_bytes >= 0),
               "vqb_pack_rows: zero_fill must be 16-byte aligned and a multiple of 16 bytes");
@@ -368,11 +381,11 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
     if (gv == G_ && nv == NV_) {                                                                                     \
       if (src_dtype == VQB_F32)                                                                                      \
         launch_pdl(pack_rows_vec_kernel<float, G_, NV_>, blocks, 256, 0, st, (const float*)src, rows, rows_pad, D, Dp, \
-            normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz);        \
+            normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz, lo_norm_max);        \
       else                                                                                                           \
         launch_pdl(pack_rows_vec_kernel<__nv_bfloat16, G_, NV_>, blocks, 256, 0, st, (const __nv_bfloat16*)src, rows, \
             rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys,            \
-            keys ? n_keys : 0, zf, nz);                                                                                      \
+            keys ? n_keys : 0, zf, nz, lo_norm_max);                                                                                      \
       VQB_LAUNCH_OK();                                                                                               \
       return VQB_OK;                                                                                                 \
     }
@@ -385,11 +398,11 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
     if (src_dtype == VQB_F32)
       launch_pdl(pack_rows_kernel<float, G>, blocks, 256, 0, st, (const float*)src, rows, rows_pad, D, Dp, normalize,
                                                           planes, (__nv_bfloat16*)dst_planes, half_sqnorm,
-                                                          writeback, keys, keys ? n_keys : 0, zf, nz);
+                                                          writeback, keys, keys ? n_keys : 0, zf, nz, lo_norm_max);
     else
       launch_pdl(pack_rows_kernel<__nv_bfloat16, G>, blocks, 256, 0, st, 
           (const __nv_bfloat16*)src, rows, rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes,
-          half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz);
+          half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz, lo_norm_max);
   }));
   VQB_LAUNCH_OK();
   return VQB_OK;

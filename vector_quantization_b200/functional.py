@@ -22,6 +22,41 @@ from . import ops
 PRECISION_PLANES = {'fp32': 3, 'exact': 3, 'high': 2, 'fast': 1}
 DEFAULT_PRECISION = 'fp32'
 
+# Certified one-term pass.  From this padded depth on the assignment is bound by the tensor pipe, and
+# the two MMA terms of an fp16-pair codebook are run as ONE term (hi plane) + a proof: rows whose best/runner-up margin
+# exceeds twice the operand error bound keep their arg-max, the others are re-run with both terms.  Results are
+# identical to the two-term contraction by construction.  VQB_CERTIFIED=0 disables it.
+import os as _os
+CERTIFIED_MIN_DP = 128 if _os.environ.get('VQB_CERTIFIED', '1') != '0' else 1 << 30
+
+
+LAST_CERTIFY = {}   # debugging / tests / bench: the device-side count tensor of the most recent certified pass
+
+
+def certified_assign(a: ops.Operand, b: ops.Operand, keys: torch.Tensor, *, scale_columns: bool = False,
+                     index_offset: int = 0, a_inv_norm: torch.Tensor | None = None) -> torch.Tensor:
+    """arg-max of <a_i, b_j> (times the column scale) with ONE MMA term where the fp16 pair would need two.
+    Exactly one of (a, b) is an 'f16x2' pair carrying `lo_norm_max`; the other is a one-plane 'f16' operand.
+      pair on the b side (row arg-min: tokens x codebook): scores are <x_i, hi_j>, the bound scales with |x_i|
+        (`a_inv_norm` = 1/|x_i|);
+      pair on the a side (column arg-min: codebook x tokens with the 1/|x_n| column scale): the bound is delta itself.
+    keys must be reset (all-ones).  Same result as ops.assign(a, b, keys, l2=False, ...)."""
+    pair_is_b = b.fmt == 'f16x2'
+    pair = b if pair_is_b else a
+    assert pair.fmt == 'f16x2' and pair.lo_norm_max is not None and (a if pair_is_b else b).fmt == 'f16'
+    hi = ops.Operand(pair.planes, pair.rows, pair.dim, 1, None, plane_rows=pair.plane_rows, inv_norm=pair.inv_norm, fmt='f16')
+    second = ops.new_keys(a.rows, keys.device)
+    if pair_is_b:
+        ops.assign(a, hi, keys, l2=False, index_offset=index_offset, scale_columns=scale_columns, second_keys=second)
+    else:
+        ops.assign(hi, b, keys, l2=False, index_offset=index_offset, scale_columns=scale_columns, second_keys=second)
+    row_list, count, compact = ops.certify(keys, second, a.rows, pair.lo_norm_max,
+                                           row_inv_norm=a_inv_norm if pair_is_b else None)
+    LAST_CERTIFY.update(count=count, rows=a.rows)
+    redo = ops.gather_operand_rows(a, row_list, count)            # the uncertified rows as a compact operand
+    ops.assign(redo, b, compact, l2=False, index_offset=index_offset, scale_columns=scale_columns, a_rows_dev=count)
+    return ops.scatter_keys(compact, row_list, count, keys)
+
 
 class _L2Normalize(torch.autograd.Function):
 
@@ -66,7 +101,8 @@ def pack_codebook(W: torch.Tensor, metric: str, *, precision: str = DEFAULT_PREC
     pair = cos and _pair_ok(W, normalize, precision, tokens)
     return ops.pack_rows(W, normalize=normalize, planes=None if pair else _planes_for(W, normalize, precision),
                          want_half_sqnorm=not cos, writeback=W if writeback_normalized else None,
-                         reset_keys=reset_keys, fmt='f16x2' if pair else 'bf16', zero_fill=zero_fill)
+                         reset_keys=reset_keys, fmt='f16x2' if pair else 'bf16', zero_fill=zero_fill,
+                         want_lo_norm=pair and ops.operand_shape(1, W.shape[1])[1] >= CERTIFIED_MIN_DP)
 
 
 @torch.no_grad()
@@ -103,6 +139,11 @@ def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precisi
                 keys_are_reset = True
     if not keys_are_reset:
         keys.fill_(-1)
+    if codebook.lo_norm_max is not None and tokens.fmt == 'f16':
+        # D >= 128, fp16-pair codebook: one MMA term + certificate instead of two terms
+        inv = tokens.inv_norm if tokens.inv_norm is not None else ops.row_inv_norm(x, f16_rows=True)
+        tokens.inv_norm = inv
+        return certified_assign(tokens, codebook, keys, index_offset=index_offset, a_inv_norm=inv)
     return ops.assign(tokens, codebook, keys, l2=not cos, index_offset=index_offset)
 
 
@@ -119,7 +160,10 @@ def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, preci
         if x.dtype == torch.bfloat16:
             # raw bf16 tokens as ONE fp16 plane + the per-column 1/|x_n| scale in the epilogue: two MMA terms
             raw = tokens if (tokens is not None and tokens.fmt == 'f16') else ops.pack_rows(x, fmt='f16')
-            raw.inv_norm = ops.row_inv_norm(x, f16_rows=True)
+            if raw.inv_norm is None:
+                raw.inv_norm = ops.row_inv_norm(x, f16_rows=True)
+            if codebook.lo_norm_max is not None:
+                return certified_assign(codebook, raw, keys, scale_columns=True, index_offset=index_offset)
             return ops.assign(codebook, raw, keys, l2=False, scale_columns=True, index_offset=index_offset)
         toks = ops.pack_rows(x, normalize=True, fmt='f16x2')      # normalised tokens as a pair: three terms
         return ops.assign(codebook, toks, keys, l2=False, index_offset=index_offset)

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, PLANES_F16, PLANES_F16X2, VQB_BF16, VQB_F32, FSQParams, check
 
 __all__ = [
-    'Operand', 'as_operand', 'pack_rows', 'assign', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
+    'Operand', 'as_operand', 'pack_rows', 'assign', 'certify', 'gather_operand_rows', 'scatter_keys', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
     'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
     'fsq_decode', 'transpose_last2', 'compact_tokens', 'distance_matrix', 'comm_kmeans_ema_update', 'comm_cvq_update',
@@ -93,6 +93,7 @@ class Operand:
     half_sqnorm: torch.Tensor | None = None
     plane_rows: int = 0  # row stride between planes; 0 = padded default, rows = zero-copy view of a bf16 tensor
     inv_norm: torch.Tensor | None = None  # fp32 [rows_pad] 1/|row| (per-column scale for raw-token column arg-min)
+    lo_norm_max: torch.Tensor | None = None  # fp32 [1]: max_j |row_j - hi_j| of an 'f16x2' operand (one-term error bound)
     fmt: str = 'bf16'    # 'bf16': 1..3 bf16 planes | 'f16': one fp16 plane | 'f16x2': the fp16 (hi, lo * 2^11) pair
 
     @property
@@ -112,7 +113,7 @@ def operand_shape(rows: int, D: int) -> tuple[int, int]:
 def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None = None,
               want_half_sqnorm: bool = False, writeback: torch.Tensor | None = None,
               reset_keys: torch.Tensor | None = None, fmt: str = 'bf16',
-              zero_fill: torch.Tensor | None = None) -> Operand:
+              zero_fill: torch.Tensor | None = None, want_lo_norm: bool = False) -> Operand:
     """fp32/bf16 rows -> operand planes (see vqb_pack_rows).
     fmt='bf16': exact bf16 planes; `planes=None` picks the exact representation (1 plane for un-normalised bf16
                 input, 3 planes otherwise).
@@ -145,9 +146,11 @@ def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None 
     h = torch.empty((rows_pad,), dtype=torch.float32, device=src.device) if want_half_sqnorm else None
     if writeback is not None:
         assert writeback.dtype == torch.float32 and writeback.shape == src.shape
+    lo = torch.zeros((1,), dtype=torch.float32, device=src.device) if (want_lo_norm and fmt == 'f16x2') else None
     _call('vqb_pack_rows', lib.vqb_pack_rows, dev, _p(src), _dt(src), rows, D, int(normalize), code, _p(dst), _p(h),
-          _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _p(zero_fill), zero_bytes, _S)
-    return Operand(dst, rows, D, planes, h, fmt=fmt)
+          _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _p(zero_fill), zero_bytes,
+          _p(lo), _S)
+    return Operand(dst, rows, D, planes, h, fmt=fmt, lo_norm_max=lo)
 
 
 def transpose_last2(src: torch.Tensor) -> torch.Tensor:
@@ -179,11 +182,16 @@ def new_keys(n: int, device) -> torch.Tensor:
 
 
 def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset: int = 0,
-           backend: int = BACKEND_TCGEN05, scale_columns: bool = False) -> torch.Tensor:
+           backend: int = BACKEND_TCGEN05, scale_columns: bool = False, second_keys: torch.Tensor | None = None,
+           a_rows_dev: torch.Tensor | None = None) -> torch.Tensor:
     """keys[i] = min(keys[i], key(argmax_j score)), score = <a_i,b_j> - 0.5|b_j|^2 (l2), <a_i,b_j> * (1/|b_j|)
-    (scale_columns: b holds RAW rows + `inv_norm`), or <a_i,b_j>."""
+    (scale_columns: b holds RAW rows + `inv_norm`), or <a_i,b_j>.
+    second_keys: also record the runner-up score of every row (certified one-term pass); a_rows_dev: int32 [1] device
+    tensor bounding the number of valid A rows (vqb_assign_ex)."""
     lib = _lib.load()
-    dev = _cuda(a.planes, b.planes, keys)
+    dev = _cuda(a.planes, b.planes, keys, second_keys, a_rows_dev)
+    assert a_rows_dev is None or a_rows_dev.dtype == torch.int32
+    assert second_keys is None or (second_keys.dtype == torch.int64 and second_keys.numel() >= a.rows)
     assert a.dim == b.dim and keys.dtype == torch.int64 and keys.numel() >= a.rows
     side, mode = None, 0
     if l2:
@@ -192,8 +200,49 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
     elif scale_columns:
         assert b.inv_norm is not None
         side, mode = b.inv_norm, 2
-    _call('vqb_assign', lib.vqb_assign, dev, _p(a.planes), a.abi_planes, a.rows, a.plane_rows, _p(b.planes), b.abi_planes, b.rows,
-          b.plane_rows, a.dim, _p(side), mode, index_offset, _p(keys), backend, _S)
+    if second_keys is None and a_rows_dev is None:
+        _call('vqb_assign', lib.vqb_assign, dev, _p(a.planes), a.abi_planes, a.rows, a.plane_rows, _p(b.planes),
+              b.abi_planes, b.rows, b.plane_rows, a.dim, _p(side), mode, index_offset, _p(keys), backend, _S)
+    else:
+        _call('vqb_assign', lib.vqb_assign_ex, dev, _p(a.planes), a.abi_planes, a.rows, a.plane_rows, _p(b.planes),
+              b.abi_planes, b.rows, b.plane_rows, a.dim, _p(side), mode, index_offset, _p(keys), _p(second_keys),
+              _p(a_rows_dev), backend, _S)
+    return keys
+
+
+def certify(keys: torch.Tensor, second_keys: torch.Tensor, rows: int, delta: torch.Tensor, *,
+            row_inv_norm: torch.Tensor | None = None, noise: float = 2.0 ** -20):
+    """Rows whose best - runner-up margin does not exceed twice the one-term error bound -> (row_list int32 [rows],
+    count int32 [1], compact_keys int64 [rows] with the first `count` entries reset)."""
+    lib = _lib.load()
+    dev = _cuda(keys, second_keys, delta, row_inv_norm)
+    row_list = torch.empty((rows,), dtype=torch.int32, device=keys.device)
+    count = torch.empty((1,), dtype=torch.int32, device=keys.device)
+    compact = torch.empty((rows,), dtype=torch.int64, device=keys.device)
+    ws = torch.empty((int(lib.vqb_certify_workspace_bytes(rows)),), dtype=torch.uint8, device=keys.device)
+    _call('vqb_certify', lib.vqb_certify, dev, _p(keys), _p(second_keys), rows, _p(row_inv_norm), _p(delta), noise,
+          _p(row_list), _p(count), _p(compact), _p(ws), _S)
+    return row_list, count, compact
+
+
+def gather_operand_rows(src: Operand, row_list: torch.Tensor, count: torch.Tensor) -> Operand:
+    """Compact copy of the listed rows of a packed operand (all planes, side vectors included); capacity = src.rows."""
+    lib = _lib.load()
+    dev = _cuda(src.planes, row_list, count)
+    P, Dp = src.planes.shape[0] if src.planes.dim() == 3 else 1, src.planes.shape[-1]
+    src_plane_rows = src.plane_rows or (src.planes.shape[1] if src.planes.dim() == 3 else src.rows)
+    rows_pad = operand_shape(src.rows, src.dim)[0]
+    dst = torch.empty((src.nplanes, rows_pad, Dp), dtype=torch.bfloat16, device=src.planes.device)
+    _call('vqb_gather_plane_rows', lib.vqb_gather_plane_rows, dev, _p(src.planes), src.nplanes, src_plane_rows, Dp,
+          _p(row_list), _p(count), src.rows, _p(dst), rows_pad, _S)
+    out = Operand(dst, src.rows, src.dim, src.nplanes, None, fmt=src.fmt)
+    return out
+
+
+def scatter_keys(compact: torch.Tensor, row_list: torch.Tensor, count: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    dev = _cuda(compact, row_list, count, keys)
+    _call('vqb_scatter_keys', lib.vqb_scatter_keys, dev, _p(compact), _p(row_list), _p(count), row_list.numel(), _p(keys), _S)
     return keys
 
 
