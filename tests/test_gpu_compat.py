@@ -133,7 +133,9 @@ def test_cvqvae_training_step_with_multinomial_anchor(dev):
     """A CVQ-VAE step with MultinomialAnchor: every updated code row is the blend of its old row and ONE token row,
     with the oracle's per-code decay."""
     N, K, D = 256, 32, 8
-    x, E = O.synthetic_latents(N, K, D, seed=6)
+    _, E = O.synthetic_latents(N, K, D, seed=6)
+    g = torch.Generator().manual_seed(6)
+    x = E[torch.randint(0, 8, (N,), generator=g)] + 0.05 * torch.randn(N, D, generator=g)   # only 8 of the 32 codes are used
     cfg = dict(type='VQGANQuantizer', distance=dict(type='L2Distance'),
                callbacks=[dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='MultinomialAnchor'))],
                losses=dict(l=dict(type='VQGANLoss')), init_weights=dict(type='vqgan'))
