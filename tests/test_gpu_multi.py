@@ -95,6 +95,22 @@ def _sharded(rank, world):
     return quant.cpu(), z.cpu()
 
 
+def _sharded_certified(rank, world):
+    """cfg-5-like: cosine, bf16 tokens, D = 256 -> the globally certified one-term pass."""
+    from oracle import oracle as O
+    from vector_quantization_b200 import functional as Fq
+    from vector_quantization_b200 import parallel
+    dev = torch.device('cuda', rank)
+    N, K, D = 3000, 2048, 256
+    x, E = O.synthetic_latents(N, K, D, seed=13, normalized_codebook=True, clustered=False)
+    lo, hi = parallel.shard_range(K, rank, world)
+    xb = x.to(torch.bfloat16).to(dev)
+    quant, keys = parallel.sharded_nearest_code(xb, E[lo:hi].to(dev), 'Cosine', shard_lo=lo)
+    flagged = int(Fq.LAST_CERTIFY['count'])
+    quant2, _ = parallel.sharded_nearest_code(xb, E[lo:hi].to(dev), 'Cosine', shard_lo=lo, precision='exact')
+    return quant.cpu(), quant2.cpu(), flagged
+
+
 def _lazy_init(rank, world):
     """Distributed k-means init: every rank keeps ITS tokens; the result must equal the reference's rank-0 k-means
     over the concatenated tokens (oracle); rank 0 seeds `random` like the oracle run."""
@@ -124,6 +140,7 @@ CASES = {
     'cvq': lambda r, w: _quantizer_step(CVQ, 384, 96, 32, False, r, w),
     'cluster': lambda r, w: _quantizer_step(CLUSTER, 256, 64, 64, False, r, w),
     'sharded': _sharded,
+    'sharded_certified': _sharded_certified,
     'lazy_init': _lazy_init,
 }
 
@@ -187,4 +204,21 @@ def test_codebook_sharded_assignment_and_decode(comm):
         rows, gap = O.index_mismatch_report(d, q_ref, quant)
         assert (gap < 1e-5 * d[rows, q_ref[rows]].clamp_min(1)).all() and rows.numel() <= 3
         assert torch.equal(z, E[quant])
+    assert torch.equal(res[0][0], res[1][0])
+
+
+@pytest.mark.parametrize('comm', ['p2p', 'nccl'])
+def test_codebook_sharded_assignment_globally_certified_one_term(comm):
+    """Cosine, D = 256, bf16 tokens, codebook split over two ranks: the one-term pass certified against the GLOBAL
+    runner-up equals the exact three-plane contraction index for index (and the oracle under the near-tie policy);
+    on random data some rows fail the certificate and are re-run on every shard."""
+    from oracle import oracle as O
+    res = _spawn('sharded_certified', comm=comm)
+    x, E = O.synthetic_latents(3000, 2048, 256, seed=13, normalized_codebook=True, clustered=False)
+    q_ref, d = O.encode('Cosine', x.to(torch.bfloat16).float(), E)
+    for quant, quant_exact, flagged in res:
+        assert 0 < flagged < 1500
+        rows, gap = O.index_mismatch_report(d, q_ref, quant)
+        assert (gap < 1e-5).all() and rows.numel() <= 6
+        assert (quant != quant_exact).sum() <= 2           # the pair's own 2^-22 operand error at fp32-level near-ties
     assert torch.equal(res[0][0], res[1][0])

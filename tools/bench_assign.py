@@ -33,6 +33,7 @@ cases = [  # name, N, K, D, metric, x dtype, planes_x, planes_e
     ('cfg4 cos D256 1x1', 16384, 8192, 256, 'cos', torch.bfloat16, 1, 1),
     ('cfg1 l2 D256 3x3', 16384, 8192, 256, 'l2', torch.float32, 3, 3),
     ('cfg5/8 cos D768 1x1', 65536, 32768, 768, 'cos', torch.bfloat16, 1, 1),
+    ('cfg5/8 cos D768 1xpair', 65536, 32768, 768, 'cos', torch.bfloat16, 1, 'pair'),
 ]
 out = []
 flt = sys.argv[1] if len(sys.argv) > 1 else ''
@@ -54,6 +55,29 @@ for name, N, K, D, metric, dt, px, pe in cases:
                gelem_per_s=round(N * K / med / 1e6, 1), mtok_per_s=round(N / med / 1e3, 1))
     pk = timeit(lambda: ops.pack_rows(E, normalize=cos, planes=None if pair else pe, want_half_sqnorm=not cos, fmt='f16x2' if pair else 'bf16'), iters=5)[0]
     rec['pack_codebook_ms'] = round(pk, 4)
+    if pair and ops.operand_shape(1, D)[1] >= 128:
+        # certified one-term pass (hi plane + certificate + exact re-run of the uncertified rows), random AND clustered
+        from vector_quantization_b200 import functional as Fq
+        b2 = ops.pack_rows(E, normalize=True, fmt='f16x2', want_lo_norm=True)
+        for tag, xs in (('random', x), ('clustered', (torch.nn.functional.normalize(E)[torch.randint(0, K, (N,), device=dev)]
+                                                      + 0.5 / D ** 0.5 * torch.randn(N, D, device=dev)).to(dt))):
+            a2 = ops.pack_rows(xs, fmt='f16')
+            a2.inv_norm = ops.row_inv_norm(xs, f16_rows=True)
+
+            def cert():
+                keys.fill_(-1)
+                Fq.certified_assign(a2, b2, keys, a_inv_norm=a2.inv_norm)
+
+            def plain():
+                keys.fill_(-1)
+                ops.assign(a2, b2, keys, l2=False)
+            m_c, _ = timeit(cert)
+            frac = float(Fq.LAST_CERTIFY['count']) / N
+            m_p, _ = timeit(plain)
+            rec[f'certified_{tag}_ms'] = round(m_c, 4)
+            rec[f'two_term_{tag}_ms'] = round(m_p, 4)
+            rec[f'uncertified_fraction_{tag}'] = round(frac, 4)
+            rec[f'certified_{tag}_algo_tflops'] = round(flops / m_c / 1e9, 1)
     print(json.dumps(rec), flush=True)
     out.append(rec)
     del x, E, a, b, keys

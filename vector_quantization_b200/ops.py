@@ -211,14 +211,15 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
 
 
 def certify(keys: torch.Tensor, second_keys: torch.Tensor, rows: int, delta: torch.Tensor, *,
-            row_inv_norm: torch.Tensor | None = None, noise: float = 2.0 ** -20):
+            row_inv_norm: torch.Tensor | None = None, noise: float = 2.0 ** -20,
+            compact_out: torch.Tensor | None = None):
     """Rows whose best - runner-up margin does not exceed twice the one-term error bound -> (row_list int32 [rows],
     count int32 [1], compact_keys int64 [rows] with the first `count` entries reset)."""
     lib = _lib.load()
     dev = _cuda(keys, second_keys, delta, row_inv_norm)
     row_list = torch.empty((rows,), dtype=torch.int32, device=keys.device)
     count = torch.empty((1,), dtype=torch.int32, device=keys.device)
-    compact = torch.empty((rows,), dtype=torch.int64, device=keys.device)
+    compact = compact_out if compact_out is not None else torch.empty((rows,), dtype=torch.int64, device=keys.device)
     ws = torch.empty((int(lib.vqb_certify_workspace_bytes(rows)),), dtype=torch.uint8, device=keys.device)
     _call('vqb_certify', lib.vqb_certify, dev, _p(keys), _p(second_keys), rows, _p(row_inv_norm), _p(delta), noise,
           _p(row_list), _p(count), _p(compact), _p(ws), _S)

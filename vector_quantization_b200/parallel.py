@@ -219,9 +219,10 @@ def _keys_region(n: int, device: torch.device) -> 'PeerRegion | None':
     """Peer region holding the [n] packed keys of the codebook-sharded assignment (one per (n, device), reused)."""
     k = (n, device.index)
     if k not in _KEY_REGIONS:
-        region = try_peer_region(n * 8, device)
+        region = try_peer_region(3 * (n * 8 + 512), device)
         if region is not None:
-            region.alloc('keys', (n,), torch.int64)
+            for name in ('keys', 'second', 'compact'):
+                region.alloc(name, (n,), torch.int64)
         _KEY_REGIONS[k] = region
     return _KEY_REGIONS[k]
 
@@ -241,15 +242,45 @@ def sharded_nearest_code(x: torch.Tensor, W_shard: torch.Tensor, metric: str, *,
     n = x.shape[0]
     region = _keys_region(n, x.device)
     keys = region.keys if region is not None else torch.empty((n,), dtype=torch.int64, device=x.device)
+
+    def reduce_min(name: str, t: torch.Tensor) -> torch.Tensor:
+        # the buffers live in the peer region: one launch reduces them over NVLink (two-shot min-loc) into every rank's copy
+        if region is not None:
+            ops.comm_allreduce_min_keys(region, n, name)
+            return t
+        return all_reduce_min_keys_(t)
+
     book = Fq.pack_codebook(W_shard, metric, precision=precision, reset_keys=keys, tokens=x)
-    Fq.nearest_code(x, book, metric, precision=precision, keys=keys, keys_are_reset=True, index_offset=shard_lo)
-    if region is not None:
-        # per-shard keys live in the peer region: one launch reduces them over NVLink (two-shot min-loc) into every
-        # rank's copy; the result is cloned out so that the next call can reuse the region
-        ops.comm_allreduce_min_keys(region, n)
-        keys = keys.clone()
+    if book.lo_norm_max is None:
+        Fq.nearest_code(x, book, metric, precision=precision, keys=keys, keys_are_reset=True, index_offset=shard_lo)
+        keys = reduce_min('keys', keys)
     else:
-        all_reduce_min_keys_(keys)
+        # Certified one-term pass (Fq.certified_assign), certified GLOBALLY: a shard-local certificate would not protect
+        # the comparison of the one-term scores ACROSS shards.  Every shard finds its best and runner-up with the hi
+        # plane; the global best is the min-loc reduce of the bests; the global runner-up is the reduce of "my best if it
+        # lost, my runner-up if it won"; rows whose global margin is within twice the error bound are re-run with both
+        # terms on every shard (the certificate lists them in ascending order on every rank) and reduced again.
+        toks = ops.pack_rows(x, fmt='f16')
+        inv = ops.row_inv_norm(x, f16_rows=True)
+        hi = ops.Operand(book.planes, book.rows, book.dim, 1, None, plane_rows=book.plane_rows, fmt='f16')
+        second = ops.new_keys(n, x.device)
+        ops.assign(toks, hi, keys, l2=False, index_offset=shard_lo, second_keys=second)
+        mine = keys.clone()
+        keys = reduce_min('keys', keys)
+        cand = region.second if region is not None else second
+        torch.where(mine == keys, second, mine, out=cand)
+        cand = reduce_min('second', cand)
+        # the bound must hold for every shard: the analytic worst case of an fp16 hi plane of unit rows, 2^-11
+        delta = torch.full((1,), 2.0 ** -11, dtype=torch.float32, device=x.device)
+        row_list, count, compact = ops.certify(keys, cand, n, delta, row_inv_norm=inv,
+                                               compact_out=region.compact if region is not None else None)
+        Fq.LAST_CERTIFY.update(count=count, rows=n)
+        redo = ops.gather_operand_rows(toks, row_list, count)
+        ops.assign(redo, book, compact, l2=False, index_offset=shard_lo, a_rows_dev=count)
+        compact = reduce_min('compact', compact)
+        ops.scatter_keys(compact, row_list, count, keys)
+    if region is not None:
+        keys = keys.clone()      # the result is cloned out so that the next call can reuse the region
     return ops.unpack_keys(keys), keys
 
 
