@@ -270,8 +270,11 @@ def sharded_nearest_code(x: torch.Tensor, W_shard: torch.Tensor, metric: str, *,
         cand = region.second if region is not None else second
         torch.where(mine == keys, second, mine, out=cand)
         cand = reduce_min('second', cand)
-        # the bound must hold for every shard: the analytic worst case of an fp16 hi plane of unit rows, 2^-11
-        delta = torch.full((1,), 2.0 ** -11, dtype=torch.float32, device=x.device)
+        # the bound must hold for every shard: the largest |e_j - hi_j| over ALL shards (one 4-byte MAX all-reduce; the
+        # analytic worst case 2^-11 would be about twice as loose and double the re-run)
+        delta = book.lo_norm_max
+        if _on():
+            dist.all_reduce(delta, op=dist.ReduceOp.MAX)
         row_list, count, compact = ops.certify(keys, cand, n, delta, row_inv_norm=inv,
                                                compact_out=region.compact if region is not None else None)
         Fq.LAST_CERTIFY.update(count=count, rows=n)
