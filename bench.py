@@ -477,14 +477,14 @@ def main():
     # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/, per launch)
     traffic, ncu_note = None, None
     try:
-        ncu = json.load(open(ROOT / 'profiles' / 'r1_assign_ncu_summary.json'))
+        ncu = json.load(open(ROOT / 'profiles' / 'r2_assign_ncu_summary.json'))
         if args.workload == 'cfg2':
             to_b = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
             traffic = sum(float(ncu[k]['value']) * to_b[ncu[k]['unit']]
                           for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
             ncu_note = dict(tensor_pipe_active_pct=float(
                 ncu['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']['value']),
-                source='profiles/r1_assign_ncu_summary.json')
+                source='profiles/r2_assign_ncu_summary.json (ncu --set full capture of this kernel in this workload; per launch)')
     except Exception:  # noqa: BLE001
         pass
     roofline = dict(bound='tensor', kernel='assign_tc_kernel (tcgen05 distance GEMM + fused arg-min)',
