@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
 #pragma unroll
     for (int it = 0; it < NV; ++it) {
       const int d0 = (it * G + lane) * V;
+      float gw[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const float yv = yr[it][i], wv = wr[it][i];
@@ -296,7 +297,18 @@ __global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
         }
         gr[it][i] = g_y;
         gy_dot_y = fmaf(g_y, yv, gy_dot_y);
-        if (gW && valid && d0 + i < D) atomicAdd(gW + q * D + d0 + i, g_w);
+        gw[i] = g_w;
+      }
+      if (gW && valid && d0 < D) {
+        float* dst = gW + q * D + d0;
+        if constexpr (V == 8) {   // two red.global.add.v4.f32 instead of eight scalar atomics (the slice is 32-byte aligned)
+          atomicAdd(reinterpret_cast<float4*>(dst), make_float4(gw[0], gw[1], gw[2], gw[3]));
+          atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(gw[4], gw[5], gw[6], gw[7]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i)
+            if (d0 + i < D) atomicAdd(dst + i, gw[i]);
+        }
       }
     }
     if (normalize_x) {
