@@ -559,7 +559,10 @@ def main():
 
     # ---- end-to-end: pinned host inputs -> device -> step -> results back to pinned host ----
     xh = x0.pin_memory()
-    gh = gz0.pin_memory()
+    # The upstream gradient crosses PCIe as bf16 (what a bf16-autocast decoder backward produces: autograd only widens
+    # it to z's fp32 afterwards) and is widened on the device, into the step's fp32 gradient buffer.
+    gh = gz0.to(torch.bfloat16).pin_memory()
+    g_stage = [torch.empty(N, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]
     loss_h = torch.empty([], dtype=torch.float32).pin_memory()
     quant_h = torch.empty(N, dtype=torch.int64).pin_memory()
     gx_h = torch.empty(N, D, dtype=torch.bfloat16).pin_memory()
@@ -581,7 +584,8 @@ def main():
         with torch.cuda.stream(s_in), torch.no_grad():
             s_in.wait_event(ev_run[j])            # the previous step that used input set j has consumed it
             xi.copy_(xh, non_blocking=True)
-            gzi.copy_(gh, non_blocking=True)
+            g_stage[i & 1].copy_(gh, non_blocking=True)
+            gzi.copy_(g_stage[i & 1])             # bf16 -> fp32 widening on the device
             ev_in[j].record(s_in)
         cur.wait_event(ev_in[j])
         cur.wait_event(ev_out[j])                 # result buffers of graph j have been read back
@@ -612,7 +616,7 @@ def main():
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t)
-    h2d = xh.numel() * 2 + gh.numel() * 4
+    h2d = xh.numel() * 2 + gh.numel() * 2
     d2h = 4 + quant_h.numel() * 8 + gx_h.numel() * 2
     clocks = sampler.stop()
 
@@ -646,7 +650,9 @@ def main():
             clocks=clocks, roofline=roofline, collective=collective, cpu_baseline=cpu_baseline,
             gpu_eager_baseline=gpu_eager, breakdown_ms=breakdown,
             e2e=dict(value=N * world / (e2e_ms * 1e-3), unit=unit, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
-                     d2h_bytes_per_step=d2h, cpu_affinity=numa),
+                     d2h_bytes_per_step=d2h, cpu_affinity=numa,
+                     note='per step: bf16 tokens + bf16 upstream gradient host->device (widened to fp32 on the device), '
+                          'loss + int64 indices + bf16 token gradient device->host; three streams, PCIe-bound'),
             gpu_launches=launches_per_step * args.steps)))
     if world > 1:
         # graphs that captured NCCL collectives must be gone before the communicator is torn down; a watchdog
