@@ -551,7 +551,7 @@ def main():
                   f'({key}); no NCCL call on the data path') if fused else
                  ('torch.distributed all_reduce (NCCL)' if world > 1 else 'none (single GPU)'),
             ms=(sum(t) / len(t)) if (t and fused) else None,
-            protocol=('low-latency: 8-byte (value, epoch) words, no barrier/fence, 2 one-way NVLink hops'
+            protocol=('low-latency: every fp32 word carries the exchange parity in its mantissa LSB (1x wire bytes), no barrier/fence, 2 one-way NVLink hops'
                       if fused and 'll_in' in cb[0]._region.offsets else
                       ('barrier: flag, peer reads, peer writes + fence, flag' if fused else None)),
             ms_note='one fused exchange+update launch, measured as a burst of 50 back-to-back launches on every rank '

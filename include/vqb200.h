@@ -297,11 +297,12 @@ int vqb_comm_free(void* region);
 int vqb_comm_bind(void* region, const void* const* peer_regions_host /* [world], [rank] == region */, int rank, int world);
 /* stats_off: fp32 [K*D sums | K counts] (per-rank partials of vqb_scatter_stats); w_off: fp32 [K, D] codebook.
  * = all_reduce(SUM) + vqb_kmeans_ema_update in one launch; afterwards every rank's codebook holds the same rows. */
-/* ll_in_off / ll_out_off: (size_t)-1 selects the barrier protocol (bandwidth-efficient, ~6 NVLink hops).  Otherwise the
- * LOW-LATENCY protocol: every fp32 travels as one 8-byte (value, epoch) word, so data is its own flag and the
- * exchange needs no barrier or fence (2 one-way hops).  ll_in_off: uint64 [world][ceil(K/world)][D+1] staging for the
- * partial sums pushed to this rank; ll_out_off: uint64 [K][D] staging for the updated rows pushed to this rank.  Both
- * zero-initialised once, never reset (the epoch only grows). */
+/* ll_in_off / ll_out_off: (size_t)-1 selects the barrier protocol (six NVLink hops).  Otherwise the LOW-LATENCY
+ * protocol: every fp32 word is its own flag (its mantissa LSB carries the parity of the exchange counter), so the
+ * exchange needs no barrier or fence (two one-way hops) at 1x wire bytes; transmitted values lose their LSB (<= 1 ulp)
+ * and every replica stores the same truncated rows.  ll_in_off: uint32 [world][ceil(K/world)][D+1] staging for the
+ * partial sums pushed to this rank; ll_out_off: uint32 [K][D] staging for the updated rows pushed to this rank.  Both
+ * zero-initialised once, never reset. */
 int vqb_comm_kmeans_ema_update(void* region, int rank, int world, size_t stats_off, size_t w_off, size_t ll_in_off,
                                size_t ll_out_off, int64_t K, int D, float decay, float one_minus_decay, void* stream);
 /* counts_off: int64 [K counts | numel] per-rank partials; anchors_off: fp32 [K, D] per-rank nearest-token rows;

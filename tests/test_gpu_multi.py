@@ -26,12 +26,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, out, comm):
+def _worker(rank, world, port, case, out, comm, ack):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), VQB_COMM=comm)
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
         out.put((rank, CASES[case](rank, world)))
+        ack.wait(120)            # stay alive until the parent has read the (shared-memory) tensors
     finally:
         dist.destroy_process_group()
 
@@ -40,10 +41,26 @@ def _spawn(case, world=2, comm='p2p'):
     ctx = mp.get_context('spawn')
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, out, comm)) for r in range(world)]
+    ack = ctx.Event()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, out, comm, ack)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(out.get() for _ in range(world))
+    # never block on the queue: a worker that died (exception, trapped kernel) must fail the test, not hang it
+    import time
+    res, deadline = {}, time.time() + 240
+    while len(res) < world:
+        if not out.empty():
+            r, v = out.get()
+            res[r] = v
+            continue
+        dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+        if dead or time.time() > deadline or all(p.exitcode is not None for p in procs):
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
+            raise AssertionError(f'worker(s) failed or timed out: exit codes {[p.exitcode for p in procs]}')
+        time.sleep(0.05)
+    ack.set()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0

@@ -24,11 +24,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(rank, world, port, fn, out):
+def _run(rank, world, port, fn, out, ack):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         out.put((rank, fn(rank, world)))
+        ack.wait(60)             # stay alive until the parent has read the (shared-memory) tensors
     finally:
         dist.destroy_process_group()
 
@@ -37,12 +38,28 @@ def _spawn(fn, world=2):
     ctx = mp.get_context('spawn')
     out = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_run, args=(r, world, port, fn, out)) for r in range(world)]
+    ack = ctx.Event()
+    procs = [ctx.Process(target=_run, args=(r, world, port, fn, out, ack)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(out.get() for _ in range(world))
+    # never block on the queue: a worker that died (exception, trapped kernel) must fail the test, not hang it
+    import time
+    res, deadline = {}, time.time() + 240
+    while len(res) < world:
+        if not out.empty():
+            r, v = out.get()
+            res[r] = v
+            continue
+        dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+        if dead or time.time() > deadline or all(p.exitcode is not None for p in procs):
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
+            raise AssertionError(f'worker(s) failed or timed out: exit codes {[p.exitcode for p in procs]}')
+        time.sleep(0.05)
+    ack.set()
     for p in procs:
-        p.join(60)
+        p.join(120)
         assert p.exitcode == 0
     return [res[r] for r in range(world)]
 

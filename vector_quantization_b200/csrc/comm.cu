@@ -28,6 +28,7 @@ struct CommCtl {
   uint32_t sig[2][kMaxWorld];  // sig[set][r] is written by rank r: the epoch it has reached on barrier `set`
   uint32_t epoch;              // collectives completed by THIS rank
   uint32_t ticket;             // blocks of the running collective that have finished (self-resetting)
+  uint32_t ll_epoch;           // low-latency exchanges completed by THIS rank (its parity is the in-word flag)
 };
 static_assert(sizeof(CommCtl) <= 256, "control block");
 constexpr size_t kPeerTableOff = 256;
@@ -218,37 +219,42 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_kernel(Comm c, size_t sta
 
 // ---- low-latency variant of the VQ-KD exchange (payloads up to a few MB) --------------------------------------
 // The barrier protocol above costs six NVLink hops (flag, read round trip, write + ack, flag: ~20 us measured).
-// Here every 4-byte value travels as an 8-byte (value, epoch) word in ONE naturally aligned store, so the data is its
-// own flag (the "LL" idea of NCCL): no barriers, no fences, two one-way hops.
+// Here every fp32 word is its OWN flag: its mantissa LSB carries the parity of the exchange epoch.  A staging slot is
+// rewritten at every exchange, so it holds either the word of the previous exchange (other parity) or the current one:
+// one bit distinguishes them, any 4-byte store is atomic, and the wire carries 1x the payload (an (value, epoch)
+// 8-byte word, NCCL's "LL" format, was measured first: 2x the bytes, 20.7 us at 8 GPUs).  The price is the LSB of the
+// transmitted values (truncation by at most one ulp, 6e-8 relative — the statistics are fp32 sums whose own rounding
+// noise is larger; every replica stores the SAME truncated rows, so the codebooks stay bit-identical across ranks).
+// No barriers, no fences, two one-way hops:
 //   phase 1  every rank PUSHES the partial sums/counts of the rows it does not own into the owner's staging area
 //   phase 2  the owner polls its staging area (local memory), reduces in fixed rank order, applies the k-means/EMA
 //            update and pushes the new rows into every peer's row staging (its own codebook is written directly)
 //   phase 3  every rank polls its row staging and writes the rows it does not own into its codebook
-// Staging is single-buffered: a rank cannot start epoch e+1 before every owner has consumed its epoch-e words
+// Staging is single-buffered: a rank cannot start exchange e+1 before every owner has consumed its words of exchange e
 // (phase 3 needs all owners' rows, which they send after consuming).  All blocks of the grid must be co-resident
-// (a block spins on words that remote blocks produce); the host sizes the grid from the occupancy query.
-__device__ __forceinline__ void st_ll(unsigned long long* p, float v, uint32_t e) {
-  const unsigned long long w = ((unsigned long long)e << 32) | __float_as_uint(v);
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+// (a block spins on words that remote blocks produce); the host sizes the grid accordingly.
+__device__ __forceinline__ uint32_t ll_word(float v, uint32_t e) { return (__float_as_uint(v) & ~1u) | (e & 1u); }
+__device__ __forceinline__ void st_ll(uint32_t* p, float v, uint32_t e) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(ll_word(v, e)) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_ll_raw(const unsigned long long* p) {
-  unsigned long long w;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+__device__ __forceinline__ uint32_t ld_ll_raw(const uint32_t* p) {
+  uint32_t w;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
   return w;
 }
 // value of a low-latency word: `w` is what a first (batched) load returned; re-polls only if it had not arrived yet
-__device__ __forceinline__ float ld_ll(const unsigned long long* p, unsigned long long w, uint32_t e, const Comm& c) {
-  if ((uint32_t)(w >> 32) != e) {
+__device__ __forceinline__ float ld_ll(const uint32_t* p, uint32_t w, uint32_t e, const Comm& c) {
+  if (((w ^ e) & 1u) != 0u) {
     const long long t0 = clock64();
     do {
-      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+      w = ld_ll_raw(p);
       if (clock64() - t0 > 4000000000ll) {
-        printf("vqb comm: rank %d timed out polling a low-latency word (epoch %u, found %u)\n", c.rank, e, (uint32_t)(w >> 32));
+        printf("vqb comm: rank %d timed out polling a low-latency word (exchange %u)\n", c.rank, e);
         __trap();
       }
-    } while ((uint32_t)(w >> 32) != e);
+    } while (((w ^ e) & 1u) != 0u);
   }
-  return __uint_as_float((uint32_t)w);
+  return __uint_as_float(w & ~1u);
 }
 
 template <int G, int NPL>
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
   pdl_wait();
   pdl_launch_dependents();
   CommCtl* ctl = c.ctl();
-  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(&ctl->epoch) + 1;
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(&ctl->ll_epoch) + 1;
   if (threadIdx.x < c.world) peer_table()[threadIdx.x] = reinterpret_cast<char* const*>(c.base + kPeerTableOff)[threadIdx.x];
   __syncthreads();
   const uint32_t e = s_epoch;
@@ -275,15 +281,14 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
     const int owner = k / per;
     if (owner == c.rank) continue;
     const float v = j < D ? stats[(int64_t)k * D + j] : stats[K * (int64_t)D + k];
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(c.peer(owner) + in_off) +
-                              ((int64_t)c.rank * per + (k - owner * per)) * W1 + j;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(c.peer(owner) + in_off) + ((int64_t)c.rank * per + (k - owner * per)) * W1 + j;
     st_ll(dst, v, e);
   }
 
   // ---- phase 2: reduce my rows in fixed rank order, update, publish ----
   const int lane = threadIdx.x % G;
   const int rows_per_block = blockDim.x / G;
-  const unsigned long long* __restrict__ stage_in = reinterpret_cast<const unsigned long long*>(c.base + in_off);
+  const uint32_t* __restrict__ stage_in = reinterpret_cast<const uint32_t*>(c.base + in_off);
   for (int base = lo + blockIdx.x * rows_per_block; base < hi; base += gridDim.x * rows_per_block) {
     const int k_raw = base + threadIdx.x / G;
     const bool valid = k_raw < hi;
@@ -293,17 +298,17 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
     for (int j = 0; j < NPL; ++j) s[j] = 0.f;
     constexpr int B = NPL <= 4 ? kBatch : (NPL <= 8 ? 4 : (NPL <= 16 ? 2 : 1));
     for (int r0 = 0; r0 < c.world; r0 += B) {          // every poll of a batch is in flight before the first check
-      unsigned long long wc[B], wv[B][NPL];
+      uint32_t wc[B], wv[B][NPL];
 #pragma unroll
       for (int b = 0; b < B; ++b) {
         const int r = r0 + b;
         if (r < c.world && r != c.rank) {
-          const unsigned long long* row = stage_in + ((int64_t)r * per + (k - lo)) * W1;
+          const uint32_t* row = stage_in + ((int64_t)r * per + (k - lo)) * W1;
           wc[b] = ld_ll_raw(row + D);
 #pragma unroll
           for (int j = 0; j < NPL; ++j) {
             const int d = lane + j * G;
-            wv[b][j] = d < D ? ld_ll_raw(row + d) : 0ull;
+            wv[b][j] = d < D ? ld_ll_raw(row + d) : 0u;
           }
         }
       }
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
             if (d < D) s[j] += stats[(int64_t)k * D + d];
           }
         } else {
-          const unsigned long long* row = stage_in + ((int64_t)r * per + (k - lo)) * W1;
+          const uint32_t* row = stage_in + ((int64_t)r * per + (k - lo)) * W1;
           cnt += ld_ll(row + D, wc[b], e, c);
 #pragma unroll
           for (int j = 0; j < NPL; ++j) {
@@ -353,24 +358,25 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
     for (int j = 0; j < NPL; ++j) {
       const int d = lane + j * G;
       if (valid && d < D) {
-        const float out = __fdiv_rn(s[j], dn2);
+        // the row every replica stores: the LSB is the wire flag, so it is cleared here as well (bit-identical replicas)
+        const float out = __uint_as_float(__float_as_uint(__fdiv_rn(s[j], dn2)) & ~1u);
         Wl[(int64_t)k * D + d] = out;
         for (int r = 0; r < c.world; ++r)
-          if (r != c.rank) st_ll(reinterpret_cast<unsigned long long*>(c.peer(r) + out_off) + (int64_t)k * D + d, out, e);
+          if (r != c.rank) st_ll(reinterpret_cast<uint32_t*>(c.peer(r) + out_off) + (int64_t)k * D + d, out, e);
       }
     }
   }
 
   // ---- phase 3: collect the rows of the other owners ----
-  const unsigned long long* __restrict__ stage_out = reinterpret_cast<const unsigned long long*>(c.base + out_off);
+  const uint32_t* __restrict__ stage_out = reinterpret_cast<const uint32_t*>(c.base + out_off);
   const int mine0 = lo * D, mine1 = hi * D;
   for (int idx0 = tid; idx0 < (int)K * D; idx0 += 4 * nthreads) {
-    unsigned long long w4[4];
+    uint32_t w4[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int idx = idx0 + u * nthreads;
       const bool on = idx < (int)K * D && !(idx >= mine0 && idx < mine1);
-      w4[u] = on ? ld_ll_raw(stage_out + idx) : 0ull;
+      w4[u] = on ? ld_ll_raw(stage_out + idx) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
     __threadfence();
     if (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1) {
       ctl->ticket = 0;
-      *reinterpret_cast<volatile uint32_t*>(&ctl->epoch) = e;
+      *reinterpret_cast<volatile uint32_t*>(&ctl->ll_epoch) = e;
       __threadfence();
     }
   }
@@ -598,7 +604,7 @@ int vqb_comm_kmeans_ema_update(void* region, int rank, int world, size_t stats_o
   Comm c{static_cast<char*>(region), rank, world};
   VQB_REQUIRE(D <= 1024, "vqb_comm_kmeans_ema_update: D <= 1024");
   const bool ll = ll_in_off != (size_t)-1 && ll_out_off != (size_t)-1;
-  VQB_REQUIRE(!ll || (ll_in_off % 8 == 0 && ll_out_off % 8 == 0 && K * (int64_t)(D + 1) < (1ll << 31)),
+  VQB_REQUIRE(!ll || (ll_in_off % 4 == 0 && ll_out_off % 4 == 0 && K * (int64_t)(D + 1) < (1ll << 31)),
               "vqb_comm_kmeans_ema_update: bad low-latency staging");
   const int g = pow2_lanes_c(D);           // one lane per element up to 32: the exchange is latency-bound, go wide
   int npl = 1;

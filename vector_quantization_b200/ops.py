@@ -458,7 +458,7 @@ def comm_kmeans_ema_update(region, K: int, D: int, decay: float, *, stats: str =
 def comm_ll_layout(K: int, D: int, world: int):
     """Staging buffers of the low-latency exchange: (name, shape, dtype) entries for PeerRegion.alloc."""
     per = (K + world - 1) // world
-    return [('ll_in', (world * per * (D + 1),), torch.int64), ('ll_out', (K * D,), torch.int64)]
+    return [('ll_in', (world * per * (D + 1),), torch.int32), ('ll_out', (K * D,), torch.int32)]
 
 
 def comm_cvq_update(region, K: int, D: int, *, decay: float, eps: float, minloc: bool, counts: str = 'counts',
