@@ -276,13 +276,25 @@ __global__ void __launch_bounds__(256) comm_kmeans_ema_ll_kernel(Comm c, size_t 
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
 
   // ---- phase 1: push my partials to the owners ----
-  for (int idx = tid; idx < (int)K * W1; idx += nthreads) {
-    const int k = idx / W1, j = idx - k * W1;
-    const int owner = k / per;
-    if (owner == c.rank) continue;
-    const float v = j < D ? stats[(int64_t)k * D + j] : stats[K * (int64_t)D + k];
-    uint32_t* dst = reinterpret_cast<uint32_t*>(c.peer(owner) + in_off) + ((int64_t)c.rank * per + (k - owner * per)) * W1 + j;
-    st_ll(dst, v, e);
+  for (int idx0 = tid; idx0 < (int)K * W1; idx0 += 4 * nthreads) {   // 4 independent local loads in flight per thread
+    float v[4];
+    uint32_t* dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + u * nthreads;
+      dst[u] = nullptr;
+      if (idx < (int)K * W1) {
+        const int k = idx / W1, j = idx - k * W1;
+        const int owner = k / per;
+        if (owner != c.rank) {
+          v[u] = j < D ? stats[(int64_t)k * D + j] : stats[K * (int64_t)D + k];
+          dst[u] = reinterpret_cast<uint32_t*>(c.peer(owner) + in_off) + ((int64_t)c.rank * per + (k - owner * per)) * W1 + j;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst[u] != nullptr) st_ll(dst[u], v[u], e);
   }
 
   // ---- phase 2: reduce my rows in fixed rank order, update, publish ----
@@ -454,6 +466,10 @@ __global__ void __launch_bounds__(256) comm_cvq_update_kernel(Comm c, size_t cou
     __syncwarp();
     if (lane == 0)
       for (int r = 0; r < c.world; ++r) reinterpret_cast<float*>(c.peer(r) + prob_off)[k] = p;
+    // In fp32 `dec` rounds to exactly 1 once p*K*10/(1-decay) exceeds ~17.3 (any code used at > 2 % of the uniform rate):
+    // the blend is then W*1 + anchor*0 = W bit for bit, so neither the peers' anchor rows are read nor the unchanged row
+    // is published — in a healthy codebook the 8 MB anchor exchange shrinks to the rows of the rarely used codes.
+    if (omdec == 0.f) continue;
     for (int d = lane; d < D; d += 32) {
       float a = 0.f;
       if (minloc) {
@@ -610,8 +626,8 @@ int vqb_comm_kmeans_ema_update(void* region, int rank, int world, size_t stats_o
   int npl = 1;
   while (g * npl < D) npl <<= 1;
   int blocks = blocks_for((K + world - 1) / world, 256 / g);
-  if (ll) {   // every block must be resident: it spins on words produced by REMOTE blocks
-    blocks = sm_count() * 2;
+  if (ll) {   // every block must be resident (it spins on words produced by REMOTE blocks): 4 x 256 threads per SM
+    blocks = sm_count() * 4;
   }
 #define LAUNCH(G_, NPL_)                                                                                                   \
   if (ll)                                                                                                                  \

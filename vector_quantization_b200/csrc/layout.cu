@@ -45,37 +45,64 @@ __global__ void __launch_bounds__(256) transpose_last2_vec_kernel(const T* __res
   const int64_t b = blockIdx.z;
   const T* __restrict__ s = src + b * rows * cols;
   T* __restrict__ d = dst + b * rows * cols;
-  const int64_t c0 = (int64_t)blockIdx.x * TC, r0 = (int64_t)blockIdx.y * TR;
-  // load: (TC / VE) vectors per row
+  const int64_t r0 = (int64_t)blockIdx.y * TR;
   constexpr int VPR = TC / VE;
-  for (int v = threadIdx.x; v < TR * VPR; v += 256) {
-    const int r = v / VPR, cv = (v % VPR) * VE;
-    if (r0 + r < rows && c0 + cv < cols) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(s + (r0 + r) * cols + c0 + cv);
-      const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-      for (int i = 0; i < VE; ++i) tile[r][cv + i] = e[i];
-    }
-  }
-  __syncthreads();
-  // store: output row = source column c, TR contiguous elements along r -> TR / VE vectors per output row
   constexpr int VPC = TR / VE;
-  for (int v = threadIdx.x; v < TC * VPC; v += 256) {
-    const int c = v % TC, rv = (v / TC) * VE;   // consecutive lanes -> consecutive c: conflict-free shared reads
-    if (c0 + c < cols && r0 + rv < rows) {
-      uint4 raw;
-      T* e = reinterpret_cast<T*>(&raw);
+  // a block walks the column tiles of its row band (gridDim.x < number of column tiles when there are plenty of
+  // images): a 4-8 KB tile per block left the kernel bound by block scheduling, not by bandwidth
+  for (int64_t c0 = (int64_t)blockIdx.x * TC; c0 < cols; c0 += (int64_t)gridDim.x * TC) {
+    // load: (TC / VE) vectors per row
+    for (int v = threadIdx.x; v < TR * VPR; v += 256) {
+      const int r = v / VPR, cv = (v % VPR) * VE;
+      if (r0 + r < rows && c0 + cv < cols) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(s + (r0 + r) * cols + c0 + cv);
+        const T* e = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-      for (int i = 0; i < VE; ++i) e[i] = tile[rv + i][c];
-      *reinterpret_cast<uint4*>(d + (c0 + c) * rows + r0 + rv) = raw;
+        for (int i = 0; i < VE; ++i) tile[r][cv + i] = e[i];
+      }
     }
+    __syncthreads();
+    // store: output row = source column c, TR contiguous elements along r -> TR / VE vectors per output row
+    for (int v = threadIdx.x; v < TC * VPC; v += 256) {
+      // consecutive lanes -> consecutive vectors of ONE output row (then the next row): full 64-128 B segments per
+      // row instead of 16-byte pieces strided by the row pitch; the padded pitch keeps the shared reads conflict-free
+      // (long output rows, VPC > 8, keep the column-fastest order: their shared reads would conflict 4-way)
+      const int rv = (VPC <= 8 ? v % VPC : v / TC) * VE, c = VPC <= 8 ? v / VPC : v % TC;
+      if (c0 + c < cols && r0 + rv < rows) {
+        uint4 raw;
+        T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int i = 0; i < VE; ++i) e[i] = tile[rv + i][c];
+        *reinterpret_cast<uint4*>(d + (c0 + c) * rows + r0 + rv) = raw;
+      }
+    }
+    __syncthreads();
   }
 }
 
 template <typename TO>
 __global__ void compact_tokens_kernel(const unsigned long long* __restrict__ keys, int64_t n, int64_t offset,
                                       TO* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  // 8 keys per thread: four 128-bit loads, 16 (uint16) or 32 (int32) bytes stored contiguously
+  const int64_t n8 = n / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    ulonglong2 k[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = reinterpret_cast<const ulonglong2*>(keys)[i * 4 + j];
+    TO v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = (TO)(k[j].x == kNoKey ? 0 : (int64_t)key_index(k[j].x) - offset);
+      v[2 * j + 1] = (TO)(k[j].y == kNoKey ? 0 : (int64_t)key_index(k[j].y) - offset);
+    }
+    if constexpr (sizeof(TO) == 2) {
+      reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(v);
+    } else {
+      reinterpret_cast<uint4*>(out)[2 * i] = *reinterpret_cast<const uint4*>(v);
+      reinterpret_cast<uint4*>(out)[2 * i + 1] = *reinterpret_cast<const uint4*>(v + 4);
+    }
+  }
+  for (int64_t i = n8 * 8 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const unsigned long long k = keys[i];
     out[i] = (TO)(k == kNoKey ? 0 : (int64_t)key_index(k) - offset);
   }
@@ -101,13 +128,18 @@ int vqb_transpose_last2(const void* src, int elem_bytes, int64_t batch, int64_t 
     // tile shape follows the matrix: a narrow side (channels = 8 or 16) gets a narrow tile
 #define VQB_TR_CASE(T_, TR_, TC_)                                                                              \
     do {                                                                                                       \
-      const dim3 vgrid((unsigned)((cols + TC_ - 1) / TC_), (unsigned)((rows + TR_ - 1) / TR_), (unsigned)batch); \
+      const int64_t ct = (cols + TC_ - 1) / TC_, rt = (rows + TR_ - 1) / TR_;                                   \
+      int64_t gx = ((int64_t)sm_count() * 16 + rt * batch - 1) / (rt * batch); /* enough blocks for ~2 waves */ \
+      if (gx > ct) gx = ct;                                                                                    \
+      if (gx < 1) gx = 1;                                                                                      \
+      const dim3 vgrid((unsigned)gx, (unsigned)rt, (unsigned)batch);                                           \
       transpose_last2_vec_kernel<T_, TR_, TC_><<<vgrid, 256, 0, st>>>((const T_*)src, rows, cols, (T_*)dst);   \
     } while (0)
 #define VQB_TR_SHAPE(T_)                                      \
     do {                                                      \
       if (cols <= 16) VQB_TR_CASE(T_, 128, 16);               \
       else if (rows <= 16) VQB_TR_CASE(T_, 16, 128);          \
+      else if (cols <= 32) VQB_TR_CASE(T_, 64, 32);           \
       else VQB_TR_CASE(T_, 32, 64);                           \
     } while (0)
     if (elem_bytes == 2) VQB_TR_SHAPE(uint16_t);
@@ -136,7 +168,9 @@ int vqb_compact_tokens(const unsigned long long* keys, int64_t n, int64_t index_
   VQB_REQUIRE(keys && out, "vqb_compact_tokens: null pointer");
   VQB_REQUIRE(out_bytes == 2 || out_bytes == 4, "vqb_compact_tokens: out_bytes must be 2 (uint16) or 4 (int32)");
   if (n <= 0) return VQB_OK;
-  int blocks = (int)((n + 255) / 256);
+  VQB_REQUIRE((uintptr_t)keys % 16 == 0 && (uintptr_t)out % 16 == 0, "vqb_compact_tokens: 16-byte aligned buffers");
+  int blocks = (int)((n / 8 + 255) / 256);
+  if (blocks < 1) blocks = 1;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (out_bytes == 2) compact_tokens_kernel<uint16_t><<<blocks, 256, 0, st>>>(keys, n, index_offset, (uint16_t*)out);

@@ -184,6 +184,7 @@ __global__ void cvq_update_kernel(float* __restrict__ W, const float* __restrict
     const float omdec = __fsub_rn(1.f, dec);
     __syncwarp();
     if (lane == 0) prob[k] = p;
+    if (omdec == 0.f) continue;   // dec == 1 exactly: W*1 + anchor*0 leaves the row unchanged bit for bit (see comm.cu)
     for (int d = lane; d < D; d += 32) {
       const float a = anchors[k * D + d] * anchor_scale;
       W[k * D + d] = __fadd_rn(__fmul_rn(W[k * D + d], dec), __fmul_rn(a, omdec));
