@@ -131,6 +131,15 @@ int64_t vqb_certify_workspace_bytes(int64_t rows);
 int vqb_certify(const unsigned long long* keys, const unsigned long long* second_keys, int64_t rows,
                 const float* row_inv_norm, const float* delta, float noise, int* row_list, int* count,
                 unsigned long long* compact_keys, void* workspace, void* stream);
+/* CVQ-VAE (cvqvae/quantizer_callback.py:94-102): lists, in ascending order, the codes whose anchor can get a NON-ZERO
+ * blend weight this step.  In fp32 the per-code decay 1 - exp(-p*K*10/(1-gamma) - eps) is exactly 1 for every code
+ * used at more than ~2 % of the uniform rate, so its anchor is multiplied by exactly 0: only the listed codes need the
+ * column arg-min (NearestAnchor) and an anchor row.  Evaluated on a lower bound of the new probability (this rank's
+ * counts over the GLOBAL token total): a superset of the truly affected codes on every rank, no exchange needed.
+ * Outputs and workspace as vqb_certify (vqb_certify_workspace_bytes(K)). */
+int vqb_cvq_needy_codes(const float* prob, const int64_t* counts_local, float total_global, int64_t K, float decay,
+                        float one_minus_decay, float eps, int* code_list, int* count,
+                        unsigned long long* compact_keys, void* workspace, void* stream);
 /* dst[p][i][:] = src[p][row_list[i]][:] for i < *count (16-bit planes, Dp a multiple of 8) */
 int vqb_gather_plane_rows(const void* src, int nplanes, int64_t src_plane_rows, int Dp, const int* row_list,
                           const int* count, int64_t cap, void* dst, int64_t dst_plane_rows, void* stream);

@@ -579,7 +579,35 @@ def test_certified_pass_through_the_module(dev):
     assert (gap < 1e-5).all() and rows.numel() <= 4
     torch.testing.assert_close(loss.detach().cpu(), out['loss'][0].detach(), rtol=1e-5, atol=1e-7)
     if rows.numel() == 0:
+        ck = memo['encode']['column_keys'].cpu()
+        has_key = ck != -1                      # the column pass is restricted to the codes whose anchor has weight
         col = ops.unpack_keys(memo['encode']['column_keys']).cpu()
-        same = col == out['anchor_idx'][0]
-        assert same.float().mean() > 0.99
+        same = (col == out['anchor_idx'][0]) | ~has_key
+        assert has_key.any() and same.float().mean() > 0.99
         torch.testing.assert_close(q.embedding.weight.detach().cpu()[same], out['weight'][same], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(q.get_buffer('_probability').cpu(), out['prob'], rtol=1e-6, atol=1e-9)
+
+
+def test_cvq_needy_codes_is_a_superset_of_the_codes_with_nonzero_anchor_weight(dev):
+    """vqb_cvq_needy_codes: ascending list of the codes whose fp32 blend weight 1 - decay_k can be non-zero, from a
+    LOWER bound of the new probability (local counts over the global total).  It must contain every code whose true
+    weight (global counts) is non-zero, and leave out the clearly busy ones."""
+    K, N, world = 4096, 16384, 4
+    g = torch.Generator().manual_seed(5)
+    prob = torch.rand(K, generator=g) / K
+    prob[::3] *= 1e-4
+    local = torch.randint(0, 6, (K,), generator=g)
+    others = torch.randint(0, 14, (K,), generator=g)
+    cnt_local = torch.cat([local, torch.tensor([N])]).to(torch.int64)
+    code_list, count, compact = ops.cvq_needy_codes(prob.to(dev), cnt_local.to(dev), world * N, decay=0.99, eps=1e-3)
+    n = int(count)
+    listed = code_list[:n].cpu().long()
+    assert torch.equal(listed, listed.sort().values) and listed.unique().numel() == n
+    assert (compact[:n].cpu() == -1).all()
+    p_true = O.ema(prob, (local + others).float() / (world * N), 0.99)
+    weight = 1 - (1 - torch.exp(-p_true * K * 10 / (1 - 0.99) - 1e-3))
+    needed = (weight != 0).nonzero().flatten()
+    mask = torch.zeros(K, dtype=torch.bool)
+    mask[listed] = True
+    assert mask[needed].all(), 'a code with a non-zero anchor weight is missing from the list'
+    assert 0.1 < mask.float().mean() < 0.9

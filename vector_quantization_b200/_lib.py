@@ -50,6 +50,8 @@ SIGNATURES = {
     'vqb_certify_workspace_bytes': (c_int64, [c_int64]),
     'vqb_certify': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_void_p]),
+    'vqb_cvq_needy_codes': (c_int, [c_void_p, c_void_p, c_float, c_int64, c_float, c_float, c_float, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
     'vqb_gather_plane_rows': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                       c_void_p]),
     'vqb_gather_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -467,7 +467,17 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
         x = x.detach().contiguous()
         N = x.shape[0]
         vq.protect_saved_codebook()
-        col_keys = memo['encode'].get('column_keys')
+        world = parallel.world_size()
+
+        def column_keys(counts: torch.Tensor):
+            """The column arg-min, restricted to the codes whose anchor can get a non-zero blend weight this step: in
+            fp32 the per-code decay is exactly 1 for every code used at more than ~2 % of the uniform rate, its anchor
+            is then multiplied by exactly 0 (results are bit-identical to computing every anchor)."""
+            if not self._anchor.needs_columns or '_column_ctx' not in memo['encode']:
+                return memo['encode'].get('column_keys')
+            rows = ops.cvq_needy_codes(self.probability, counts, world * N, decay=self._ema.decay, eps=self._eps)
+            return vq.column_keys(memo['encode'], rows=rows)
+
         if getattr(self._anchor, 'peer_exchange', False):
             region = self._peer_region(x.device, [('W', (K, D), torch.float32), ('prob', (K,), torch.float32),
                                                   ('counts', (K + 1,), torch.int64), ('anchors', (K, D), torch.float32),
@@ -480,6 +490,7 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
                 # anchors are global); ONE fused launch reduces them, updates `_probability` and blends the anchors
                 # into the codebook of every replica
                 ops.bincount_accumulate(quant, region.counts.zero_(), K, total_slot=True)
+                col_keys = column_keys(region.counts)        # this rank's counts: a lower bound of the global ones
                 self._anchor.gather_local(x, col_keys, N, out=region.anchors)
                 if self._anchor.sync:
                     region.keys.copy_(col_keys)
@@ -490,7 +501,7 @@ class CVQVAECallback(UpdateMixin, BaseCallback):
         cnt = torch.zeros(K + 1, dtype=torch.int64, device=x.device)
         ops.bincount_accumulate(quant, cnt, K, total_slot=True)
         parallel.all_reduce_sum_(cnt)
-        world = parallel.world_size()
+        col_keys = column_keys(cnt)
         anchors = self._anchor.gather(x, col_keys, N, num_codes=K, distance=memo['encode'].get('distance'))
         scale = 1.0 if self._anchor.sync else 1.0 / world
         if self._anchor.sync:

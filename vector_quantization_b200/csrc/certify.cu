@@ -38,6 +38,40 @@ __global__ void __launch_bounds__(kCertBlock) certify_flag_kernel(
   if (threadIdx.x == 0) block_counts[blockIdx.x] = s_count;
 }
 
+// CVQ-VAE: which codes can receive a non-zero anchor weight this step?  (cvqvae/quantizer_callback.py:94-102)
+//   p = ema(p_old, count / total);  decay_k = 1 - exp(-p*K*10/(1-gamma) - eps);  W_k <- W_k*decay_k + anchor_k*(1 - decay_k)
+// In fp32 decay_k rounds to exactly 1 once p*K*10/(1-gamma) exceeds ~17.3, i.e. for every code used at more than ~2 % of
+// the uniform rate; the anchor of such a code is multiplied by exactly 0.  The flag is evaluated on a LOWER bound of
+// p (this rank's count over the global token total, times 0.999): p can only be larger once the counts of the other
+// ranks are in, and 1 - decay_k is non-increasing in p, so every code whose true weight is non-zero is flagged on every
+// rank (a superset, never a subset).  Only the flagged codes need the column arg-min and an anchor row.
+__global__ void __launch_bounds__(kCertBlock) cvq_needy_flag_kernel(
+    const float* __restrict__ prob, const int64_t* __restrict__ counts_local, float total_global, int64_t K, float decay,
+    float omd, float eps, uint32_t* __restrict__ ballots, int* __restrict__ block_counts) {
+  __shared__ int s_count;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const int64_t k = blockIdx.x * (int64_t)kCertBlock + threadIdx.x;
+  bool flag = false;
+  if (k < K) {
+    const float freq_lb = __fdiv_rn((float)counts_local[k], total_global);
+    const float p = (__fadd_rn(__fmul_rn(prob[k], decay), __fmul_rn(freq_lb, omd))) * 0.999f;
+    float t = __fmul_rn(__fmul_rn(-p, (float)K), 10.f);
+    t = __fsub_rn(__fdiv_rn(t, omd), eps);
+    const float dec = __fsub_rn(1.f, expf(t));
+    flag = !(__fsub_rn(1.f, dec) == 0.f);          // NaN probabilities are flagged as well
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, flag);
+  if ((threadIdx.x & 31) == 0) {
+    ballots[blockIdx.x * (kCertBlock / 32) + (threadIdx.x >> 5)] = word;
+    atomicAdd(&s_count, __popc(word));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = s_count;
+}
+
 // Compaction pass: ascending row order (deterministic, identical on every rank of a sharded run).
 __global__ void __launch_bounds__(kCertBlock) certify_compact_kernel(
     const uint32_t* __restrict__ ballots, const int* __restrict__ block_counts, int nblocks, int* __restrict__ row_list,
@@ -144,6 +178,23 @@ int vqb_certify(const unsigned long long* keys, const unsigned long long* second
                          ballots, block_counts));
   VQB_CUDA_OK(launch_pdl(certify_compact_kernel, nblocks, kCertBlock, 0, st, (const uint32_t*)ballots,
                          (const int*)block_counts, nblocks, row_list, count, compact_keys));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_cvq_needy_codes(const float* prob, const int64_t* counts_local, float total_global, int64_t K, float decay,
+                        float one_minus_decay, float eps, int* code_list, int* count, unsigned long long* compact_keys,
+                        void* workspace, void* stream) {
+  VQB_REQUIRE(prob && counts_local && code_list && count && compact_keys && workspace, "vqb_cvq_needy_codes: null pointer");
+  VQB_REQUIRE(K >= 1 && K < (1ll << 31) && total_global > 0.f, "vqb_cvq_needy_codes: bad arguments");
+  const int nblocks = (int)((K + kCertBlock - 1) / kCertBlock);
+  uint32_t* ballots = static_cast<uint32_t*>(workspace);
+  int* block_counts = reinterpret_cast<int*>(ballots + (size_t)nblocks * (kCertBlock / 32));
+  cudaStream_t st = (cudaStream_t)stream;
+  VQB_CUDA_OK(launch_pdl(cvq_needy_flag_kernel, nblocks, kCertBlock, 0, st, prob, counts_local, total_global, K, decay,
+                         one_minus_decay, eps, ballots, block_counts));
+  VQB_CUDA_OK(launch_pdl(certify_compact_kernel, nblocks, kCertBlock, 0, st, (const uint32_t*)ballots,
+                         (const int*)block_counts, nblocks, code_list, count, compact_keys));
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

@@ -149,33 +149,45 @@ def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precisi
 
 @torch.no_grad()
 def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precision: str = DEFAULT_PRECISION,
-                   index_offset: int = 0, tokens: ops.Operand | None = None) -> torch.Tensor:
+                   index_offset: int = 0, tokens: ops.Operand | None = None, rows=None) -> torch.Tensor:
     """Packed keys [K]: for every code, the nearest token (column arg-min) — the same kernel with the
-    operands swapped.  `tokens`: an already packed fmt='f16' token plane to share with `nearest_code`.  Cosine needs normalised token planes here (the token norm now varies along the
-    reduced axis); L2 needs the tokens' 0.5|x|^2."""
+    operands swapped.  `tokens`: an already packed fmt='f16' token plane to share with `nearest_code`.  Cosine needs
+    normalised token planes here (the token norm now varies along the reduced axis); L2 needs the tokens' 0.5|x|^2.
+    rows = (code_list int32, count int32 [1], compact_keys): restrict the pass to the listed codes (device-side count;
+    CVQ-VAE only needs the codes whose anchor gets a non-zero weight); the other entries stay all-ones."""
     cos = metric == 'Cosine'
-    keys = ops.new_keys(codebook.rows, x.device)
+    kw = dict(l2=False, index_offset=index_offset)
+    certified = False
     if codebook.fmt != 'bf16':
         # fp16 codebook planes need fp16 token planes
         if x.dtype == torch.bfloat16:
             # raw bf16 tokens as ONE fp16 plane + the per-column 1/|x_n| scale in the epilogue: two MMA terms
-            raw = tokens if (tokens is not None and tokens.fmt == 'f16') else ops.pack_rows(x, fmt='f16')
-            if raw.inv_norm is None:
-                raw.inv_norm = ops.row_inv_norm(x, f16_rows=True)
-            if codebook.lo_norm_max is not None:
-                return certified_assign(codebook, raw, keys, scale_columns=True, index_offset=index_offset)
-            return ops.assign(codebook, raw, keys, l2=False, scale_columns=True, index_offset=index_offset)
-        toks = ops.pack_rows(x, normalize=True, fmt='f16x2')      # normalised tokens as a pair: three terms
-        return ops.assign(codebook, toks, keys, l2=False, index_offset=index_offset)
-    if cos:
-        raw = ops.as_operand(x)
-        if raw is not None:
+            b = tokens if (tokens is not None and tokens.fmt == 'f16') else ops.pack_rows(x, fmt='f16')
+            if b.inv_norm is None:
+                b.inv_norm = ops.row_inv_norm(x, f16_rows=True)
+            kw['scale_columns'] = True
+            certified = codebook.lo_norm_max is not None
+        else:
+            b = ops.pack_rows(x, normalize=True, fmt='f16x2')      # normalised tokens as a pair: three terms
+    else:
+        b = ops.as_operand(x) if cos else None
+        if b is not None:
             # bf16 tokens: ONE exact raw plane + a per-column 1/|x_n| scale in the epilogue instead of three planes
             # of the normalised tokens (halves the MMA work of this pass)
-            raw.inv_norm = ops.row_inv_norm(x)
-            return ops.assign(codebook, raw, keys, l2=False, scale_columns=True, index_offset=index_offset)
-    toks = ops.pack_rows(x, normalize=cos, planes=_planes_for(x, cos, precision), want_half_sqnorm=not cos)
-    return ops.assign(codebook, toks, keys, l2=not cos, index_offset=index_offset)
+            b.inv_norm = ops.row_inv_norm(x)
+            kw['scale_columns'] = True
+        else:
+            b = ops.pack_rows(x, normalize=cos, planes=_planes_for(x, cos, precision), want_half_sqnorm=not cos)
+            kw['l2'] = not cos
+    keys = ops.new_keys(codebook.rows, x.device)
+    if rows is not None:
+        code_list, count, compact = rows
+        a = ops.gather_operand_rows(codebook, code_list, count)     # the listed codes as a compact operand
+        ops.assign(a, b, compact, a_rows_dev=count, **kw)
+        return ops.scatter_keys(compact, code_list, count, keys)
+    if certified:
+        return certified_assign(codebook, b, keys, scale_columns=True, index_offset=index_offset)
+    return ops.assign(codebook, b, keys, **kw)
 
 
 class _DistanceMatrix(torch.autograd.Function):

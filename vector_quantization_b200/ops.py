@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, PLANES_F16, PLANES_F16X2, VQB_BF16, VQB_F32, FSQParams, check
 
 __all__ = [
-    'Operand', 'as_operand', 'pack_rows', 'assign', 'certify', 'gather_operand_rows', 'scatter_keys', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
+    'Operand', 'as_operand', 'pack_rows', 'assign', 'certify', 'cvq_needy_codes', 'gather_operand_rows', 'scatter_keys', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
     'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
     'fsq_decode', 'transpose_last2', 'compact_tokens', 'distance_matrix', 'comm_kmeans_ema_update', 'comm_cvq_update',
@@ -224,6 +224,22 @@ def certify(keys: torch.Tensor, second_keys: torch.Tensor, rows: int, delta: tor
     _call('vqb_certify', lib.vqb_certify, dev, _p(keys), _p(second_keys), rows, _p(row_inv_norm), _p(delta), noise,
           _p(row_list), _p(count), _p(compact), _p(ws), _S)
     return row_list, count, compact
+
+
+def cvq_needy_codes(prob: torch.Tensor, counts_local: torch.Tensor, total_global: int, *, decay: float, eps: float):
+    """Codes whose anchor can receive a non-zero blend weight this step (vqb_cvq_needy_codes) ->
+    (code_list int32 [K], count int32 [1], compact_keys int64 [K] with the first `count` entries reset)."""
+    lib = _lib.load()
+    dev = _cuda(prob, counts_local)
+    K = prob.numel()
+    assert counts_local.dtype == torch.int64 and counts_local.numel() >= K
+    code_list = torch.empty((K,), dtype=torch.int32, device=prob.device)
+    count = torch.empty((1,), dtype=torch.int32, device=prob.device)
+    compact = torch.empty((K,), dtype=torch.int64, device=prob.device)
+    ws = torch.empty((int(lib.vqb_certify_workspace_bytes(K)),), dtype=torch.uint8, device=prob.device)
+    _call('vqb_cvq_needy_codes', lib.vqb_cvq_needy_codes, dev, _p(prob), _p(counts_local), float(total_global), K,
+          _f32(decay), _f32(1 - decay), _f32(eps), _p(code_list), _p(count), _p(compact), _p(ws), _S)
+    return code_list, count, compact
 
 
 def gather_operand_rows(src: Operand, row_list: torch.Tensor, count: torch.Tensor) -> Operand:

@@ -104,6 +104,7 @@ class BaseQuantizer(nn.Module):
         memo.pop('_zero_fill', None)
         quant, memo['encode'] = self._encode(x, enc)
         quant = self._callbacks.after_encode(x, quant, memo)
+        memo['encode'].pop('_column_ctx', None)      # operands kept for the callbacks' column arg-min
         return x, quant, memo
 
     def _decode(self, quant: torch.Tensor, memo: dict):
@@ -255,12 +256,25 @@ class VectorQuantizer(BaseQuantizer):
                         normalize_tokens=normalize_tokens, tokens=tokens)
         memo['keys'] = keys
         if want_columns:
-            offset = parallel.rank() * x.shape[0] if self._callbacks.column_nearest_global else 0
-            memo['column_keys'] = Fq.column_nearest(x, book, metric, precision=self.precision, index_offset=offset,
-                                                    tokens=tokens)
+            # the column arg-min (per code, the nearest token) runs when the callback asks for it: CVQVAECallback first
+            # works out WHICH codes need it this step (`column_keys`)
+            memo['_column_ctx'] = dict(x=x, book=book, tokens=tokens, metric=metric)
         if memo.pop('_lazy_unpack', False):
             return keys, memo            # forward(): the fused gather kernel unpacks the indices
         return ops.unpack_keys(keys), memo
+
+    @torch.no_grad()
+    def column_keys(self, enc_memo: dict, rows=None) -> torch.Tensor:
+        """Packed keys [K] of the nearest token per code (NearestAnchor's `d.argmin(0)`, cvqvae/anchors.py:83), computed
+        on the operands `_encode` left in its memo; `rows` restricts the pass to a device-side list of codes.  The result
+        is also stored as memo['encode']['column_keys']."""
+        ctx = enc_memo.pop('_column_ctx')
+        x = ctx['x']
+        offset = parallel.rank() * x.shape[0] if self._callbacks.column_nearest_global else 0
+        keys = Fq.column_nearest(x, ctx['book'], ctx['metric'], precision=self.precision, index_offset=offset,
+                                 tokens=ctx['tokens'], rows=rows)
+        enc_memo['column_keys'] = keys
+        return keys
 
     def _decode(self, quant: torch.Tensor, memo: dict):
         """`nn.Embedding` gather, any index shape (decode_from_quant).  Differentiable w.r.t. the codebook when it
