@@ -27,7 +27,8 @@ def _free_port():
 
 
 def _worker(rank, world, port, case, out, comm, ack):
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), VQB_COMM=comm)
+    # VQB_DRY_RUN: the reference's DRY_RUN `is_sync` assertions — every codebook update checks that all replicas agree
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), VQB_COMM=comm, VQB_DRY_RUN='1')
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
