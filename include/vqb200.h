@@ -191,6 +191,8 @@ int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D,
                         int64_t* quant_out,            /* optional [N]: the unpacked indices (memo['quant']) */
                         float* x_norm_out,             /* optional [N,D]: F.normalize(x) (memo['x']) */
                         float* z_ste_out,              /* [N,D] fp32 value x' + (W[q] - x'), x' = (normalised) x */
+                        int64_t z_hw,                  /* 0: z token-major [N,D]; h*w > 0: z written as NCHW [N/hw, D, hw] — the caller's
+                                                          '(b h w) c -> b c h w' (models/base.py:126-127) fused into the store */
                         int want_norm_mse,
                         float* mse4_out, float* partials, unsigned int* ticket, void* stream);
 
@@ -210,7 +212,9 @@ int vqb_quantize_backward(const void* g_zste, int g_dtype /* VQB_F32, or VQB_BF1
                           const float* g_codebook, const float* g_commitment,           /* DEVICE scalars, NULL = 0 */
                           const float* g_codebook_norm, const float* g_commitment_norm,
                           int want_norm_mse,
-                          void* gx_out /* x dtype */, float* gW_accum, void* stream);
+                          void* gx_out /* x dtype */, float* gW_accum,
+                          int64_t g_hw /* 0: g_zste and gx token-major; h*w > 0: both NCHW [N/hw, D, hw] (x stays token-major) */,
+                          void* stream);
 
 /* ---- row l2-normalisation (NormalizeCallback.before_encode on x) ------------------------ *
  * vq/algorithms/vq/callbacks/normalize.py:24  — forward y = x / max(||x||, 1e-12); backward

@@ -124,3 +124,53 @@ def test_quantize_nchw_vs_oracle_caller(dev):
     torch.testing.assert_close(loss.detach().cpu(), loss_ref.detach(), rtol=1e-5, atol=1e-7)
     tokens, _ = tokenizer.encode_to_quant(q, x.to(dev), dict())
     assert (tokens.cpu() == O.model_encode_to_quant('L2', x, E)).float().mean() > 0.999
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('c,hw,cfg_kind', [(32, (16, 16), 'vqkd'), (256, (8, 8), 'vqgan'), (8, (16, 16), 'llamagen'),
+                                           (32, (8, 8), 'llamagen_cvq')])
+def test_layout_fusion_launches_one_transpose_and_matches_the_rows_path(dev, dtype, c, hw, cfg_kind):
+    """`tokenizer.quantize` folds the caller's rearranges into the kernels — ONE transposed copy of the
+    latents on the way in, z written NCHW by the gather kernel, the backward reading / writing NCHW gradients: a
+    single transpose launch per forward+backward instead of three.  Configurations whose callbacks need normalised
+    tokens up front (NormalizeCallback + CVQVAECallback) keep the three-transpose path.  Either way the results equal
+    the token-major path bit for bit."""
+    h, w = hw
+    b, K = 4, 256
+    emb = dict(type='torch_nn_modules_sparse_Embedding', num_embeddings=K, embedding_dim=c)
+    cfgs = {
+        'vqkd': dict(type='VQKDQuantizer', distance=dict(type='CosineDistance'), callbacks=[dict(type='VQKDCallback', ema=dict())],
+                     losses=dict(commitment_loss=dict(type='CommitmentLoss', mse=dict(norm=True)))),
+        'vqgan': dict(type='VQGANQuantizer', distance=dict(type='L2Distance'), losses=dict(vqgan_loss=dict(type='VQGANLoss')),
+                      init_weights=dict(type='vqgan')),
+        'llamagen': dict(type='VQGANQuantizer', distance=dict(type='L2Distance'), callbacks=[dict(type='NormalizeCallback')],
+                         losses=dict(vqgan_loss=dict(type='VQGANLoss')), init_weights=dict(type='vqgan')),
+        'llamagen_cvq': dict(type='VQGANQuantizer', distance=dict(type='L2Distance'),
+                             callbacks=[dict(type='NormalizeCallback'),
+                                        dict(type='CVQVAECallback', ema=dict(), anchor=dict(type='NearestAnchor'))],
+                             losses=dict(vqgan_loss=dict(type='VQGANLoss')), init_weights=dict(type='vqgan')),
+    }
+    q = vqb.build_quantizer(dict(cfgs[cfg_kind], embedding=emb), training=False).to(dev)
+    q._forward_pre_hooks.clear()
+    rows, E = O.synthetic_latents(b * h * w, K, c, seed=c + h, normalized_codebook=True)
+    with torch.no_grad():
+        q.embedding.weight.copy_(E)
+    x0 = rows.view(b, h, w, c).permute(0, 3, 1, 2).contiguous().to(dtype).to(dev)
+    gz = torch.randn(b, c, h, w, generator=torch.Generator().manual_seed(2)).to(dev)
+    x = x0.clone().requires_grad_(True)
+    ops.PROFILE = []
+    z, loss, memo = tokenizer.quantize(q, x, dict())
+    (z * gz).sum().add(loss).backward()
+    torch.cuda.synchronize()
+    transposes = sum(name == 'vqb_transpose_last2' for name, _, _ in ops.PROFILE)
+    ops.PROFILE = None
+    assert q.can_fuse_nchw() == (cfg_kind != 'llamagen_cvq')
+    assert transposes == (1 if q.can_fuse_nchw() else 3)
+    assert z.shape == (b, c, h, w) and z.is_contiguous() and x.grad.shape == x.shape and x.grad.dtype == dtype
+    rows_in = x0.permute(0, 2, 3, 1).reshape(-1, c).contiguous().clone().requires_grad_(True)
+    z_ref, loss_ref, memo_ref = q(rows_in, dict())
+    (z_ref * gz.permute(0, 2, 3, 1).reshape(-1, c)).sum().add(loss_ref).backward()
+    assert torch.equal(memo['quantizer']['quant'], memo_ref['quant'])
+    assert torch.equal(z.detach(), z_ref.detach().view(b, h, w, c).permute(0, 3, 1, 2))
+    assert torch.equal(loss.detach(), loss_ref.detach())
+    assert torch.equal(x.grad, rows_in.grad.view(b, h, w, c).permute(0, 3, 1, 2))

@@ -53,6 +53,25 @@ __device__ __forceinline__ void store_slice(T* __restrict__ p, int d0, int D, co
   }
 }
 
+// NCHW addressing of a token-major element (n, d): the caller's `(b h w) c <-> b c h w` rearranges
+// (vq/tasks/image_tokenization/models/base.py:124,126-127) folded into the kernels.  For a fixed d consecutive tokens
+// are contiguous, so the lanes of a warp (consecutive tokens) still write / read whole 32-byte sectors.
+template <typename T, int V>
+__device__ __forceinline__ void store_slice_nchw(T* __restrict__ p, int64_t n, int64_t hw, int d0, int D, const float (&v)[V]) {
+  const int64_t b = n / hw, s = n - b * hw;
+  T* __restrict__ q = p + (b * D + d0) * hw + s;
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+    if (d0 + i < D) q[i * hw] = from_f32<T>(v[i]);
+}
+template <typename T, int V>
+__device__ __forceinline__ void load_slice_nchw(const T* __restrict__ p, int64_t n, int64_t hw, int d0, int D, float (&v)[V]) {
+  const int64_t b = n / hw, s = n - b * hw;
+  const T* __restrict__ q = p + (b * D + d0) * hw + s;
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = (d0 + i < D) ? to_f32<T>(q[i * hw]) : 0.f;
+}
+
 // block-wide deterministic sum of two values; result valid in thread 0
 __device__ __forceinline__ void block_sum2(float& a, float& b, float* sh /* >= 2*8 floats */) {
   a = warp_sum(a);
@@ -89,7 +108,7 @@ template <typename TX, int G, int V, int NV>
 __global__ void __launch_bounds__(256) quantize_forward_kernel(
     const TX* __restrict__ x, int64_t N, int D, int normalize_x, const float* __restrict__ W, int64_t K,
     const int64_t* __restrict__ quant, const unsigned long long* __restrict__ keys, int64_t key_offset,
-    int64_t* __restrict__ quant_out, float* __restrict__ xn_out, float* __restrict__ z_out, int want_norm,
+    int64_t* __restrict__ quant_out, float* __restrict__ xn_out, float* __restrict__ z_out, int64_t z_hw, int want_norm,
     float* __restrict__ mse4, float* __restrict__ partials, unsigned int* __restrict__ ticket) {
   __shared__ float sh[16];
   pdl_wait();               // keys / codebook come from the preceding launches of the step
@@ -157,7 +176,8 @@ __global__ void __launch_bounds__(256) quantize_forward_kernel(
         }
       }
       if (valid && d0 < D) {
-        store_slice<float, V>(z_out + n * D, d0, D, zr);
+        if (z_hw > 0) store_slice_nchw<float, V>(z_out, n, z_hw, d0, D, zr);   // z straight into the caller's NCHW layout
+        else store_slice<float, V>(z_out + n * D, d0, D, zr);
         if (xn_out) store_slice<float, V>(xn_out + n * D, d0, D, xr[it]);
       }
     }
@@ -205,7 +225,7 @@ __global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
     const TG* __restrict__ gz, const TX* __restrict__ x, int normalize_x, const float* __restrict__ W, int64_t K,
     const int64_t* __restrict__ quant, int64_t N, int D, const float* __restrict__ g_cb,
     const float* __restrict__ g_cm, const float* __restrict__ g_cbn, const float* __restrict__ g_cmn, int want_norm,
-    TX* __restrict__ gx, float* __restrict__ gW) {
+    TX* __restrict__ gx, float* __restrict__ gW, int64_t g_hw) {
   pdl_wait();               // upstream gradients / indices come from the preceding launches
   pdl_launch_dependents();
   const int lane = threadIdx.x % G;
@@ -228,7 +248,8 @@ __global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
       if (d0 < D) {
         load_slice<TX, V>(xrow, d0, D, yr[it]);
         load_slice<float, V>(wrow, d0, D, wr[it]);
-        load_slice<TG, V>(gz + n * D, d0, D, gr[it]);
+        if (g_hw > 0) load_slice_nchw<TG, V>(gz, n, g_hw, d0, D, gr[it]);   // upstream gradient in the caller's NCHW layout
+        else load_slice<TG, V>(gz + n * D, d0, D, gr[it]);
       } else {
 #pragma unroll
         for (int i = 0; i < V; ++i) yr[it][i] = wr[it][i] = gr[it][i] = 0.f;
@@ -323,7 +344,10 @@ __global__ void __launch_bounds__(256, 4) quantize_backward_kernel(
 #pragma unroll
     for (int it = 0; it < NV; ++it) {
       const int d0 = (it * G + lane) * V;
-      if (valid && d0 < D) store_slice<TX, V>(gx + n * D, d0, D, gr[it]);
+      if (valid && d0 < D) {
+        if (g_hw > 0) store_slice_nchw<TX, V>(gx, n, g_hw, d0, D, gr[it]);
+        else store_slice<TX, V>(gx + n * D, d0, D, gr[it]);
+      }
     }
   }
 }
@@ -414,8 +438,9 @@ int64_t vqb_loss_partials_count(void) { return 2 * kMaxPartials; }
 
 int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D, int normalize_x, const float* W, int64_t K,
                         const int64_t* quant, const unsigned long long* keys, int64_t key_index_offset,
-                        int64_t* quant_out, float* x_norm_out, float* z_out, int want_norm, float* mse4,
+                        int64_t* quant_out, float* x_norm_out, float* z_out, int64_t z_hw, int want_norm, float* mse4,
                         float* partials, unsigned int* ticket, void* stream) {
+  VQB_REQUIRE(z_hw >= 0 && (z_hw == 0 || N % z_hw == 0), "vqb_gather_ste_loss: z_hw must divide N (tokens = images x h*w)");
   VQB_REQUIRE(x && W && z_out && mse4 && partials && ticket, "vqb_gather_ste_loss: null pointer");
   VQB_REQUIRE((quant != nullptr) != (keys != nullptr), "vqb_gather_ste_loss: pass exactly one of quant / keys");
   VQB_REQUIRE(N >= 1 && D >= 1 && K >= 1, "vqb_gather_ste_loss: bad shape N=%lld D=%d K=%lld", (long long)N, D,
@@ -428,12 +453,12 @@ int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D, int normal
   bool launched = false;
   if (x_dtype == VQB_F32) {
     VQB_DISPATCH_GEOM((launch_pdl(quantize_forward_kernel<float, G, V, NV>, blocks, 256, 0, st,
-        (const float*)x, N, D, normalize_x, W, K, quant, keys, key_index_offset, quant_out, x_norm_out, z_out,
+        (const float*)x, N, D, normalize_x, W, K, quant, keys, key_index_offset, quant_out, x_norm_out, z_out, z_hw,
         want_norm, mse4, partials, ticket)))
   } else if (x_dtype == VQB_BF16) {
     VQB_DISPATCH_GEOM((launch_pdl(quantize_forward_kernel<__nv_bfloat16, G, V, NV>, blocks, 256, 0, st,
         (const __nv_bfloat16*)x, N, D, normalize_x, W, K, quant, keys, key_index_offset, quant_out, x_norm_out, z_out,
-        want_norm, mse4, partials, ticket)))
+        z_hw, want_norm, mse4, partials, ticket)))
   }
   VQB_REQUIRE(launched, "vqb_gather_ste_loss: unsupported dtype/geometry");
   VQB_LAUNCH_OK();
@@ -442,7 +467,9 @@ int vqb_gather_ste_loss(const void* x, int x_dtype, int64_t N, int D, int normal
 
 int vqb_quantize_backward(const void* gz, int g_dtype, const void* x, int x_dtype, int normalize_x, const float* W, int64_t K,
                           const int64_t* quant, int64_t N, int D, const float* g_cb, const float* g_cm,
-                          const float* g_cbn, const float* g_cmn, int want_norm, void* gx, float* gW, void* stream) {
+                          const float* g_cbn, const float* g_cmn, int want_norm, void* gx, float* gW, int64_t g_hw,
+                          void* stream) {
+  VQB_REQUIRE(g_hw >= 0 && (g_hw == 0 || N % g_hw == 0), "vqb_quantize_backward: g_hw must divide N");
   VQB_REQUIRE(gz && x && W && quant && gx, "vqb_quantize_backward: null pointer");
   VQB_REQUIRE(N >= 1 && D >= 1 && K >= 1, "vqb_quantize_backward: bad shape");
   RowGeom geom;
@@ -452,15 +479,15 @@ int vqb_quantize_backward(const void* gz, int g_dtype, const void* x, int x_dtyp
   bool launched = false;
   if (x_dtype == VQB_F32 && g_dtype == VQB_F32) {
     VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<float, float, G, V, NV>, blocks, 256, 0, st,
-        (const float*)gz, (const float*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm, (float*)gx, gW)))
+        (const float*)gz, (const float*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm, (float*)gx, gW, g_hw)))
   } else if (x_dtype == VQB_BF16 && g_dtype == VQB_F32) {
     VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<__nv_bfloat16, float, G, V, NV>, blocks, 256, 0, st,
         (const float*)gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn, want_norm,
-        (__nv_bfloat16*)gx, gW)))
+        (__nv_bfloat16*)gx, gW, g_hw)))
   } else if (x_dtype == VQB_BF16 && g_dtype == VQB_BF16) {   // bf16 upstream gradient (autocast training): read as is
     VQB_DISPATCH_GEOM((launch_pdl(quantize_backward_kernel<__nv_bfloat16, __nv_bfloat16, G, V, NV>, blocks, 256, 0, st,
         (const __nv_bfloat16*)gz, (const __nv_bfloat16*)x, normalize_x, W, K, quant, N, D, g_cb, g_cm, g_cbn, g_cmn,
-        want_norm, (__nv_bfloat16*)gx, gW)))
+        want_norm, (__nv_bfloat16*)gx, gW, g_hw)))
   }
   VQB_REQUIRE(launched, "vqb_quantize_backward: unsupported dtype/geometry");
   VQB_LAUNCH_OK();

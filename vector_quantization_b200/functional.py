@@ -287,11 +287,17 @@ class _QuantizeSTELoss(torch.autograd.Function):
     back as four device scalars (no select_backward / stack kernels between the loss and our backward)."""
 
     @staticmethod
-    def forward(ctx, x, W, index, index_is_keys, key_offset, normalize_x, want_norm, ref):
+    def forward(ctx, x, W, index, index_is_keys, key_offset, normalize_x, want_norm, ref, x_nchw):
+        # x_nchw: the caller's [b, c, h, w] latents of which `x` is the (detached) token-major copy: z is then written
+        # straight into that layout and the backward reads / writes NCHW gradients (no transposes around the kernels)
+        hw = 0 if x_nchw is None else x_nchw.shape[2] * x_nchw.shape[3]
         z, mse4, quant, xn = ops.gather_ste_loss(
             x, W, quant=None if index_is_keys else index, keys=index if index_is_keys else None,
             key_offset=key_offset, normalize_x=normalize_x, want_norm=want_norm, want_quant=index_is_keys,
-            want_xnorm=normalize_x)
+            want_xnorm=normalize_x, z_hw=hw)
+        if x_nchw is not None:
+            z = z.view(x_nchw.shape)
+        ctx.nchw = None if x_nchw is None else tuple(x_nchw.shape)
         if quant is None:
             quant = index
         ctx.save_for_backward(x, quant)
@@ -310,23 +316,27 @@ class _QuantizeSTELoss(torch.autograd.Function):
         W = ctx.codebook.tensor
         normalize_x, want_norm = ctx.cfg
         if gz is None:
-            gz = torch.zeros(x.shape, dtype=torch.float32, device=x.device)
+            gz = torch.zeros(ctx.nchw or x.shape, dtype=torch.float32, device=x.device)
         g4 = [None if g is None else g.contiguous().float() for g in (g0, g1, g2, g3)]
+        hw = 0 if ctx.nchw is None else ctx.nchw[2] * ctx.nchw[3]
+        need_gx = ctx.needs_input_grad[0] or ctx.needs_input_grad[8]
         gx, gW = ops.quantize_backward(gz.contiguous(), x, W, quant, g4, normalize_x=normalize_x,
-                                       want_norm=want_norm, need_gW=ctx.needs_input_grad[1])
-        return (gx if ctx.needs_input_grad[0] else None), gW, None, None, None, None, None, None
+                                       want_norm=want_norm, need_gW=ctx.needs_input_grad[1], g_hw=hw)
+        if ctx.nchw is not None:     # the gradient belongs to the NCHW latents
+            return None, gW, None, None, None, None, None, None, (gx.view(ctx.nchw) if need_gx else None)
+        return (gx if need_gx else None), gW, None, None, None, None, None, None, None
 
 
 def quantize_ste_loss(x: torch.Tensor, W: torch.Tensor, index: torch.Tensor, want_norm: bool, *,
                       index_is_keys: bool = False, key_offset: int = 0, normalize_x: bool = False,
-                      codebook_ref: CodebookRef | None = None):
+                      codebook_ref: CodebookRef | None = None, nchw: torch.Tensor | None = None):
     """One kernel: [x' = F.normalize(x)] -> gather W[q] -> straight-through -> MSE terms.
     -> (z_ste [N,D] fp32: value x' + (W[q] - x'), gradient to x only;
         mse4 = (codebook, commitment, codebook(norm), commitment(norm)) as four 0-dim tensors;
         quant int64 [N] (unpacked from the keys when index_is_keys);  x' (detached; x itself if not normalised))"""
     z, m0, m1, m2, m3, quant, xn = _QuantizeSTELoss.apply(x.contiguous(), W, index, bool(index_is_keys),
                                                           int(key_offset), bool(normalize_x), bool(want_norm),
-                                                          codebook_ref)
+                                                          codebook_ref, nchw)
     return z, (m0, m1, m2, m3), quant, xn
 
 

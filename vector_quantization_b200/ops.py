@@ -315,7 +315,7 @@ def as_operand(x: torch.Tensor) -> Operand | None:
 
 def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, *, quant: torch.Tensor | None = None,
                     keys: torch.Tensor | None = None, key_offset: int = 0, normalize_x: bool = False,
-                    want_norm: bool, want_quant: bool = False, want_xnorm: bool = False):
+                    want_norm: bool, want_quant: bool = False, want_xnorm: bool = False, z_hw: int = 0):
     """Fused gather + STE + loss (+ token normalisation, + key unpack) — see vqb_gather_ste_loss.
     -> (z_ste [N,D] fp32, mse4 [4], quant int64 [N] | None, x_normalised [N,D] fp32 | None)"""
     lib = _lib.load()
@@ -328,13 +328,13 @@ def gather_ste_loss(x: torch.Tensor, W: torch.Tensor, *, quant: torch.Tensor | N
     xn = torch.empty((N, D), dtype=torch.float32, device=x.device) if want_xnorm else None
     partials, ticket = _loss_ws(x.device)
     _call('vqb_gather_ste_loss', lib.vqb_gather_ste_loss, dev, _p(x), _dt(x), N, D, int(normalize_x), _p(W), W.shape[0],
-          _p(quant), _p(keys), key_offset, _p(qo), _p(xn), _p(z), int(want_norm), _p(mse4), _p(partials), _p(ticket),
+          _p(quant), _p(keys), key_offset, _p(qo), _p(xn), _p(z), z_hw, int(want_norm), _p(mse4), _p(partials), _p(ticket),
           _S)
     return z, mse4, qo, xn
 
 
 def quantize_backward(g_z: torch.Tensor, x: torch.Tensor, W: torch.Tensor, quant: torch.Tensor, g4, *,
-                      normalize_x: bool = False, want_norm: bool, need_gW: bool):
+                      normalize_x: bool = False, want_norm: bool, need_gW: bool, g_hw: int = 0):
     """g4: a float32 [4] tensor or a sequence of four 0-dim device tensors / None
     (codebook, commitment, codebook-norm, commitment-norm upstream gradients)."""
     lib = _lib.load()
@@ -349,7 +349,7 @@ def quantize_backward(g_z: torch.Tensor, x: torch.Tensor, W: torch.Tensor, quant
     gW = torch.zeros_like(W) if need_gW else None
     _call('vqb_quantize_backward', lib.vqb_quantize_backward, dev, _p(g_z), _dt(g_z), _p(x), _dt(x), int(normalize_x), _p(W),
           W.shape[0], _p(quant), N, D, _p(g4[0]), _p(g4[1]), _p(g4[2]), _p(g4[3]), int(want_norm), _p(gx), _p(gW),
-          _S)
+          g_hw, _S)
     return gx, gW
 
 

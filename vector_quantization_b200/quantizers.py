@@ -299,6 +299,18 @@ class VectorQuantizer(BaseQuantizer):
             loss = loss + v
         return loss, memo
 
+    def can_fuse_nchw(self) -> bool:
+        """May the caller's NCHW <-> token-major rearranges (models/base.py:124,126-127) be folded into the kernels?
+        Yes when forward() takes the fused path and no callback changes the tokens it is handed in before_encode
+        (NormalizeCallback defers its normalisation into the fused kernels when `lazy_normalize_ok`)."""
+        from .callbacks import BaseCallback, NormalizeCallback
+        hooked = any(self._callbacks.overrides(h) for h in ('before_decode', 'after_decode', 'before_loss', 'after_loss'))
+        known = all(type(c).before_encode is BaseCallback.before_encode or isinstance(c, NormalizeCallback)
+                    for c in self._callbacks)
+        normalizes = any(isinstance(c, NormalizeCallback) for c in self._callbacks)
+        lazy = self._callbacks.lazy_normalize_ok() and not self.wants_distance
+        return not hooked and known and (lazy or not normalizes) and not self.wants_distance
+
     def _forward_template(self, x: torch.Tensor, memo: dict):
         """The reference's unfused template (base.py:173-182 + quantizers.py:110-117) for configurations whose
         callbacks hook decode / loss: every hook point is honoured; each stage is still a kernel of the C-ABI."""
@@ -320,6 +332,7 @@ class VectorQuantizer(BaseQuantizer):
         if any(self._callbacks.overrides(h) for h in ('before_decode', 'after_decode', 'before_loss', 'after_loss')):
             return self._forward_template(x, memo)
         x = _check_tokens(x, self.embedding_dim)
+        nchw = memo.pop('_nchw', None)     # tokenizer.quantize: x is the token-major copy of these [b, c, h, w] latents
         # The packed keys go straight into the fused gather kernel, which also emits memo['quant'] — unless a callback
         # that overrides after_encode needs int64 indices first (VQKDCallback reads the keys itself).
         lazy_unpack = self._callbacks.packed_keys_ok()
@@ -334,8 +347,12 @@ class VectorQuantizer(BaseQuantizer):
         if torch.is_grad_enabled() and (x.requires_grad or W.requires_grad):
             ref = Fq.CodebookRef(W.detach())
             self._pending.add(ref)
+        if nchw is not None:
+            ref = ref or (Fq.CodebookRef(W.detach()) if torch.is_grad_enabled() and nchw.requires_grad else None)
+            if ref is not None:
+                self._pending.add(ref)
         z, mse4, quant, xn = Fq.quantize_ste_loss(x, W, index, self._loss_terms(), index_is_keys=lazy_unpack,
-                                                  normalize_x=normalize_x, codebook_ref=ref)
+                                                  normalize_x=normalize_x, codebook_ref=ref, nchw=nchw)
         memo.update(x=xn if normalize_x else x, quant=quant)
         memo['decode'] = get_memo(memo, 'decode')
         loss_memo = get_memo(memo, 'loss')

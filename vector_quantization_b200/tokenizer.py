@@ -26,6 +26,15 @@ def quantize(quantizer, x: torch.Tensor, memo: dict):
     memo['quantizer'] = the quantizer's memo (+ 'x_shape')."""
     quantizer_memo = get_memo(memo, 'quantizer')
     quantizer_memo['x_shape'] = (b, c, h, w) = tuple(x.shape)
+    if isinstance(quantizer, VectorQuantizer) and quantizer.can_fuse_nchw() and x.is_cuda:
+        # Layout fusion: ONE transposed copy of the latents feeds the assignment, the callbacks and the kernels' token
+        # reads; z is written NCHW by the gather kernel, and the backward reads the NCHW upstream gradient and writes
+        # the NCHW token gradient directly — no transpose after the quantizer, none in the backward.
+        x = x.contiguous()
+        rows = ops.transpose_last2(x.detach().view(b, c, h * w)).view(b * h * w, c)
+        quantizer_memo['_nchw'] = x
+        z, q_loss, memo['quantizer'] = quantizer(rows, quantizer_memo)
+        return z, q_loss, memo
     rows = Fq.nchw_to_rows(x)
     z, q_loss, memo['quantizer'] = quantizer(rows, quantizer_memo)
     return Fq.rows_to_nchw(z, b, c, h, w), q_loss, memo
