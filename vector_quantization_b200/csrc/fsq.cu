@@ -2,6 +2,7 @@
 // pack — one pass, HBM-bound.  Rows are D<=16 scalars (5 or 6 in the shipped configs), so a block
 // stages a contiguous [256 tokens x D] slab through shared memory to keep global traffic coalesced.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -100,6 +101,67 @@ __global__ void __launch_bounds__(kFsqTokens) fsq_forward_kernel(const TX* __res
   }
 }
 
+// Token-per-thread variant WITHOUT the shared-memory slab: a thread reads its own 10-32 byte token with the widest
+// loads the token size allows (the neighbouring lanes' pieces of the same 32-byte sectors are served by L1), so there
+// are no block barriers and every thread keeps several independent loads in flight.
+template <typename T, int DT>
+__device__ __forceinline__ void fsq_load_token(const T* __restrict__ p, float (&v)[DT]) {
+  constexpr int BYTES = DT * (int)sizeof(T);
+  if constexpr (BYTES % 8 == 0) {
+    T tmp[DT];
+#pragma unroll
+    for (int i = 0; i < BYTES / 8; ++i) reinterpret_cast<uint2*>(tmp)[i] = reinterpret_cast<const uint2*>(p)[i];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) v[d] = to_f32<T>(tmp[d]);
+  } else if constexpr (BYTES % 4 == 0) {
+    T tmp[DT];
+#pragma unroll
+    for (int i = 0; i < BYTES / 4; ++i) reinterpret_cast<uint32_t*>(tmp)[i] = reinterpret_cast<const uint32_t*>(p)[i];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) v[d] = to_f32<T>(tmp[d]);
+  } else {
+#pragma unroll
+    for (int d = 0; d < DT; ++d) v[d] = to_f32<T>(p[d]);
+  }
+}
+template <typename T, int DT>
+__device__ __forceinline__ void fsq_store_token(T* __restrict__ p, const float (&v)[DT]) {
+  constexpr int BYTES = DT * (int)sizeof(T);
+  T tmp[DT];
+#pragma unroll
+  for (int d = 0; d < DT; ++d) tmp[d] = from_f32<T>(v[d]);
+  if constexpr (BYTES % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < BYTES / 8; ++i) reinterpret_cast<uint2*>(p)[i] = reinterpret_cast<const uint2*>(tmp)[i];
+  } else if constexpr (BYTES % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < BYTES / 4; ++i) reinterpret_cast<uint32_t*>(p)[i] = reinterpret_cast<const uint32_t*>(tmp)[i];
+  } else {
+#pragma unroll
+    for (int d = 0; d < DT; ++d) p[d] = tmp[d];
+  }
+}
+
+template <typename TX, typename TO, int DT>
+__global__ void __launch_bounds__(256) fsq_forward_direct_kernel(const TX* __restrict__ x, int64_t N, const vqb_fsq_params p,
+                                                                 TO* __restrict__ zq, int32_t* __restrict__ index) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    float v[DT], out[DT];
+    fsq_load_token<TX, DT>(x + n * DT, v);
+    int code = 0;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      float z = __fsub_rn(__fmul_rn(fsq_tanh(__fadd_rn(v[d], p.shift[d])), p.max_[d]), p.odd[d]);
+      z = z * 0.5f;
+      const float r = rintf(z);
+      out[d] = fsq_div(r, p.half[d]);
+      code += ((int)r + (int)p.half[d]) * p.cumprod[d];
+    }
+    fsq_store_token<TO, DT>(zq + n * DT, out);
+    if (index) index[n] = code;
+  }
+}
+
 template <typename TG, typename TX>
 __global__ void __launch_bounds__(256) fsq_backward_kernel(const TG* __restrict__ gz, const TX* __restrict__ x,
                                                            int64_t total, const vqb_fsq_params p,
@@ -146,8 +208,20 @@ int vqb_fsq_forward(const void* x, int x_dtype, int64_t N, const vqb_fsq_params*
   int64_t blocks64 = (N + kFsqTokens - 1) / kFsqTokens;
   const int blocks = (int)(blocks64 < (int64_t)sm_count() * 8 ? blocks64 : (int64_t)sm_count() * 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define VQB_FSQ_LAUNCH(TX, TO, DT)                                                                         \
+  static int direct = -1;     // VQB_FSQ_DIRECT=0: the shared-memory slab kernel (developer A/B switch)
+  if (direct < 0) {
+    const char* e = getenv("VQB_FSQ_DIRECT");
+    direct = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+#define VQB_FSQ_SLAB(TX, TO, DT)                                                                            \
   fsq_forward_kernel<TX, TO, DT><<<blocks, kFsqTokens, 0, st>>>((const TX*)x, N, *p, (TO*)zq, index)
+#define VQB_FSQ_LAUNCH(TX, TO, DT)                                                                          \
+  do {                                                                                                      \
+    if (direct)                                                                                             \
+      fsq_forward_direct_kernel<TX, TO, DT><<<blocks, 256, 0, st>>>((const TX*)x, N, *p, (TO*)zq, index);   \
+    else                                                                                                    \
+      VQB_FSQ_SLAB(TX, TO, DT);                                                                             \
+  } while (0)
 #define VQB_FSQ_D(TX, TO)                                        \
   switch (p->D) {                                                \
     case 3: VQB_FSQ_LAUNCH(TX, TO, 3); break;                    \
@@ -156,7 +230,7 @@ int vqb_fsq_forward(const void* x, int x_dtype, int64_t N, const vqb_fsq_params*
     case 6: VQB_FSQ_LAUNCH(TX, TO, 6); break;                    \
     case 7: VQB_FSQ_LAUNCH(TX, TO, 7); break;                    \
     case 8: VQB_FSQ_LAUNCH(TX, TO, 8); break;                    \
-    default: VQB_FSQ_LAUNCH(TX, TO, 0); break;                   \
+    default: VQB_FSQ_SLAB(TX, TO, 0); break;                     \
   }
   if (x_dtype == VQB_F32 && out_dtype == VQB_F32) { VQB_FSQ_D(float, float) }
   else if (x_dtype == VQB_BF16 && out_dtype == VQB_BF16) { VQB_FSQ_D(__nv_bfloat16, __nv_bfloat16) }
@@ -164,6 +238,7 @@ int vqb_fsq_forward(const void* x, int x_dtype, int64_t N, const vqb_fsq_params*
   else { VQB_REQUIRE(false, "vqb_fsq_forward: unsupported dtype combination"); }
 #undef VQB_FSQ_D
 #undef VQB_FSQ_LAUNCH
+#undef VQB_FSQ_SLAB
   VQB_LAUNCH_OK();
   return VQB_OK;
 }
