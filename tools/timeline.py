@@ -18,13 +18,13 @@ for _ in range(3):
     ops.assign(a, b, keys, l2=False)
 torch.cuda.synchronize()
 lib = _lib.load()
-buf = (ctypes.c_longlong * (3 * 64 * 4))()
+buf = (ctypes.c_longlong * (3 * 64 * 8))()
 lib.vqb_debug_timeline.argtypes = [ctypes.c_void_p]
 print('rc', lib.vqb_debug_timeline(buf))
-ts = torch.tensor(list(buf)).view(3, 64, 4)
+ts = torch.tensor(list(buf)).view(3, 64, 8)
 t0 = int(ts[ts > 0].min())
 rel = (ts - t0).clamp_min(-1)
 print('kernel start', int(rel[0, 63, 3]))
-print('tile | producer: wait_start got_empty tma_issued | mma: start got_tmem_empty got_full committed | epi: got_full tile_done flushed')
+print('tile | producer: wait_start got_empty tma_issued | mma: start got_tmem_empty got_full loop_end elected mma_issued commit1 commit2 | epi: got_full tile_done flushed')
 for t in range(0, 64):
-    print(t, rel[0, t, :3].tolist(), rel[1, t].tolist(), rel[2, t].tolist())
+    print(t, rel[0, t, :3].tolist(), rel[1, t].tolist(), rel[2, t, :4].tolist())

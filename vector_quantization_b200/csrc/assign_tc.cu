@@ -25,8 +25,18 @@ constexpr int BN = 256;           // codes per tile (UMMA N)
 constexpr int UMMA_K = 16;        // bf16
 constexpr int kMaxTerms = 6;
 constexpr uint32_t kTmemCols = 512;  // two 256-column accumulators
+#ifndef VQB_ONE_COMMIT   // whole-tile mode: one tcgen05.commit per tile (developer A/B switch)
+#define VQB_ONE_COMMIT 1
+#endif
 constexpr int kEpilogueWarps = 8;
-constexpr int kThreads = 64 + kEpilogueWarps * 32;
+#ifndef VQB_EARLY_RELEASE
+#define VQB_EARLY_RELEASE 0
+#endif
+#ifndef VQB_ISSUERS       // whole-tile mode: MMA-issuing warps (tile t is issued by warp t % VQB_ISSUERS; developer A/B switch)
+#define VQB_ISSUERS 2
+#endif
+constexpr int kIssuer2Warp = 2 + kEpilogueWarps;              // the second issuer sits after the epilogue warps
+constexpr int kThreads = 64 + kEpilogueWarps * 32 + (VQB_ISSUERS > 1 ? 32 : 0);
 constexpr uint32_t kStashBytes = kEpilogueWarps * 4096;  // winning-chunk stash: [warp][8 float4][32 lanes]
 constexpr uint32_t kShareBytes = kEpilogueWarps * 32 * 16;  // per-row running best published to the other column half
 
@@ -193,7 +203,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // epilogue helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef VQB_TIMELINE  // developer build: clock64 timeline of the first tiles of CTA 0 (tools/timeline.py)
-__device__ long long g_ts[3][64][4];
+__device__ long long g_ts[3][64][8];
 #define TS(role, tile, ev) do { if (blockIdx.x == 0 && (tile) < 64) g_ts[role][tile][ev] = clock64(); } while (0)
 #else
 #define TS(role, tile, ev) do { } while (0)
@@ -333,27 +343,57 @@ __device__ __forceinline__ void tile_argmax(uint32_t taddr, uint32_t side_saddr,
     const int left = b_rows - (int)(gcol0 + 32 * c);
     return left >= 32 ? 32 : (left < 0 ? 0 : left);
   };
+#if defined(VQB_ABLATE) && VQB_ABLATE == 1   // developer ablation: no TMEM reads, no scan (MMA / barrier chain alone)
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tmem_empty_bar);
+  return;
+#endif
   uint32_t rc[32], rd[32];
+#if VQB_EARLY_RELEASE   // all four loads up front, accumulator handed back before any reduction (developer A/B switch)
+  tmem_ld32(taddr, ra);
+  tmem_ld32(taddr + 32, rb);
+  tmem_ld32(taddr + 64, rc);
+  tmem_ld32(taddr + 96, rd);
+  tmem_ld_wait(ra);
+  tmem_ld_wait(rb);
+  tmem_ld_wait(rc);
+  tmem_ld_wait(rd);
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tmem_empty_bar);
+  pair_argmax<SIDE, MASK, CERT>(ra, rb, side_saddr, gcol0, nv(0), nv(1), stash_saddr, best, best_col, second);
+  pair_argmax<SIDE, MASK, CERT>(rc, rd, side_saddr + 256, gcol0 + 64, nv(2), nv(3), stash_saddr, best, best_col, second);
+  return;
+#endif
   tmem_ld32(taddr, ra);
   tmem_ld32(taddr + 32, rb);
   tmem_ld_wait(ra);
   tmem_ld_wait(rb);
   tmem_ld32(taddr + 64, rc);
   tmem_ld32(taddr + 96, rd);
+#if defined(VQB_ABLATE) && VQB_ABLATE == 2   // developer ablation: TMEM reads but no scan
+  best = fmaxf(best, __uint_as_float(ra[0] ^ rb[0]));
+#else
   pair_argmax<SIDE, MASK, CERT>(ra, rb, side_saddr, gcol0, nv(0), nv(1), stash_saddr, best, best_col, second);
+#endif
   tmem_ld_wait(rc);
   tmem_ld_wait(rd);
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(tmem_empty_bar);  // every load of this warp is in registers: buffer is free
+#if defined(VQB_ABLATE) && VQB_ABLATE == 2
+  best = fmaxf(best, __uint_as_float(rc[0] ^ rd[0]));
+#else
   pair_argmax<SIDE, MASK, CERT>(rc, rd, side_saddr + 256, gcol0 + 64, nv(2), nv(3), stash_saddr, best, best_col, second);
+#endif
 }
 
 // Epilogue role: 8 warps drain every tile; warp%4 selects the TMEM lane quarter (hardware rule) and
 // (warp-2)/4 the 128-column half of the accumulator.
 template <int SIDE, bool CERT>
 __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_base, uint8_t* stash_smem,
-                                              uint8_t* share_smem, float* side_smem, uint64_t* tmem_full, uint64_t* tmem_empty, int t0,
+                                              uint8_t* share_smem, float* side_smem, uint64_t* acc_bar, int n_acc, uint64_t* tmem_empty, int t0,
                                               int t1, int b_tiles, int a_rows, int b_rows,
                                               const float* __restrict__ b_half_sqnorm, uint32_t b_index_offset,
                                               unsigned long long* __restrict__ keys,
@@ -370,7 +410,10 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
   float best = -INFINITY, second = -INFINITY;
   uint32_t best_col = 0xffffffffu;
   int at = t0 / b_tiles, bt = t0 - at * b_tiles;
-  uint32_t par0 = 0, par1 = 0;                 // per-accumulator phase parity
+  // "accumulator complete" barriers: tmem_full[2] in the k-blocked mode; in the whole-tile mode the pipeline stage's
+  // own `empty` barrier (ONE tcgen05.commit per tile tells the producer and the epilogue): a cycle of n_acc barriers
+  int acc_idx = 0;
+  uint32_t acc_par = 0;
   // The two warps that own the two column halves of a row exchange their running best through shared memory
   // (no synchronisation: a stale entry is still a real score of the row).  A partner value from an EARLIER code
   // tile that beats mine makes my current candidate irrelevant and raises my threshold, which halves the number
@@ -405,7 +448,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
           best_col = 0xffffffffu;              // mine is out of the race until a later chunk beats it
         }
       }
-      mbar_wait(tmem_full + buf, buf ? par1 : par0);
+      mbar_wait(acc_bar + acc_idx, acc_par);
       if (warp == 2 && lane == 0) TS(2, t - t0, 0);
       tc_fence_after();
       const uint32_t taddr = taddr0 + buf * BN;
@@ -420,7 +463,7 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_share), "r"(__float_as_uint(best)), "r"((uint32_t)at),
                      "r"((uint32_t)bt), "r"(0u)
                      : "memory");
-      if (buf) par1 ^= 1; else par0 ^= 1;
+      if (++acc_idx == n_acc) { acc_idx = 0; acc_par ^= 1; }
     }
     if (++bt == b_tiles || t + 1 == t1) {       // row tile finished (or this CTA's range ends): publish
       const int row = at * BM + row_in_tile;
@@ -455,6 +498,23 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
 // WHOLE = true : one pipeline stage holds every operand plane of one (row tile, code tile) work item
 //                (Dp == BK <= 64): one barrier wait, all term MMAs back to back, two commits per tile.
 // WHOLE = false: classic k-blocked ring, one stage = one BK-wide slab of one plane pair (large D).
+// MMA issue sequence of one whole-K tile for a term table known at compile time (NT terms, bit t of SCALE set when
+// term t starts with the scale-input-d instruction).
+template <int BK, int NT, uint32_t SCALE>
+__device__ __forceinline__ void issue_terms(uint32_t d_tmem, uint64_t desc_hi, const uint32_t* a_lo, const uint32_t* b_lo,
+                                            uint32_t a_add, uint32_t b_add, uint32_t idesc) {
+#pragma unroll
+  for (int term = 0; term < NT; ++term) {
+    const uint64_t adesc = desc_hi | (uint64_t)(a_lo[term] + a_add);
+    const uint64_t bdesc = desc_hi | (uint64_t)(b_lo[term] + b_add);
+#pragma unroll
+    for (int k = 0; k < BK / UMMA_K; ++k) {
+      if (k == 0 && ((SCALE >> term) & 1u)) umma_f16_scaled(d_tmem, adesc, bdesc, idesc);
+      else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (term | k) != 0);
+    }
+  }
+}
+
 template <int BK, bool WHOLE>
 __global__ void __launch_bounds__(kThreads, 1)
 assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -481,7 +541,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* a_full = tmem_empty + 2;
   uint64_t* a_empty = a_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 2);
+  uint64_t* a_ready = a_empty + 2;   // resident A tile converted to fp16 (a_convert mode)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 2);
 
   // PDL: barrier init / TMEM allocation below overlap the tail of the preceding launch (the operand packs);
   // global memory is first touched after pdl_wait().
@@ -500,12 +561,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(tmem_full + i, 1);
       mbar_init(tmem_empty + i, kEpilogueWarps);
       mbar_init(a_full + i, 1);
-      mbar_init(a_empty + i, 1);
+      mbar_init(a_empty + i, WHOLE ? VQB_ISSUERS : 1);   // every issuer releases every row tile
+      mbar_init(a_ready + i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
-  if (warp >= 2) {  // epilogue: invalidate this thread's slot of the running-best exchange (tag = no row tile)
+  if (warp >= 2 && warp < 2 + kEpilogueWarps) {  // epilogue: invalidate this thread's slot of the running-best exchange (tag = no row tile)
     const uint32_t slot = smem_u32(share_smem) + ((uint32_t)(warp - 2) * 32 + (uint32_t)lane) * 16;
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(0xff800000u), "r"(0xffffffffu), "r"(0u), "r"(0u) : "memory");
   }
@@ -526,144 +588,218 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer (warp-converged, one elected lane issues) =====================
-    {
+    if constexpr (WHOLE) {
+      // The row tile's A planes are RESIDENT in one of two slots and loaded one row tile AHEAD (a few code tiles into
+      // row tile r the slot of r-1 is free again), so neither the TMA latency nor the bf16 -> fp16 conversion of
+      // zero-copy tokens (done here, by this warp, off the MMA thread's critical path) is exposed at a row-tile change.
+      const int n_local = (int)(t1 - t0), b_tiles_i = (int)b_tiles;
+      const int at0 = (int)(t0 / b_tiles);
+      const int rt_count = n_local > 0 ? (int)((t1 - 1) / b_tiles) - at0 + 1 : 0;   // row tiles this CTA touches
+      const int ahead = nstages + 1 < b_tiles_i - 1 ? nstages + 1 : b_tiles_i - 1;  // code tile at which A(r+1) is fetched
+      const int ahead_cvt = ahead + 3 < b_tiles_i - 1 ? ahead + 3 : b_tiles_i - 1;  // ... and converted
+      int bt = (int)(t0 - (int64_t)at0 * b_tiles), rt = 0, a_loaded = 0, a_converted = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_a = [&]() {
+        const int slot = a_loaded & 1;
+        mbar_wait(a_empty + slot, (uint32_t)((a_loaded >> 1) & 1) ^ 1);   // MMAs of the slot's previous row tile retired
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full + slot, a_slot_bytes);
+          for (int p = 0; p < pa; ++p)
+            tma_load_2d(smem_a + slot * a_slot_bytes + p * kABytes, &tmap_a, a_full + slot, 0,
+                        (int)(p * a_rows_pad) + (at0 + a_loaded) * BM);
+        }
+        __syncwarp();
+        ++a_loaded;
+      };
+      auto convert_a = [&]() {
+        const int slot = a_converted & 1;
+        mbar_wait(a_full + slot, (uint32_t)((a_converted >> 1) & 1));
+        convert_slot_bf16_to_f16(smem_u32(smem_a) + (uint32_t)slot * a_slot_bytes, a_slot_bytes, lane);
+        if (lane == 0) mbar_arrive(a_ready + slot);
+        ++a_converted;
+      };
+      if (n_local > 0) load_a();
+      for (int local = 0; local < n_local; ++local) {
+        TS(0, local, 0);
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        TS(0, local, 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
+          uint8_t* sb = smem + (size_t)stage * stage_bytes;
+          for (int p = 0; p < pb; ++p)
+            tma_load_2d(sb + p * kBBytes, &tmap_b, full_bar + stage, 0, (int)(p * b_rows_pad) + bt * BN);
+        }
+        __syncwarp();
+        TS(0, local, 2);
+        if (a_loaded == rt + 1 && a_loaded < rt_count && bt >= ahead) load_a();
+        if (a_convert && a_converted < a_loaded && (a_converted == rt || bt >= ahead_cvt)) convert_a();
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+        if (++bt == b_tiles_i) { bt = 0; ++rt; }
+      }
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       int64_t at = t0 / b_tiles, bt = t0 - at * b_tiles;
-      int64_t cur_at = -1, a_count = 0;
       for (int64_t t = t0; t < t1; ++t) {
         const int a_row = (int)(at * BM), b_row = (int)(bt * BN);
-        if constexpr (WHOLE) {
-          if (at != cur_at) {  // new row tile: load its A planes into the next resident slot
-            const int slot = (int)(a_count & 1);
-            mbar_wait(a_empty + slot, (uint32_t)((a_count >> 1) & 1) ^ 1);
+#pragma unroll 1
+        for (int term = 0; term < terms.n; ++term) {
+          const int arow = (int)(terms.a[term] * a_rows_pad) + a_row, brow = (int)(terms.b[term] * b_rows_pad) + b_row;
+#pragma unroll 1
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(a_full + slot, a_slot_bytes);
-              for (int p = 0; p < pa; ++p)
-                tma_load_2d(smem_a + slot * a_slot_bytes + p * kABytes, &tmap_a, a_full + slot, 0,
-                            (int)(p * a_rows_pad) + a_row);
+              mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
+              uint8_t* sa = smem + (size_t)stage * stage_bytes;
+              tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, arow);
+              tma_load_2d(sa + kABytes, &tmap_b, full_bar + stage, kb * BK, brow);
             }
             __syncwarp();
-            ++a_count;
-            cur_at = at;
-          }
-          TS(0, t - t0, 0);
-          mbar_wait(empty_bar + stage, phase ^ 1);
-          TS(0, t - t0, 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
-            uint8_t* sb = smem + (size_t)stage * stage_bytes;
-            for (int p = 0; p < pb; ++p)
-              tma_load_2d(sb + p * kBBytes, &tmap_b, full_bar + stage, 0, (int)(p * b_rows_pad) + b_row);
-          }
-          __syncwarp();
-          TS(0, t - t0, 2);
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
-        } else {
-#pragma unroll 1
-          for (int term = 0; term < terms.n; ++term) {
-            const int arow = (int)(terms.a[term] * a_rows_pad) + a_row, brow = (int)(terms.b[term] * b_rows_pad) + b_row;
-#pragma unroll 1
-            for (int kb = 0; kb < kblocks; ++kb) {
-              mbar_wait(empty_bar + stage, phase ^ 1);
-              if (elect_one()) {
-                mbar_arrive_expect_tx(full_bar + stage, stage_bytes);
-                uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, arow);
-                tma_load_2d(sa + kABytes, &tmap_b, full_bar + stage, kb * BK, brow);
-              }
-              __syncwarp();
-              if (++stage == nstages) { stage = 0; phase ^= 1; }
-            }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
         if (++bt == b_tiles) { bt = 0; ++at; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-converged, one elected lane issues) =====================
-    {
+  } else if (warp == 1 || warp == kIssuer2Warp) {
+    // ===================== MMA issuer =====================
+    if constexpr (WHOLE) {
+      // This warp's serial instruction stream sets the tile period for D <= 64 (profiles/r2_notes.md section 10), so it
+      // is kept to the two barrier tests (issued back to back), the MMAs with descriptors prepared outside the loop,
+      // and ONE commit: the stage's `empty` barrier tells the producer "slot reusable" and the epilogue "accumulator
+      // complete" at once.  (Running the loop on ONE thread instead of warp-converged + elected issue was 50 % slower:
+      // divergent code cannot use the uniform datapath the tcgen05 operands live in.)
+      {
+        const uint32_t smem_base = smem_u32(smem);
+        const uint64_t desc_hi = make_smem_desc<BK>(0);
+        uint32_t a_lo[kMaxTerms], b_lo[kMaxTerms];
+        uint32_t scale_mask = 0;
+#pragma unroll
+        for (int term = 0; term < kMaxTerms; ++term) {
+          a_lo[term] = ((smem_u32(smem_a) + (uint32_t)terms.a[term] * kABytes) & 0x3ffff) >> 4;
+          b_lo[term] = ((smem_base + (uint32_t)terms.b[term] * kBBytes) & 0x3ffff) >> 4;
+          scale_mask |= (terms.scale[term] != 0 ? 1u : 0u) << term;
+        }
+        // opaque to the optimiser, or it re-reads the table from the constant bank inside the loop
+        asm volatile("" : "+r"(scale_mask));
+        const int n_terms = terms.n;
+        const uint32_t a_slot_add = a_slot_bytes >> 4, stage_add = stage_bytes >> 4;
+        const int n_local = (int)(t1 - t0), b_tiles_i = (int)b_tiles;
+        uint64_t* const a_bar = a_convert ? a_ready : a_full;
+        // Tile `local` belongs to issuer local % VQB_ISSUERS: with two issuers each owns one TMEM accumulator, and the
+        // serial barrier-test / issue / commit stream of one tile overlaps the other issuer's.
+        const int me = warp == 1 ? 0 : 1;
+        const int at0 = (int)(t0 / b_tiles);
+        const int rt_count = n_local > 0 ? (int)((t1 - 1) / b_tiles) - at0 + 1 : 0;   // row tiles this CTA touches
+        int bt = (int)(t0 - (int64_t)at0 * b_tiles) + me, rt = 0, stage = me, released = 0, cur_rt = -1;
+        uint32_t phase = 0, a_add = 0;
+        while (bt >= b_tiles_i) { bt -= b_tiles_i; ++rt; }
+        while (stage >= nstages) { stage -= nstages; phase ^= 1; }
+        auto release_until = [&](int upto) {   // every issuer arrives once per row tile, in order (a_empty counts VQB_ISSUERS)
+          while (released < upto) {
+            if (elect_one()) umma_commit(a_empty + (released & 1));   // after this thread's MMAs on that slot (if any)
+            __syncwarp();
+            ++released;
+          }
+        };
+        for (int local = me; local < n_local; local += VQB_ISSUERS) {
+          const uint32_t buf = (uint32_t)local & 1u;
+          const uint32_t e_par = (((uint32_t)local >> 1) & 1u) ^ 1u;
+          TS(1, local, 0);
+          const bool e_ok = mbar_try_wait(tmem_empty + buf, e_par);   // epilogue has drained this accumulator
+          const bool f_ok = mbar_try_wait(full_bar + stage, phase);   // the code tile's planes have landed
+          if (rt != cur_rt) {           // my first tile of a row tile: release the ones I am done with, wait for its A planes
+            release_until(rt);
+            mbar_wait(a_bar + (rt & 1), (uint32_t)((rt >> 1) & 1));
+            a_add = (uint32_t)(rt & 1) * a_slot_add;
+            cur_rt = rt;
+          }
+          if (!e_ok) mbar_wait(tmem_empty + buf, e_par);
+          TS(1, local, 1);
+          if (!f_ok) mbar_wait(full_bar + stage, phase);
+          TS(1, local, 2);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          const uint32_t b_add = (uint32_t)stage * stage_add;
+          if (elect_one()) {
+            // straight-line issue for the two common tables (fp16 pair: lo' term, then the 2^-11-scaled hi term; one
+            // plane): with the term count and the scale flags known at compile time the sequence is two adds per MMA
+            if (n_terms == 2 && scale_mask == 2u) {
+              issue_terms<BK, 2, 2u>(d_tmem, desc_hi, a_lo, b_lo, a_add, b_add, idesc);
+            } else if (n_terms == 1) {
+              issue_terms<BK, 1, 0u>(d_tmem, desc_hi, a_lo, b_lo, a_add, b_add, idesc);
+            } else {
+#pragma unroll
+              for (int term = 0; term < kMaxTerms; ++term) {
+                if (term < n_terms) {
+                  const uint64_t adesc = desc_hi | (uint64_t)(a_lo[term] + a_add);
+                  const uint64_t bdesc = desc_hi | (uint64_t)(b_lo[term] + b_add);
+#pragma unroll
+                  for (int k = 0; k < BK / UMMA_K; ++k) {
+                    if (k == 0 && ((scale_mask >> term) & 1u)) umma_f16_scaled(d_tmem, adesc, bdesc, idesc);
+                    else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (term | k) != 0);
+                  }
+                }
+              }
+            }
+            TS(1, local, 5);
+            umma_commit(empty_bar + stage);  // these MMAs retired: stage reusable AND (one-commit mode) accumulator complete
+            TS(1, local, 6);
+#if !VQB_ONE_COMMIT
+            umma_commit(tmem_full + buf);
+#endif
+            TS(1, local, 7);
+          }
+          __syncwarp();
+          bt += VQB_ISSUERS;
+          while (bt >= b_tiles_i) { bt -= b_tiles_i; ++rt; }
+          stage += VQB_ISSUERS;
+          while (stage >= nstages) { stage -= nstages; phase ^= 1; }
+          TS(1, local, 3);
+        }
+        release_until(rt_count);
+      }
+    } else if (warp == 1) {
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int64_t local = 0;
-      int64_t a_count_m = 0;
-      const int b_tiles_i = (int)b_tiles;
-      int bt_m = (int)(t0 % b_tiles);
       for (int64_t t = t0; t < t1; ++t, ++local) {
         const int buf = (int)(local & 1);
         const uint32_t use = (uint32_t)(local >> 1);
-        TS(1, local, 0);
         mbar_wait(tmem_empty + buf, (use & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
-        if constexpr (WHOLE) {
-          if (bt_m == 0 || t == t0) {  // first tile of a row tile in this CTA's range: its A planes must have landed
-            mbar_wait(a_full + (a_count_m & 1), (uint32_t)((a_count_m >> 1) & 1));
-            // zero-copy bf16 tokens against fp16 codebook planes: convert the resident A tile once per row tile
-            if (a_convert)
-              convert_slot_bf16_to_f16(smem_u32(smem_a) + (uint32_t)(a_count_m & 1) * a_slot_bytes, a_slot_bytes, lane);
-            ++a_count_m;
-          }
-          const int slot = (int)((a_count_m - 1) & 1);
-          const bool last_of_row_tile = (bt_m == b_tiles_i - 1) || (t + 1 == t1);
-          TS(1, local, 1);
+        const int nv = terms.n * kblocks;
+        int term = 0, kb = 0;
+#pragma unroll 1
+        for (int v = 0; v < nv; ++v) {
+          const bool rescale = kb == 0 && terms.scale[term] != 0;  // first MMA of a term that follows the 2^11-scaled ones
           mbar_wait(full_bar + stage, phase);
-          TS(1, local, 2);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a) + (uint32_t)slot * a_slot_bytes;
-          const uint32_t sb = smem_base + (uint32_t)stage * stage_bytes;
+          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
           if (elect_one()) {
+            const uint64_t adesc = make_smem_desc<BK>(sa), bdesc = make_smem_desc<BK>(sa + kABytes);
 #pragma unroll
-            for (int term = 0; term < kMaxTerms; ++term) {
-              if (term < terms.n) {
-                const uint64_t adesc = make_smem_desc<BK>(sa + (uint32_t)terms.a[term] * kABytes);
-                const uint64_t bdesc = make_smem_desc<BK>(sb + (uint32_t)terms.b[term] * kBBytes);
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                  if (k == 0 && terms.scale[term]) umma_f16_scaled(d_tmem, adesc, bdesc, idesc);
-                  else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (term | k) != 0);
-                }
-              }
+            for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+              if (k == 0 && rescale) umma_f16_scaled(d_tmem, adesc, bdesc, idesc);
+              else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (v | k) != 0);
             }
-            umma_commit(empty_bar + stage);  // smem slot reusable once these MMAs retire
-            umma_commit(tmem_full + buf);    // accumulator complete -> epilogue
-            if (last_of_row_tile) umma_commit(a_empty + slot);  // resident A planes no longer needed
+            umma_commit(empty_bar + stage);
+            if (v == nv - 1) umma_commit(tmem_full + buf);  // accumulator complete -> epilogue
           }
           __syncwarp();
-          if (++bt_m == b_tiles_i) bt_m = 0;
+          if (++kb == kblocks) { kb = 0; ++term; }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
-        } else {
-          const int nv = terms.n * kblocks;
-          int term = 0, kb = 0;
-#pragma unroll 1
-          for (int v = 0; v < nv; ++v) {
-            const bool rescale = kb == 0 && terms.scale[term] != 0;  // first MMA of a term that follows the 2^11-scaled ones
-            mbar_wait(full_bar + stage, phase);
-            tc_fence_after();
-            const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-            if (elect_one()) {
-              const uint64_t adesc = make_smem_desc<BK>(sa), bdesc = make_smem_desc<BK>(sa + kABytes);
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
-                if (k == 0 && rescale) umma_f16_scaled(d_tmem, adesc, bdesc, idesc);
-                else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (v | k) != 0);
-              }
-              umma_commit(empty_bar + stage);
-              if (v == nv - 1) umma_commit(tmem_full + buf);  // accumulator complete -> epilogue
-            }
-            __syncwarp();
-            if (++kb == kblocks) { kb = 0; ++term; }
-            if (++stage == nstages) { stage = 0; phase ^= 1; }
-          }
         }
-        TS(1, local, 3);
       }
     }
-  } else {
+  } else if (warp < 2 + kEpilogueWarps) {
     // ===================== epilogue: fused arg-max =====================
 #define VQB_EPI(SIDE_, CERT_)                                                                                       \
-  epilogue_loop<SIDE_, CERT_>(warp, lane, tmem_base, stash_smem, share_smem, side_smem, tmem_full, tmem_empty, (int)t0,        \
+  epilogue_loop<SIDE_, CERT_>(warp, lane, tmem_base, stash_smem, share_smem, side_smem, (WHOLE && VQB_ONE_COMMIT) ? empty_bar : tmem_full,           \
+                              (WHOLE && VQB_ONE_COMMIT) ? nstages : 2, tmem_empty, (int)t0,                                  \
                               (int)t1, (int)b_tiles, (int)a_rows, (int)b_rows, b_half_sqnorm, (uint32_t)b_index_offset, keys, \
                               second_keys)
     if (second_keys != nullptr) {   // certified one-term mode (cosine family: no side term, or the column scale)
@@ -786,7 +922,7 @@ static int launch(const void* a_planes, int pa, int64_t a_rows, int64_t a_pad, c
   int nstages = (int)((196608 - kStashBytes - a_resident) / stage_bytes);
   if (nstages > 8) nstages = 8;
   const size_t smem_bytes = 1024 + a_resident + (size_t)nstages * stage_bytes + kStashBytes + kShareBytes + 2 * BN * sizeof(float) +
-                            (2 * nstages + 8) * 8 + 16;
+                            (2 * nstages + 10) * 8 + 16;
   static bool attr_set[64] = {false};  // function attributes are per device
   int dev = 0;
   cudaGetDevice(&dev);
