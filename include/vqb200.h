@@ -149,6 +149,20 @@ int vqb_gather_f32(const float* src, const int* row_list, const int* count, int6
 int vqb_scatter_keys(const unsigned long long* compact_keys, const int* row_list, const int* count, int64_t cap,
                      unsigned long long* keys, void* stream);
 
+/* L2 distance (reference: torch.cdist in L2Distance.forward, vq/algorithms/vq/distances.py:28-35) when the operand
+ * width leaves VQB_L2_FOLD_COLUMNS spare zero columns (Dp - D >= 6; LlamaGen's D = 8 -> Dp = 16): the -0.5|.|^2 side
+ * terms are written INTO the packed exact-bf16 planes, so that the plain contraction over Dp columns already is
+ * <x_i, e_j> - 0.5|e_j|^2 - 0.5|x_i|^2 = -0.5 |x_i - e_j|^2 and vqb_assign runs with side_mode 0 (the per-column
+ * subtraction of side_mode 1 doubles the instruction count of the D <= 64 epilogue).  Columns D..D+2 carry the codes'
+ * term (the codes operand holds the three exact bf16 pieces of -0.5|e|^2, the tokens operand holds 1), columns
+ * D+3..D+5 the tokens' term the other way round; an operand with 3 planes keeps its pieces in one column across the
+ * planes, an operand with fewer planes spreads them over its three columns of plane 0.
+ * role 0: tokens (half_sqnorm may be NULL: the term is constant along the row arg-min), role 1: codes.
+ * Call after vqb_pack_rows on the same stream; both operands of a vqb_assign must be folded, with opposite roles. */
+#define VQB_L2_FOLD_COLUMNS 6
+int vqb_fold_l2_side(void* planes, int n_planes /* 1..3 exact bf16 planes */, int64_t rows, int D,
+                     const float* half_sqnorm, int role, void* stream);
+
 /* out[r] = 1 / max(||x_r||, 1e-12), zero in the padding up to vqb_operand_rows_pad(rows): the side_mode-2 column
  * scale that lets the column arg-min of NearestAnchor use RAW (un-normalised, one exact bf16 plane) tokens. */
 int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D,

@@ -611,3 +611,48 @@ def test_cvq_needy_codes_is_a_superset_of_the_codes_with_nonzero_anchor_weight(d
     mask[listed] = True
     assert mask[needed].all(), 'a code with a non-zero anchor weight is missing from the list'
     assert 0.1 < mask.float().mean() < 0.9
+
+
+@pytest.mark.parametrize('N,K,D,x_dtype,e_dtype', [
+    (3000, 1000, 8, torch.float32, torch.float32),      # 3 x 3 planes: the pieces of -0.5|e|^2 sit in one column, three planes
+    (2500, 700, 8, torch.bfloat16, torch.float32),      # 1 x 3
+    (2500, 700, 10, torch.float32, torch.bfloat16),     # 3 x 1: the pieces are spread over three columns of plane 0
+    (4096, 16384 // 8, 8, torch.bfloat16, torch.bfloat16),
+    (1000, 300, 24, torch.float32, torch.float32),      # Dp = 32
+])
+def test_assign_l2_side_terms_folded_into_the_contraction(dev, N, K, D, x_dtype, e_dtype):
+    """vqb_fold_l2_side: with the L2 side terms written into the spare operand columns, the plain arg-max of the
+    contraction (side_mode 0) is the arg-min of the reference's cdist (vq/algorithms/vq/distances.py:28-35), for the
+    row pass (nearest code per token) and the column pass (nearest token per code), on both backends."""
+    from vector_quantization_b200 import functional as Fq
+    assert ops.can_fold_l2(D)
+    x, E = O.synthetic_latents(N, K, D, seed=21)
+    x, E = x.to(x_dtype), E.to(e_dtype)
+    q_ref, d = O.encode('L2', x.float(), E.float())
+    book = Fq.pack_codebook(E.to(dev).float() if e_dtype == torch.float32 else E.to(dev), 'L2')
+    assert book.folded == 'codes'
+    keys = Fq.nearest_code(x.to(dev), book, 'L2')
+    q, score = ops.unpack_keys(keys, want_score=True)
+    _check_indices(d, q_ref, q.cpu(), what='folded L2 row arg-min', squared=True)
+    # the folded score is -0.5 * |x - e|^2 up to the 1-column products (tokens role without its own term: + 0.5|x|^2)
+    want = -0.5 * (d[torch.arange(N), q.cpu()] ** 2) + 0.5 * x.float().pow(2).sum(1)
+    assert torch.allclose(score.cpu(), want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+    col = ops.unpack_keys(Fq.column_nearest(x.to(dev), book, 'L2')).cpu()
+    _check_indices(d.t().contiguous(), d.argmin(0), col, what='folded L2 column arg-min', squared=True)
+    # same answers as the un-folded side_mode-1 path and as the SIMT backend on the folded operands
+    a = ops.pack_rows(x.to(dev), planes=None)
+    b = ops.pack_rows(E.to(dev), want_half_sqnorm=True)
+    plain = ops.unpack_keys(ops.assign(a, b, ops.new_keys(N, dev), l2=True)).cpu()
+    _check_indices(d, plain, q.cpu(), what='folded vs side-term L2', squared=True)
+    ops.fold_l2_side(a, 'tokens')
+    ops.fold_l2_side(b, 'codes')
+    simt = ops.unpack_keys(ops.assign(a, b, ops.new_keys(N, dev), l2=True, backend=ops.BACKEND_SIMT)).cpu()
+    _check_indices(d, simt, q.cpu(), what='folded L2, SIMT backend', squared=True)
+
+
+def test_fold_l2_side_rejects_operands_without_spare_columns(dev):
+    x = torch.randn(64, 32, device=dev)
+    op = ops.pack_rows(x, want_half_sqnorm=True)
+    assert not ops.can_fold_l2(32)
+    with pytest.raises(Exception):
+        ops.fold_l2_side(op, 'codes')

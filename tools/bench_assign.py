@@ -53,6 +53,15 @@ for name, N, K, D, metric, dt, px, pe in cases:
     rec = dict(case=name, ms_median=round(med, 4), ms_best=round(best, 4), terms=terms,
                algo_tflops=round(flops / med / 1e9, 1), mma_tflops=round(flops * terms * (ops.operand_shape(1, D)[1] / D) / med / 1e9, 1),
                gelem_per_s=round(N * K / med / 1e6, 1), mtok_per_s=round(N / med / 1e3, 1))
+    if not cos and ops.can_fold_l2(D):
+        # the same assignment with the side terms folded into the spare operand columns (vqb_fold_l2_side)
+        af = ops.fold_l2_side(ops.pack_rows(x, planes=px), 'tokens')
+        bf = ops.fold_l2_side(ops.pack_rows(E, planes=pe, want_half_sqnorm=True), 'codes')
+        m_f, b_f = timeit(lambda: ops.assign(af, bf, keys, l2=True))
+        rec['folded_ms_median'], rec['folded_ms_best'] = round(m_f, 4), round(b_f, 4)
+        rec['fold_launch_ms'] = round(timeit(lambda: ops._call('vqb_fold_l2_side', ops._lib.load().vqb_fold_l2_side,
+                                                                 bf.planes.device, ops._p(bf.planes), bf.nplanes, bf.rows, bf.dim,
+                                                                 ops._p(bf.half_sqnorm), 1, ops._S), iters=5)[0], 4)
     pk = timeit(lambda: ops.pack_rows(E, normalize=cos, planes=None if pair else pe, want_half_sqnorm=not cos, fmt='f16x2' if pair else 'bf16'), iters=5)[0]
     rec['pack_codebook_ms'] = round(pk, 4)
     if pair and ops.operand_shape(1, D)[1] >= 128:

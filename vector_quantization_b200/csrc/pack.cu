@@ -301,6 +301,37 @@ __global__ void __launch_bounds__(256) row_inv_norm_kernel(const T* __restrict__
   }
 }
 
+// L2 distance with spare K padding: the side terms ride in the contraction instead of the epilogue (see
+// vqb_fold_l2_side in vqb200.h).  One thread per row; -h is split EXACTLY into three bf16 pieces (an fp32 value is
+// hi + mid + lo), kept in one column across three planes or, for fewer planes, in three columns of plane 0.
+__global__ void __launch_bounds__(256) fold_l2_side_kernel(__nv_bfloat16* __restrict__ planes, int n_planes, int64_t rows,
+                                                           int64_t rows_pad, int D, int Dp,
+                                                           const float* __restrict__ half_sqnorm, int role) {
+  pdl_wait();               // the planes and the side vector come from the preceding pack launch
+  pdl_launch_dependents();
+  const int own = role == 1 ? D : D + 3, partner = role == 1 ? D + 3 : D;
+  const __nv_bfloat16 one = __float2bfloat16(1.f);
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    __nv_bfloat16* row0 = planes + r * Dp;
+    for (int c = 0; c < 3; ++c) row0[partner + c] = one;
+    if (half_sqnorm == nullptr) continue;
+    const float v = -half_sqnorm[r];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);            // exact
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));   // exact: 24 = 3 x 8 significant bits
+    if (n_planes >= 3) {
+      row0[own] = hi;
+      row0[rows_pad * Dp + own] = mid;
+      row0[2 * rows_pad * Dp + own] = lo;
+    } else {
+      row0[own] = hi;
+      row0[own + 1] = mid;
+      row0[own + 2] = lo;
+    }
+  }
+}
+
 template <int G, typename F>
 static inline void launch_rows(int64_t rows, F&& f) {
   const int rows_per_block = 256 / G;
@@ -440,6 +471,24 @@ int vqb_l2norm_forward(const void* x, int x_dtype, int64_t rows, int D, void* y,
     else
       l2norm_fwd_kernel<float, __nv_bfloat16, G><<<blocks, 256, 0, st>>>((const float*)x, rows, D, (__nv_bfloat16*)y);
   }));
+  VQB_LAUNCH_OK();
+  return VQB_OK;
+}
+
+int vqb_fold_l2_side(void* planes, int n_planes, int64_t rows, int D, const float* half_sqnorm, int role, void* stream) {
+  VQB_REQUIRE(planes, "vqb_fold_l2_side: null pointer");
+  VQB_REQUIRE(n_planes >= 1 && n_planes <= 3, "vqb_fold_l2_side: exact bf16 planes only (1..3), got %d", n_planes);
+  VQB_REQUIRE(role == 0 || role == 1, "vqb_fold_l2_side: role must be 0 (tokens) or 1 (codes)");
+  VQB_REQUIRE(rows >= 0 && D >= 1, "vqb_fold_l2_side: bad shape rows=%lld D=%d", (long long)rows, D);
+  const int Dp = (int)vqb_operand_dp(D);
+  VQB_REQUIRE(Dp - D >= VQB_L2_FOLD_COLUMNS, "vqb_fold_l2_side: needs %d spare columns (D=%d, Dp=%d)", VQB_L2_FOLD_COLUMNS, D, Dp);
+  VQB_REQUIRE(role == 0 || half_sqnorm, "vqb_fold_l2_side: the codes role needs half_sqnorm");
+  if (rows == 0) return VQB_OK;
+  int64_t blocks = (rows + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  VQB_CUDA_OK(launch_pdl(fold_l2_side_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, (__nv_bfloat16*)planes, n_planes,
+                         rows, vqb_operand_rows_pad(rows), D, Dp, half_sqnorm, role));
   VQB_LAUNCH_OK();
   return VQB_OK;
 }

@@ -27,6 +27,7 @@ DEFAULT_PRECISION = 'fp32'
 # exceeds twice the operand error bound keep their arg-max, the others are re-run with both terms.  Results are
 # identical to the two-term contraction by construction.  VQB_CERTIFIED=0 disables it.
 import os as _os
+FOLD_L2 = _os.environ.get('VQB_FOLD_L2', '1') != '0'   # L2 side terms in the spare operand columns (needs Dp - D >= 6: D <= 10, 17..26, ...)
 CERTIFIED_MIN_DP = 128 if _os.environ.get('VQB_CERTIFIED', '1') != '0' else 1 << 30
 
 
@@ -99,10 +100,15 @@ def pack_codebook(W: torch.Tensor, metric: str, *, precision: str = DEFAULT_PREC
     cos = metric == 'Cosine'
     normalize = cos or writeback_normalized
     pair = cos and _pair_ok(W, normalize, precision, tokens)
-    return ops.pack_rows(W, normalize=normalize, planes=None if pair else _planes_for(W, normalize, precision),
+    book = ops.pack_rows(W, normalize=normalize, planes=None if pair else _planes_for(W, normalize, precision),
                          want_half_sqnorm=not cos, writeback=W if writeback_normalized else None,
                          reset_keys=reset_keys, fmt='f16x2' if pair else 'bf16', zero_fill=zero_fill,
                          want_lo_norm=pair and ops.operand_shape(1, W.shape[1])[1] >= CERTIFIED_MIN_DP)
+    if not cos and FOLD_L2 and ops.can_fold_l2(W.shape[1]):
+        # small-D L2 (LlamaGen's 16384 x 8): the -0.5|e|^2 term rides in the operand's spare columns and the kernel's
+        # epilogue is the plain arg-max of the cosine path (half the instructions per score)
+        ops.fold_l2_side(book, 'codes')
+    return book
 
 
 @torch.no_grad()
@@ -137,6 +143,8 @@ def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precisi
                 tokens = ops.pack_rows(x, normalize=norm, planes=_planes_for(x, norm, precision),
                                        reset_keys=None if keys_are_reset else keys)
                 keys_are_reset = True
+    if codebook.folded is not None and tokens.folded is None:
+        ops.fold_l2_side(tokens, 'tokens')      # the 1-columns that pick up the codes' -0.5|e|^2
     if not keys_are_reset:
         keys.fill_(-1)
     if codebook.lo_norm_max is not None and tokens.fmt == 'f16':
@@ -179,6 +187,8 @@ def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, preci
         else:
             b = ops.pack_rows(x, normalize=cos, planes=_planes_for(x, cos, precision), want_half_sqnorm=not cos)
             kw['l2'] = not cos
+            if codebook.folded is not None:
+                ops.fold_l2_side(b, 'tokens')   # here the tokens' -0.5|x|^2 is the term that varies along the reduced axis
     keys = ops.new_keys(codebook.rows, x.device)
     if rows is not None:
         code_list, count, compact = rows

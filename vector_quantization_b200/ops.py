@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import BACKEND_SIMT, BACKEND_TCGEN05, PLANES_F16, PLANES_F16X2, VQB_BF16, VQB_F32, FSQParams, check
 
 __all__ = [
-    'Operand', 'as_operand', 'pack_rows', 'assign', 'certify', 'cvq_needy_codes', 'gather_operand_rows', 'scatter_keys', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
+    'Operand', 'as_operand', 'pack_rows', 'fold_l2_side', 'can_fold_l2', 'assign', 'certify', 'cvq_needy_codes', 'gather_operand_rows', 'scatter_keys', 'row_inv_norm', 'new_keys', 'unpack_keys', 'keys_flip_sign', 'gather_ste_loss',
     'quantize_backward', 'l2norm_forward', 'l2norm_backward', 'scatter_stats', 'bincount_accumulate',
     'kmeans_ema_update', 'gather_rows_by_key', 'cvq_update', 'embedding_gather', 'fsq_params', 'fsq_forward', 'fsq_backward',
     'fsq_decode', 'transpose_last2', 'compact_tokens', 'distance_matrix', 'comm_kmeans_ema_update', 'comm_cvq_update',
@@ -95,6 +95,7 @@ class Operand:
     inv_norm: torch.Tensor | None = None  # fp32 [rows_pad] 1/|row| (per-column scale for raw-token column arg-min)
     lo_norm_max: torch.Tensor | None = None  # fp32 [1]: max_j |row_j - hi_j| of an 'f16x2' operand (one-term error bound)
     fmt: str = 'bf16'    # 'bf16': 1..3 bf16 planes | 'f16': one fp16 plane | 'f16x2': the fp16 (hi, lo * 2^11) pair
+    folded: str | None = None   # 'tokens' | 'codes': the L2 side terms live in the spare columns (fold_l2_side)
 
     @property
     def pair(self) -> bool:
@@ -153,6 +154,28 @@ def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None 
     return Operand(dst, rows, D, planes, h, fmt=fmt, lo_norm_max=lo)
 
 
+L2_FOLD_COLUMNS = 6
+
+
+def can_fold_l2(D: int) -> bool:
+    """True when the operand width of D leaves the spare zero columns the folded L2 side terms need."""
+    return operand_shape(1, D)[1] - D >= L2_FOLD_COLUMNS
+
+
+def fold_l2_side(op: Operand, role: str) -> Operand:
+    """vqb_fold_l2_side: write the L2 side terms into the spare columns of a packed exact-bf16 operand (in place).
+    role 'codes' needs op.half_sqnorm; role 'tokens' uses it when present (column arg-min) and 1-columns only
+    otherwise (row arg-min).  Both operands of an `assign(..., l2=True)` must be folded, with opposite roles; the
+    kernel then runs without its per-column side term."""
+    lib = _lib.load()
+    assert op.fmt == 'bf16' and op.plane_rows == 0 and op.folded is None and role in ('tokens', 'codes')
+    dev = _cuda(op.planes, op.half_sqnorm)
+    _call('vqb_fold_l2_side', lib.vqb_fold_l2_side, dev, _p(op.planes), op.nplanes, op.rows, op.dim, _p(op.half_sqnorm),
+          1 if role == 'codes' else 0, _S)
+    op.folded = role
+    return op
+
+
 def transpose_last2(src: torch.Tensor) -> torch.Tensor:
     """[B, R, C] -> [B, C, R] contiguous (vqb_transpose_last2): the caller's NCHW <-> token-major rearranges."""
     lib = _lib.load()
@@ -194,7 +217,11 @@ def assign(a: Operand, b: Operand, keys: torch.Tensor, *, l2: bool, index_offset
     assert second_keys is None or (second_keys.dtype == torch.int64 and second_keys.numel() >= a.rows)
     assert a.dim == b.dim and keys.dtype == torch.int64 and keys.numel() >= a.rows
     side, mode = None, 0
-    if l2:
+    assert (a.folded is None) == (b.folded is None) and (a.folded is None or a.folded != b.folded), \
+        'folded L2 operands come in (tokens, codes) pairs'
+    if l2 and b.folded is not None:
+        pass                       # the side terms are part of the contraction
+    elif l2:
         assert b.half_sqnorm is not None, 'L2 assignment needs the packed operand to carry half_sqnorm'
         side, mode = b.half_sqnorm, 1
     elif scale_columns:
@@ -252,7 +279,7 @@ def gather_operand_rows(src: Operand, row_list: torch.Tensor, count: torch.Tenso
     dst = torch.empty((src.nplanes, rows_pad, Dp), dtype=torch.bfloat16, device=src.planes.device)
     _call('vqb_gather_plane_rows', lib.vqb_gather_plane_rows, dev, _p(src.planes), src.nplanes, src_plane_rows, Dp,
           _p(row_list), _p(count), src.rows, _p(dst), rows_pad, _S)
-    out = Operand(dst, src.rows, src.dim, src.nplanes, None, fmt=src.fmt)
+    out = Operand(dst, src.rows, src.dim, src.nplanes, None, fmt=src.fmt, folded=src.folded)
     return out
 
 
