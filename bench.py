@@ -268,6 +268,9 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS) + ['cfg5'])
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-readback', default='result', choices=['result', 'all'],
+                    help="end-to-end leg: 'result' reads the step's results back to the host (loss + token ids); "
+                         "'all' also ships the bf16 token gradient, which in a training loop stays on the device")
     ap.add_argument('--breakdown', action='store_true',
                     help='also time CUDA graphs of step prefixes (encode only / + gather+loss / + backward)')
     args = ap.parse_args()
@@ -578,6 +581,8 @@ def main():
     for ev in ev_run + ev_out:
         ev.record(cur)
 
+    read_all = args.e2e_readback == 'all'
+
     def e2e_step(i):
         j = i % n_sets
         xi, gzi = sets[j]
@@ -598,7 +603,8 @@ def main():
                     out[name].record_stream(s_out)
             loss_h.copy_(out['loss'], non_blocking=True)
             quant_h.copy_(out['quant'], non_blocking=True)
-            gx_h.copy_(out['gx'], non_blocking=True)
+            if read_all:
+                gx_h.copy_(out['gx'], non_blocking=True)
             ev_out[j].record(s_out)
 
     for i in range(3):
@@ -617,7 +623,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t)
     h2d = xh.numel() * 2 + gh.numel() * 2
-    d2h = 4 + quant_h.numel() * 8 + gx_h.numel() * 2
+    d2h = 4 + quant_h.numel() * 8 + (gx_h.numel() * 2 if read_all else 0)
     clocks = sampler.stop()
 
     cpu_baseline = gpu_eager = None
@@ -651,8 +657,11 @@ def main():
             gpu_eager_baseline=gpu_eager, breakdown_ms=breakdown,
             e2e=dict(value=N * world / (e2e_ms * 1e-3), unit=unit, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, cpu_affinity=numa,
+                     readback=args.e2e_readback,
                      note='per step: bf16 tokens + bf16 upstream gradient host->device (widened to fp32 on the device), '
-                          'loss + int64 indices + bf16 token gradient device->host; three streams, PCIe-bound'),
+                          'loss + int64 token ids' + (' + bf16 token gradient' if read_all else '') + ' device->host '
+                          '(the token gradient and z stay on the device, as in a training loop, unless --e2e-readback all); '
+                          'three streams, PCIe-bound'),
             gpu_launches=launches_per_step * args.steps)))
     if world > 1:
         # graphs that captured NCCL collectives must be gone before the communicator is torn down; a watchdog
