@@ -9,9 +9,13 @@
 // K_virtual = n_terms * Dp.  Persistent CTAs own a contiguous range of (row-tile, code-tile) work
 // items so the grid is exactly one CTA per SM with balanced work.
 //
-// Warp roles (320 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// Warp roles (352 threads):  warp 0 = TMA producer (whole-tile mode: also fetches the next row tile's A planes a
+//                            row tile ahead and converts zero-copy bf16 tokens to fp16 in shared memory),
+//                            warp 1 = TMEM allocator + MMA issuer,
 //                            warps 2..9 = epilogue (warp%4 selects the TMEM lane quarter,
-//                            (warp-2)/4 the 128-column half of the 256-wide accumulator).
+//                            (warp-2)/4 the 128-column half of the 256-wide accumulator),
+//                            warp 10 = second MMA issuer (whole-tile mode: the issuers alternate tiles and
+//                            each owns one TMEM accumulator; idle in the k-blocked mode).
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -496,7 +500,8 @@ __device__ __forceinline__ void epilogue_loop(int warp, int lane, uint32_t tmem_
 // the kernel
 // ---------------------------------------------------------------------------------------------
 // WHOLE = true : one pipeline stage holds every operand plane of one (row tile, code tile) work item
-//                (Dp == BK <= 64): one barrier wait, all term MMAs back to back, two commits per tile.
+//                (Dp == BK <= 64): two barrier tests back to back, all term MMAs back to back, ONE commit per tile
+//                (the stage's `empty` barrier also tells the epilogue that the accumulator is complete).
 // WHOLE = false: classic k-blocked ring, one stage = one BK-wide slab of one plane pair (large D).
 // MMA issue sequence of one whole-K tile for a term table known at compile time (NT terms, bit t of SCALE set when
 // term t starts with the scale-input-d instruction).
