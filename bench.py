@@ -268,6 +268,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS) + ['cfg5'])
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-h2d-streams', type=int, default=1, choices=[1, 2],
+                    help='end-to-end leg: copy the tokens and the upstream gradient on one or on two copy streams')
     ap.add_argument('--e2e-readback', default='result', choices=['result', 'all'],
                     help="end-to-end leg: 'result' reads the step's results back to the host (loss + token ids); "
                          "'all' also ships the bf16 token gradient, which in a training loop stays on the device")
@@ -574,6 +576,8 @@ def main():
     # of step i-1 overlap the kernels of step i (two copy engines + SMs).  Every step still copies ITS inputs
     # from pinned host memory and reads ITS results back inside the timed region.
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    s_in2 = torch.cuda.Stream() if args.e2e_h2d_streams == 2 else s_in   # second DMA queue for the gradient
+    ev_in2 = [torch.cuda.Event() for _ in range(n_sets)]
     ev_in = [torch.cuda.Event() for _ in range(n_sets)]
     ev_run = [torch.cuda.Event() for _ in range(n_sets)]
     ev_out = [torch.cuda.Event() for _ in range(n_sets)]
@@ -589,10 +593,14 @@ def main():
         with torch.cuda.stream(s_in), torch.no_grad():
             s_in.wait_event(ev_run[j])            # the previous step that used input set j has consumed it
             xi.copy_(xh, non_blocking=True)
+            ev_in[j].record(s_in)
+        with torch.cuda.stream(s_in2), torch.no_grad():
+            s_in2.wait_event(ev_run[j])
             g_stage[i & 1].copy_(gh, non_blocking=True)
             gzi.copy_(g_stage[i & 1])             # bf16 -> fp32 widening on the device
-            ev_in[j].record(s_in)
+            ev_in2[j].record(s_in2)
         cur.wait_event(ev_in[j])
+        cur.wait_event(ev_in2[j])
         cur.wait_event(ev_out[j])                 # result buffers of graph j have been read back
         out = run(i)
         ev_run[j].record(cur)
