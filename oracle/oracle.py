@@ -26,7 +26,6 @@ All citations are `file:line` relative to /root/reference.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass, field
 from typing import Sequence
 

@@ -10,8 +10,7 @@ import ctypes
 import os
 import pathlib
 import subprocess
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_ubyte, c_uint,
-                    c_ulonglong, c_void_p)
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t, c_ubyte, c_void_p
 
 _HERE = pathlib.Path(__file__).resolve().parent
 # VQB200_LIB: developer override, e.g. to A/B two builds of the library on the same GPU box

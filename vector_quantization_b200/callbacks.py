@@ -19,7 +19,7 @@ import torch
 
 from . import functional as Fq
 from . import ops, parallel
-from .registry import AnchorRegistry, Config, VQITQuantizerCallbackRegistry, get_config
+from .registry import AnchorRegistry, Config, VQITQuantizerCallbackRegistry
 
 __all__ = ['BaseCallback', 'ComposedCallback', 'UpdateMixin', 'NormalizeCallback', 'LazyInitWeightsMixin',
            'VQKDCallback', 'VQGAN_VQKDCallback', 'CVQVAECallback', 'EMA']
