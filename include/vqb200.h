@@ -162,6 +162,11 @@ int vqb_scatter_keys(const unsigned long long* compact_keys, const int* row_list
 #define VQB_L2_FOLD_COLUMNS 6
 int vqb_fold_l2_side(void* planes, int n_planes /* 1..3 exact bf16 planes */, int64_t rows, int D,
                      const float* half_sqnorm, int role, void* stream);
+/* vqb_pack_rows with the fold fused into the pack launch (no second launch when D is a multiple of 8).
+ * fold_role 0: tokens without their own term (row arg-min), 1: codes, 2: tokens with their term (column arg-min). */
+int vqb_pack_rows_fold(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes /* 1..3 */,
+                       void* dst_planes, float* half_sqnorm, float* writeback_f32, unsigned long long* keys_to_reset,
+                       int64_t n_keys, void* zero_fill, int64_t zero_bytes, int fold_role, void* stream);
 
 /* out[r] = 1 / max(||x_r||, 1e-12), zero in the padding up to vqb_operand_rows_pad(rows): the side_mode-2 column
  * scale that lets the column arg-min of NearestAnchor use RAW (un-normalised, one exact bf16 plane) tokens. */

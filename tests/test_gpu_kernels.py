@@ -646,6 +646,11 @@ def test_assign_l2_side_terms_folded_into_the_contraction(dev, N, K, D, x_dtype,
     _check_indices(d, plain, q.cpu(), what='folded vs side-term L2', squared=True)
     ops.fold_l2_side(a, 'tokens')
     ops.fold_l2_side(b, 'codes')
+    # the fold fused into the pack launch (vqb_pack_rows_fold) writes the same planes as pack + vqb_fold_l2_side
+    assert torch.equal(ops.pack_rows(x.to(dev), planes=None, fold='tokens').planes, a.planes)
+    assert torch.equal(ops.pack_rows(E.to(dev), want_half_sqnorm=True, fold='codes').planes, b.planes)
+    with_h = ops.fold_l2_side(ops.pack_rows(x.to(dev), planes=None, want_half_sqnorm=True), 'tokens')
+    assert torch.equal(ops.pack_rows(x.to(dev), planes=None, want_half_sqnorm=True, fold='tokens+h').planes, with_h.planes)
     simt = ops.unpack_keys(ops.assign(a, b, ops.new_keys(N, dev), l2=True, backend=ops.BACKEND_SIMT)).cpu()
     _check_indices(d, simt, q.cpu(), what='folded L2, SIMT backend', squared=True)
 

@@ -59,6 +59,8 @@ SIGNATURES = {
                            c_int, c_int64, c_void_p, c_int, c_void_p]),
     'vqb_row_inv_norm': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'vqb_fold_l2_side': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    'vqb_pack_rows_fold': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                           c_void_p, c_int64, c_int, c_void_p]),
     'vqb_unpack_keys': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     'vqb_compact_tokens': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     'vqb_transpose_last2': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
     const T* __restrict__ src, int64_t rows, int64_t rows_pad, int D, int Dp, int normalize, int planes,
     __nv_bfloat16* __restrict__ dst, float* __restrict__ half_sqnorm, float* __restrict__ writeback,
     unsigned long long* __restrict__ keys, int64_t n_keys, uint4* __restrict__ zero_fill, int64_t n_zero16,
-    float* __restrict__ lo_norm_max) {
+    float* __restrict__ lo_norm_max, int fold_role) {
   pdl_wait();               // the source rows / the key buffer may still be in use by the preceding launch
   pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_keys; i += (int64_t)gridDim.x * blockDim.x)
@@ -156,14 +156,43 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
     float ss2 = 0.f, lo2 = 0.f;
 #pragma unroll
     for (int it = 0; it < NV; ++it) {
-      const int d0 = (it * G + lane) * 8;
       if (normalize) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[it][i] = __fdiv_rn(v[it][i], denom);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) ss2 = fmaf(v[it][i], v[it][i], ss2);
+    }
+    if (half_sqnorm || fold_role >= 0) ss2 = group_sum<G>(ss2);   // warp-uniform condition; the row's |.|^2
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int d0 = (it * G + lane) * 8;
       if (d0 < Dp) {
+        if (fold_role >= 0 && d0 == D && real) {
+          // vqb_fold_l2_side fused into the pack: the lane that owns the first padding chunk writes the folded L2 side
+          // terms instead of zeros (columns D..D+2: the codes' term / the tokens' ones, D+3..D+5 the other way round)
+          const int own = fold_role == 1 ? 0 : 3, partner = 3 - own;
+          const float hv = fold_role == 0 ? 0.f : -0.5f * ss2;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(hv);
+          const float r1 = hv - __bfloat162float(hi);
+          const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+          const __nv_bfloat16 piece[3] = {hi, mid, lo};
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            if (p < planes) {
+              uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+              __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&raw);
+              if (p == 0)
+                for (int c = 0; c < 3; ++c) e[partner + c] = __float2bfloat16(1.f);
+              if (planes >= 3) e[own] = piece[p];
+              else if (p == 0)
+                for (int c = 0; c < 3; ++c) e[own + c] = piece[c];
+              *reinterpret_cast<uint4*>(dst + ((int64_t)p * rows_pad + r) * Dp + d0) = raw;
+            }
+          }
+          continue;
+        }
         if (writeback && real && d0 < D) {
           *reinterpret_cast<float4*>(writeback + r * D + d0) = make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
           *reinterpret_cast<float4*>(writeback + r * D + d0 + 4) = make_float4(v[it][4], v[it][5], v[it][6], v[it][7]);
@@ -214,7 +243,6 @@ __global__ void __launch_bounds__(256) pack_rows_vec_kernel(
       }
     }
     if (half_sqnorm) {
-      ss2 = group_sum<G>(ss2);
       if (lane == 0) half_sqnorm[r] = real ? 0.5f * ss2 : INFINITY;
     }
     if (lo_norm_max) {
@@ -380,9 +408,9 @@ size_t vqb_operand_bytes(int64_t rows, int D, int planes) {
   return (size_t)plane_count(planes) * (size_t)vqb_operand_rows_pad(rows) * (size_t)vqb_operand_dp(D) * 2;
 }
 
-int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes,
+static int pack_rows_impl(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes,
                   void* dst_planes, float* half_sqnorm, float* writeback, unsigned long long* keys,
-                  int64_t n_keys, void* zero_fill, int64_t zero_bytes, float* lo_norm_max, void* stream) {
+                  int64_t n_keys, void* zero_fill, int64_t zero_bytes, float* lo_norm_max, int fold_role, void* stream) {
   VQB_REQUIRE(src && dst_planes, "vqb_pack_rows: null pointer");
   VQB_REQUIRE(zero_fill == nullptr || ((uintptr_t)zero_fill % 16 == 0 && zero_bytes % 16 == 0 && zero_bytes >= 0),
               "vqb_pack_rows: zero_fill must be 16-byte aligned and a multiple of 16 bytes");
@@ -412,11 +440,11 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
     if (gv == G_ && nv == NV_) {                                                                                     \
       if (src_dtype == VQB_F32)                                                                                      \
         launch_pdl(pack_rows_vec_kernel<float, G_, NV_>, blocks, 256, 0, st, (const float*)src, rows, rows_pad, D, Dp, \
-            normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz, lo_norm_max);        \
+            normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz, lo_norm_max, fold_role);        \
       else                                                                                                           \
         launch_pdl(pack_rows_vec_kernel<__nv_bfloat16, G_, NV_>, blocks, 256, 0, st, (const __nv_bfloat16*)src, rows, \
             rows_pad, D, Dp, normalize, planes, (__nv_bfloat16*)dst_planes, half_sqnorm, writeback, keys,            \
-            keys ? n_keys : 0, zf, nz, lo_norm_max);                                                                                      \
+            keys ? n_keys : 0, zf, nz, lo_norm_max, fold_role);                                                                           \
       VQB_LAUNCH_OK();                                                                                               \
       return VQB_OK;                                                                                                 \
     }
@@ -436,7 +464,35 @@ int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int norma
           half_sqnorm, writeback, keys, keys ? n_keys : 0, zf, nz, lo_norm_max);
   }));
   VQB_LAUNCH_OK();
+  if (fold_role >= 0) {   // rows that do not take the vector path: the fold runs as its own launch
+    VQB_REQUIRE(fold_role == 0 || half_sqnorm, "vqb_pack_rows_fold: this row width needs half_sqnorm for roles 1 and 2");
+    int64_t blocks = (rows + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    VQB_CUDA_OK(launch_pdl(fold_l2_side_kernel, (int)blocks, 256, 0, st, (__nv_bfloat16*)dst_planes, planes, rows, rows_pad, D,
+                           Dp, fold_role == 0 ? (const float*)nullptr : (const float*)half_sqnorm, fold_role == 1 ? 1 : 0));
+    VQB_LAUNCH_OK();
+  }
   return VQB_OK;
+}
+
+int vqb_pack_rows(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes,
+                  void* dst_planes, float* half_sqnorm, float* writeback, unsigned long long* keys,
+                  int64_t n_keys, void* zero_fill, int64_t zero_bytes, float* lo_norm_max, void* stream) {
+  return pack_rows_impl(src, src_dtype, rows, D, normalize, planes, dst_planes, half_sqnorm, writeback, keys, n_keys,
+                        zero_fill, zero_bytes, lo_norm_max, -1, stream);
+}
+
+int vqb_pack_rows_fold(const void* src, int src_dtype, int64_t rows, int D, int normalize, int planes,
+                       void* dst_planes, float* half_sqnorm, float* writeback, unsigned long long* keys,
+                       int64_t n_keys, void* zero_fill, int64_t zero_bytes, int fold_role, void* stream) {
+  VQB_REQUIRE(planes >= 1 && planes <= 3, "vqb_pack_rows_fold: exact bf16 planes only (1..3), got %d", planes);
+  VQB_REQUIRE(fold_role >= 0 && fold_role <= 2, "vqb_pack_rows_fold: fold_role must be 0, 1 or 2");
+  VQB_REQUIRE(D >= 1 && vqb_operand_dp(D) - D >= VQB_L2_FOLD_COLUMNS, "vqb_pack_rows_fold: needs %d spare columns (D=%d)",
+              VQB_L2_FOLD_COLUMNS, D);
+  return pack_rows_impl(src, src_dtype, rows, D, normalize, planes, dst_planes, half_sqnorm, writeback, keys, n_keys,
+                        zero_fill, zero_bytes, nullptr, fold_role, stream);
 }
 
 int vqb_row_inv_norm(const void* x, int x_dtype, int64_t rows, int D, int f16_rows, float* out, void* stream) {

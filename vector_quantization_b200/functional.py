@@ -100,15 +100,13 @@ def pack_codebook(W: torch.Tensor, metric: str, *, precision: str = DEFAULT_PREC
     cos = metric == 'Cosine'
     normalize = cos or writeback_normalized
     pair = cos and _pair_ok(W, normalize, precision, tokens)
-    book = ops.pack_rows(W, normalize=normalize, planes=None if pair else _planes_for(W, normalize, precision),
+    # small-D L2 (LlamaGen's 16384 x 8): the -0.5|e|^2 term rides in the operand's spare columns (written by the pack
+    # launch itself) and the kernel's epilogue is the plain arg-max of the cosine path (half the instructions per score)
+    fold = 'codes' if (not cos and FOLD_L2 and ops.can_fold_l2(W.shape[1])) else None
+    return ops.pack_rows(W, normalize=normalize, planes=None if pair else _planes_for(W, normalize, precision),
                          want_half_sqnorm=not cos, writeback=W if writeback_normalized else None,
                          reset_keys=reset_keys, fmt='f16x2' if pair else 'bf16', zero_fill=zero_fill,
-                         want_lo_norm=pair and ops.operand_shape(1, W.shape[1])[1] >= CERTIFIED_MIN_DP)
-    if not cos and FOLD_L2 and ops.can_fold_l2(W.shape[1]):
-        # small-D L2 (LlamaGen's 16384 x 8): the -0.5|e|^2 term rides in the operand's spare columns and the kernel's
-        # epilogue is the plain arg-max of the cosine path (half the instructions per score)
-        ops.fold_l2_side(book, 'codes')
-    return book
+                         want_lo_norm=pair and ops.operand_shape(1, W.shape[1])[1] >= CERTIFIED_MIN_DP, fold=fold)
 
 
 @torch.no_grad()
@@ -138,10 +136,11 @@ def nearest_code(x: torch.Tensor, codebook: ops.Operand, metric: str, *, precisi
                 keys_are_reset = True
         else:
             norm = normalize_tokens and not cos
-            tokens = None if norm else ops.as_operand(x)
+            tokens = None if (norm or codebook.folded is not None) else ops.as_operand(x)
             if tokens is None:
                 tokens = ops.pack_rows(x, normalize=norm, planes=_planes_for(x, norm, precision),
-                                       reset_keys=None if keys_are_reset else keys)
+                                       reset_keys=None if keys_are_reset else keys,
+                                       fold='tokens' if codebook.folded is not None else None)
                 keys_are_reset = True
     if codebook.folded is not None and tokens.folded is None:
         ops.fold_l2_side(tokens, 'tokens')      # the 1-columns that pick up the codes' -0.5|e|^2
@@ -185,10 +184,10 @@ def column_nearest(x: torch.Tensor, codebook: ops.Operand, metric: str, *, preci
             b.inv_norm = ops.row_inv_norm(x)
             kw['scale_columns'] = True
         else:
-            b = ops.pack_rows(x, normalize=cos, planes=_planes_for(x, cos, precision), want_half_sqnorm=not cos)
+            # folded codebook: here the tokens' -0.5|x|^2 is the term that varies along the reduced axis
+            b = ops.pack_rows(x, normalize=cos, planes=_planes_for(x, cos, precision), want_half_sqnorm=not cos,
+                              fold='tokens+h' if codebook.folded is not None else None)
             kw['l2'] = not cos
-            if codebook.folded is not None:
-                ops.fold_l2_side(b, 'tokens')   # here the tokens' -0.5|x|^2 is the term that varies along the reduced axis
     keys = ops.new_keys(codebook.rows, x.device)
     if rows is not None:
         code_list, count, compact = rows

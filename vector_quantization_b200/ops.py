@@ -114,7 +114,7 @@ def operand_shape(rows: int, D: int) -> tuple[int, int]:
 def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None = None,
               want_half_sqnorm: bool = False, writeback: torch.Tensor | None = None,
               reset_keys: torch.Tensor | None = None, fmt: str = 'bf16',
-              zero_fill: torch.Tensor | None = None, want_lo_norm: bool = False) -> Operand:
+              zero_fill: torch.Tensor | None = None, want_lo_norm: bool = False, fold: str | None = None) -> Operand:
     """fp32/bf16 rows -> operand planes (see vqb_pack_rows).
     fmt='bf16': exact bf16 planes; `planes=None` picks the exact representation (1 plane for un-normalised bf16
                 input, 3 planes otherwise).
@@ -148,6 +148,17 @@ def pack_rows(src: torch.Tensor, *, normalize: bool = False, planes: int | None 
     if writeback is not None:
         assert writeback.dtype == torch.float32 and writeback.shape == src.shape
     lo = torch.zeros((1,), dtype=torch.float32, device=src.device) if (want_lo_norm and fmt == 'f16x2') else None
+    if fold is not None:
+        # L2 side terms folded into the spare columns by the pack launch itself (vqb_pack_rows_fold): 'codes', 'tokens'
+        # (row arg-min: ones only) or 'tokens+h' (column arg-min: the tokens' own term as well)
+        assert fmt == 'bf16' and fold in ('codes', 'tokens', 'tokens+h')
+        role = {'tokens': 0, 'codes': 1, 'tokens+h': 2}[fold]
+        if role != 0 and h is None and D % 8 != 0:
+            h = torch.empty((rows_pad,), dtype=torch.float32, device=src.device)
+        _call('vqb_pack_rows', lib.vqb_pack_rows_fold, dev, _p(src), _dt(src), rows, D, int(normalize), code, _p(dst), _p(h),
+              _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _p(zero_fill), zero_bytes,
+              role, _S)
+        return Operand(dst, rows, D, planes, h, fmt=fmt, folded='codes' if role == 1 else 'tokens')
     _call('vqb_pack_rows', lib.vqb_pack_rows, dev, _p(src), _dt(src), rows, D, int(normalize), code, _p(dst), _p(h),
           _p(writeback), _p(reset_keys), reset_keys.numel() if reset_keys is not None else 0, _p(zero_fill), zero_bytes,
           _p(lo), _S)
