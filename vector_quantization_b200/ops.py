@@ -68,10 +68,17 @@ def _call(name: str, fn, dev: torch.device, *args) -> None:
     """One C-ABI launch on the current stream of `dev`, with `dev` as the current CUDA device for the duration of
     the call (the library launches on, and encodes TMA descriptors for, the current device)."""
     global LAUNCHES
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev)
-        args = tuple(c_void_p(stream.cuda_stream) if a is _S else a for a in args)
+    # (raw torch._C calls: the eager step is bound by host-side launch cost, and the `torch.cuda.device` context manager
+    # plus a `Stream` object per launch were a third of it - tools/profile_eager.py)
+    index = dev.index if dev.index is not None else torch._C._cuda_getDevice()
+    previous = torch._C._cuda_getDevice()
+    if previous != index:
+        torch._C._cuda_setDevice(index)
+    try:
+        raw_stream = c_void_p(torch._C._cuda_getCurrentRawStream(index))
+        args = tuple(raw_stream if a is _S else a for a in args)
         if PROFILE is not None:
+            stream = torch.cuda.current_stream(dev)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             status = fn(*args)
@@ -79,6 +86,9 @@ def _call(name: str, fn, dev: torch.device, *args) -> None:
             PROFILE.append((name, a, b))
         else:
             status = fn(*args)
+    finally:
+        if previous != index:
+            torch._C._cuda_setDevice(previous)
     LAUNCHES += 1
     check(status, name)
 
