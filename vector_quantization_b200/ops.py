@@ -50,7 +50,8 @@ def _cuda(*ts: torch.Tensor | None) -> torch.device:
 
 
 def _p(t: torch.Tensor | None):
-    return c_void_p(t.data_ptr()) if t is not None else None
+    """Device pointer as a plain int (ctypes converts ints and None for `c_void_p` parameters; no wrapper object)."""
+    return t.data_ptr() if t is not None else None
 
 
 class _StreamArg:
@@ -75,7 +76,7 @@ def _call(name: str, fn, dev: torch.device, *args) -> None:
     if previous != index:
         torch._C._cuda_setDevice(index)
     try:
-        raw_stream = c_void_p(torch._C._cuda_getCurrentRawStream(index))
+        raw_stream = torch._C._cuda_getCurrentRawStream(index)   # plain int: 0 (the default stream) converts to NULL
         args = tuple(raw_stream if a is _S else a for a in args)
         if PROFILE is not None:
             stream = torch.cuda.current_stream(dev)
